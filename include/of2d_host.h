@@ -1,0 +1,71 @@
+/*
+ * of2d_host.h -- C entry points of libof2d_host{32,64}.so, the C++ host layer that mirrors the
+ * reference's class API (ImageRegistration{OpticalFlow,Demons,Fluid}, Image, Motion, Kernel, ...)
+ * on top of include/of2d_cuda.h.  Built twice: host32 = float fields (the reference as written),
+ * host64 = double fields (fp64 mode).
+ *
+ * The reference's only foreign-function boundary is its MEX entry point
+ *     void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
+ * (WrapperOpticalFlow2d.cpp:18-20); both libraries export exactly that symbol with the same five
+ * call shapes (see opticalflow2d_b200/host/mex/WrapperOpticalFlow2d.cpp and INTEGRATION.md).  The
+ * functions below exist so that a process without an Octave interpreter (tests, bench.py, another
+ * FFI) can build the mxArray arguments, call mexFunction, and read back the control-flow trace the
+ * reference only prints.
+ */
+#ifndef OF2D_HOST_H
+#define OF2D_HOST_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OF2D_HOST_OK 0
+#define OF2D_HOST_EINVAL 2    /* std::invalid_argument escaped (reference: wrong nparams, dimension mismatch) */
+#define OF2D_HOST_ERUNTIME 3  /* std::runtime_error escaped (divide by zero, mexErrMsgTxt, CUDA failure) */
+#define OF2D_HOST_EOTHER 4
+
+int of2d_host_real_bits(void);                 /* 32 or 64 */
+const char *of2d_host_last_error(void);
+void of2d_host_capture_printf(int on);         /* collect mexPrintf output instead of dropping it */
+const char *of2d_host_printed(void);
+int of2d_host_set_strict(int strict);          /* 1: no FMA contraction anywhere (bit-exact parity mode) */
+int of2d_host_set_stream(void *cuda_stream);   /* run on the caller's cudaStream_t */
+int of2d_host_sync(void);
+unsigned long long of2d_host_launch_count(void);
+void of2d_host_shutdown(void);
+
+/* in-process mxArray (real double only), as the interpreter would provide */
+void *of2d_mx_create(int ndim, const size_t *dims);
+double *of2d_mx_data(void *mx);
+size_t of2d_mx_numel(void *mx);
+int of2d_mx_ndim(void *mx);
+size_t of2d_mx_dim(void *mx, int d);
+void of2d_mx_free(void *mx);
+
+/* mexFunction behind a C status: replaces Octave's `OpticalFlow2d(...)` dispatch (WrapperOpticalFlow2d.cpp:18-155) */
+int of2d_mex_call(int nlhs, void **plhs, int nrhs, void **prhs);
+
+/* the same classes without the MEX singleton: ImageRegistration ctor / set_*_image / estimate_motion /
+   copy_estimated_motion (src/ImageRegistration.h:14-29) */
+typedef struct of2d_session of2d_session;
+int of2d_session_create(int dimx, int dimy, int nscales, const int *niter, int nrefine, int reg, const double *regparams, int nparams, int verbose, of2d_session **out);
+void of2d_session_destroy(of2d_session *s);
+int of2d_session_set_images(of2d_session *s, const double *Iref, const double *Imov);
+int of2d_session_estimate(of2d_session *s);
+int of2d_session_get_motion(of2d_session *s, double *planar_out);      /* 2*N doubles: x plane, y plane */
+int of2d_session_get_motion_aos(of2d_session *s, void *out_real);       /* N {x,y} pairs in the field precision */
+int of2d_session_warp(of2d_session *s, const double *img, double *out);
+
+/* trace of the last estimate_motion(); s == NULL addresses the MEX singleton */
+int of2d_trace_num_levels(of2d_session *s);
+long of2d_trace_total_iterations(of2d_session *s);
+int of2d_trace_level_info(of2d_session *s, int level, int *scale, int *refine, int *iterations, int *nregrid);
+int of2d_trace_level_series(of2d_session *s, int level, int which, double *out, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,124 @@
+// ctx.cu -- context, memory and stream plumbing of libof2d_cuda.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_error[512] = "";
+
+void of2d_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+
+const char *of2d_last_error(void) { return g_error; }
+
+int of2d_device_count(int *count) {
+    *count = 0;
+    OF2D_CUDA_TRY(cudaGetDeviceCount(count));
+    return OF2D_SUCCESS;
+}
+
+int of2d_ctx_create(int device, of2d_ctx **out) {
+    *out = nullptr;
+    int n = 0;
+    OF2D_CUDA_TRY(cudaGetDeviceCount(&n));
+    if (n == 0 || device < 0 || device >= n) {
+        of2d_set_error("of2d_ctx_create: no usable CUDA device %d (count %d); this library has no CPU fallback", device, n);
+        return OF2D_ERR_CUDA;
+    }
+    OF2D_CUDA_TRY(cudaSetDevice(device));
+    of2d_ctx *c = new of2d_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    c->fast_math = true;
+    OF2D_CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    OF2D_CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    OF2D_CUDA_TRY(cudaMalloc(&c->d_partials, sizeof(double) * kMaxPartialBlocks * 4));
+    OF2D_CUDA_TRY(cudaMalloc(&c->d_status, sizeof(unsigned) * kMaxBatchStatus));
+    OF2D_CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(unsigned) * kMaxBatchStatus));
+    OF2D_CUDA_TRY(cudaHostAlloc(&c->h_mailbox, 4096, cudaHostAllocDefault));
+    OF2D_CUDA_TRY(cudaMalloc(&c->d_mailbox, 4096));
+    OF2D_CUDA_TRY(cudaMemset(c->d_mailbox, 0, 4096));
+    *out = c;
+    return OF2D_SUCCESS;
+}
+
+void of2d_ctx_destroy(of2d_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_partials);
+    cudaFree(c->d_status);
+    cudaFree(c->d_progress);
+    cudaFree(c->d_mailbox);
+    cudaFree(c->d_kernel);
+    cudaFreeHost(c->h_mailbox);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int of2d_ctx_set_stream(of2d_ctx *c, void *s) {
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return OF2D_SUCCESS;
+}
+void *of2d_ctx_get_stream(of2d_ctx *c) { return (void *)c->stream; }
+int of2d_ctx_sync(of2d_ctx *c) {
+    OF2D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return OF2D_SUCCESS;
+}
+int of2d_ctx_set_fast_math(of2d_ctx *c, int on) {
+    c->fast_math = on != 0;
+    return OF2D_SUCCESS;
+}
+uint64_t of2d_ctx_launch_count(of2d_ctx *c) { return c->launches; }
+
+int of2d_malloc(of2d_ctx *c, size_t bytes, void **p) {
+    *p = nullptr;
+    OF2D_CUDA_TRY(cudaSetDevice(c->device));
+    OF2D_CUDA_TRY(cudaMalloc(p, bytes ? bytes : 1));
+    return OF2D_SUCCESS;
+}
+int of2d_free(of2d_ctx *c, void *p) {
+    if (!p) return OF2D_SUCCESS;
+    OF2D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    OF2D_CUDA_TRY(cudaFree(p));
+    return OF2D_SUCCESS;
+}
+int of2d_host_alloc(size_t bytes, void **p) {
+    *p = nullptr;
+    OF2D_CUDA_TRY(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
+    return OF2D_SUCCESS;
+}
+int of2d_host_free(void *p) {
+    if (p) OF2D_CUDA_TRY(cudaFreeHost(p));
+    return OF2D_SUCCESS;
+}
+int of2d_memset(of2d_ctx *c, void *p, int byte, size_t bytes) {
+    OF2D_CUDA_TRY(cudaMemsetAsync(p, byte, bytes, c->stream));
+    return OF2D_SUCCESS;
+}
+int of2d_h2d(of2d_ctx *c, void *d, const void *h, size_t bytes) {
+    OF2D_CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+    return OF2D_SUCCESS;
+}
+int of2d_d2h(of2d_ctx *c, void *h, const void *d, size_t bytes) {
+    OF2D_CUDA_TRY(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+    OF2D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return OF2D_SUCCESS;
+}
+int of2d_d2h_async(of2d_ctx *c, void *h, const void *d, size_t bytes) {
+    OF2D_CUDA_TRY(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return OF2D_SUCCESS;
+}
+int of2d_d2d(of2d_ctx *c, void *dst, const void *src, size_t bytes) {
+    OF2D_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return OF2D_SUCCESS;
+}
+
+}  // extern "C"

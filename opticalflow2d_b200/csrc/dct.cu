@@ -1,0 +1,448 @@
+// dct.cu -- shared-memory DCT kernels that replace fftw in the curvature solver
+// (OpticalFlowCurvature.cpp:6-167; fftw_plan_r2r_2d REDFT10 / REDFT01, :52-55).
+//
+// Transform definitions (FFTW manual, unnormalised):
+//   REDFT10 (DCT-II):  Y_k = 2 sum_j X_j cos(pi (j+1/2) k / n)
+//   REDFT01 (DCT-III): Y_k = X_0 + 2 sum_{j>=1} X_j cos(pi j (k+1/2) / n)
+//
+// The x and y components of the motion field always travel together, so every line transform is
+// ONE complex FFT of z = a + i b (a = x component, b = y component):
+//   DCT-II  (Makhoul): v[m] = a[2m], v[n-1-m] = a[2m+1]; Z = FFT(v_a + i v_b);
+//                      V_a = (Z_k + conj Z_{n-k})/2, V_b = (Z_k - conj Z_{n-k})/(2i); A_k = 2 Re(V_a e^{-i pi k/2n})
+//   DCT-III          : h_j = (X_j - i X_{n-j}) e^{+i pi j/2n}, h_0 = X_0; t = n IFFT(h_a + i h_b);
+//                      a[2m] = Re t[m], a[2m+1] = Re t[n-1-m] (b from Im)
+// The forward FFT is an in-place radix-2 DIT fed in bit-reversed order by the (scattering) load; the
+// inverse is an in-place DIF whose bit-reversed output is undone by the (gathering) store, so no
+// separate permutation pass exists.
+//
+// One curvature iteration = three kernels (algorithmic traffic in DESIGN.md):
+//   P1 rows    : rhs = u - tau f (f = L-SSD force, fused)  -> DCT-II along x  -> spectrum
+//   P2 columns : DCT-II along y -> x 1/(1 + tau alpha lap^2) -> DCT-III along y (spectrum stays in smem)
+//   P3 rows    : DCT-III along x -> u' = rhs / (4 N)
+// Non-power-of-two lengths take a direct O(n^2) path (correct, not fast).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "device_math.cuh"
+
+namespace {
+
+template <class S> struct Cplx;
+template <> struct Cplx<float> { using type = float2; };
+template <> struct Cplx<double> { using type = double2; };
+template <class S> using cplx_t = typename Cplx<S>::type;
+
+template <class S> __device__ __forceinline__ cplx_t<S> cmul(cplx_t<S> a, cplx_t<S> b) {
+    cplx_t<S> r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+
+constexpr int FFT_THREADS = 256;
+
+struct LineTables {
+    const void *tw;    // e^{-2 pi i k / n}, k < n/2       (cplx<S>)
+    const void *q;     // e^{-i pi k / (2n)}, k < n        (cplx<S>)
+    const double *costab;  // cos(pi m / (2n)), m < 4n (direct path only)
+    int n, log2n, pow2;
+};
+
+// in-place radix-2 DIT, input in bit-reversed order, output natural. sign<0: forward.
+template <class S>
+__device__ void fft_dit(cplx_t<S> *x, int n, int log2n, const cplx_t<S> *__restrict__ tw, int sign) {
+    for (int s = 0; s < log2n; s++) {
+        const int half = 1 << s;
+        for (int b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
+            const int k = b & (half - 1);
+            const int i0 = ((b >> s) << (s + 1)) + k;
+            cplx_t<S> w = tw[k << (log2n - 1 - s)];
+            if (sign > 0) w.y = -w.y;
+            const cplx_t<S> a = x[i0], c = cmul<S>(w, x[i0 + half]);
+            cplx_t<S> p, m;
+            p.x = a.x + c.x; p.y = a.y + c.y; m.x = a.x - c.x; m.y = a.y - c.y;
+            x[i0] = p; x[i0 + half] = m;
+        }
+        __syncthreads();
+    }
+}
+// in-place radix-2 DIF, input natural, output in bit-reversed order.
+template <class S>
+__device__ void fft_dif(cplx_t<S> *x, int n, int log2n, const cplx_t<S> *__restrict__ tw, int sign) {
+    for (int s = log2n - 1; s >= 0; s--) {
+        const int half = 1 << s;
+        for (int b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
+            const int k = b & (half - 1);
+            const int i0 = ((b >> s) << (s + 1)) + k;
+            cplx_t<S> w = tw[k << (log2n - 1 - s)];
+            if (sign > 0) w.y = -w.y;
+            const cplx_t<S> a = x[i0], c = x[i0 + half];
+            cplx_t<S> p, m;
+            p.x = a.x + c.x; p.y = a.y + c.y; m.x = a.x - c.x; m.y = a.y - c.y;
+            x[i0] = p; x[i0 + half] = cmul<S>(w, m);
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ int bitrev(int i, int log2n) { return (int)(__brev((unsigned)i) >> (32 - log2n)); }
+// Makhoul reordering: natural position m -> FFT input position
+__device__ __forceinline__ int makhoul_pos(int m, int n) { return (m & 1) ? n - 1 - (m >> 1) : (m >> 1); }
+
+// smem slot where sample m of a line must be placed before dct2_line()
+template <class S>
+__device__ __forceinline__ int dct2_load_slot(int m, const LineTables &T) {
+    return T.pow2 ? bitrev(makhoul_pos(m, T.n), T.log2n) : m;
+}
+// smem slot where output sample m of dct3_line() is found
+template <class S>
+__device__ __forceinline__ int dct3_store_slot(int m, const LineTables &T) {
+    return T.pow2 ? bitrev(makhoul_pos(m, T.n), T.log2n) : m;
+}
+
+// DCT-II of the two real sequences packed in x (slots filled through dct2_load_slot); on return
+// x[k] = (A_k, B_k) in natural order. `tmp` is only used by the direct path.
+template <class S>
+__device__ void dct2_line(cplx_t<S> *x, cplx_t<S> *tmp, const LineTables &T) {
+    const int n = T.n;
+    if (T.pow2) {
+        fft_dit<S>(x, n, T.log2n, (const cplx_t<S> *)T.tw, -1);
+        const cplx_t<S> *q = (const cplx_t<S> *)T.q;
+        for (int k = threadIdx.x; k <= (n >> 1); k += blockDim.x) {
+            const int nk = (n - k) & (n - 1);
+            const cplx_t<S> zk = x[k], zn = x[nk];
+            // V_a = (Z_k + conj Z_nk)/2, V_b = (Z_k - conj Z_nk)/(2i)
+            {
+                const S var = (S)0.5 * (zk.x + zn.x), vai = (S)0.5 * (zk.y - zn.y);
+                const S vbr = (S)0.5 * (zk.y + zn.y), vbi = (S)-0.5 * (zk.x - zn.x);
+                const cplx_t<S> w = q[k];
+                cplx_t<S> o; o.x = (S)2 * (var * w.x - vai * w.y); o.y = (S)2 * (vbr * w.x - vbi * w.y);
+                x[k] = o;
+            }
+            if (nk != k) {
+                const S var = (S)0.5 * (zn.x + zk.x), vai = (S)0.5 * (zn.y - zk.y);
+                const S vbr = (S)0.5 * (zn.y + zk.y), vbi = (S)-0.5 * (zn.x - zk.x);
+                const cplx_t<S> w = q[nk];
+                cplx_t<S> o; o.x = (S)2 * (var * w.x - vai * w.y); o.y = (S)2 * (vbr * w.x - vbi * w.y);
+                x[nk] = o;
+            }
+        }
+        __syncthreads();
+    } else {
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            double sa = 0.0, sb = 0.0;
+            for (int j = 0; j < n; j++) {
+                const double c = T.costab[((long)(2 * j + 1) * k) % (4 * n)];
+                sa += (double)x[j].x * c; sb += (double)x[j].y * c;
+            }
+            cplx_t<S> o; o.x = (S)(2.0 * sa); o.y = (S)(2.0 * sb);
+            tmp[k] = o;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < n; k += blockDim.x) x[k] = tmp[k];
+        __syncthreads();
+    }
+}
+
+// DCT-III of x[k] = (A_k, B_k) (natural order); outputs are read through dct3_store_slot().
+template <class S>
+__device__ void dct3_line(cplx_t<S> *x, cplx_t<S> *tmp, const LineTables &T) {
+    const int n = T.n;
+    if (T.pow2) {
+        const cplx_t<S> *q = (const cplx_t<S> *)T.q;
+        for (int j = threadIdx.x; j <= (n >> 1); j += blockDim.x) {
+            if (j == 0) {
+                cplx_t<S> o; o.x = x[0].x; o.y = x[0].y;   // h_0 = X_0 for both sequences: z_0 = A_0 + i B_0
+                x[0] = o;
+                continue;
+            }
+            const int nj = n - j;
+            const cplx_t<S> Xj = x[j], Xn = x[nj];
+            {   // slot j: e^{+i pi j/2n} = conj(q[j])
+                const S cr = q[j].x, ci = -q[j].y;
+                const S har = Xj.x * cr + Xn.x * ci, hai = Xj.x * ci - Xn.x * cr;
+                const S hbr = Xj.y * cr + Xn.y * ci, hbi = Xj.y * ci - Xn.y * cr;
+                cplx_t<S> o; o.x = har - hbi; o.y = hai + hbr;
+                x[j] = o;
+            }
+            if (nj != j) {
+                const S cr = q[nj].x, ci = -q[nj].y;
+                const S har = Xn.x * cr + Xj.x * ci, hai = Xn.x * ci - Xj.x * cr;
+                const S hbr = Xn.y * cr + Xj.y * ci, hbi = Xn.y * ci - Xj.y * cr;
+                cplx_t<S> o; o.x = har - hbi; o.y = hai + hbr;
+                x[nj] = o;
+            }
+        }
+        __syncthreads();
+        fft_dif<S>(x, n, T.log2n, (const cplx_t<S> *)T.tw, +1);
+    } else {
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            double sa = 0.0, sb = 0.0;
+            for (int j = 1; j < n; j++) {
+                const double c = T.costab[((long)j * (2 * k + 1)) % (4 * n)];
+                sa += (double)x[j].x * c; sb += (double)x[j].y * c;
+            }
+            cplx_t<S> o; o.x = (S)((double)x[0].x + 2.0 * sa); o.y = (S)((double)x[0].y + 2.0 * sb);
+            tmp[k] = o;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < n; k += blockDim.x) x[k] = tmp[k];
+        __syncthreads();
+    }
+}
+
+// ---- P1: rows.  One CTA per row j: rhs = u - tau f, DCT-II along x, spectrum row out -----------------
+template <class R, class S>
+__global__ void __launch_bounds__(FFT_THREADS) k_curv_rows_fwd(int nx, int ny, const vec2_t<R> *__restrict__ u, const vec2_t<R> *__restrict__ gradI,
+                                                               const R *__restrict__ It, R tau, cplx_t<S> *__restrict__ spec, LineTables T) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx_t<S> *x = reinterpret_cast<cplx_t<S> *>(smem_raw);
+    cplx_t<S> *tmp = x + nx;
+    const int j = blockIdx.x;
+    const size_t row = (size_t)j * nx;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+        const vec2_t<R> uu = u[row + i];
+        const vec2_t<R> f = lssd_force<R>(gradI[row + i], It[row + i], uu);   // OpticalFlow.cpp:33
+        cplx_t<S> v;                                                          // OpticalFlowCurvature.cpp:90-91
+        v.x = (S)(uu.x - tau * f.x);
+        v.y = (S)(uu.y - tau * f.y);
+        x[dct2_load_slot<S>(i, T)] = v;
+    }
+    __syncthreads();
+    dct2_line<S>(x, tmp, T);
+    for (int p = threadIdx.x; p < nx; p += blockDim.x) spec[row + p] = x[p];
+}
+
+// ---- P2: columns.  One CTA per group of C adjacent columns p: DCT-II along y, eigenvalue, DCT-III ----
+template <class S>
+__global__ void __launch_bounds__(FFT_THREADS) k_curv_cols(int nx, int ny, int C, cplx_t<S> *__restrict__ spec, const double *__restrict__ cosx,
+                                                           const double *__restrict__ cosy, double tau_alpha, LineTables T) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx_t<S> *lines = reinterpret_cast<cplx_t<S> *>(smem_raw);   // [C][ny]
+    cplx_t<S> *tmp = lines + (size_t)C * ny;                      // [ny] (direct path only)
+    const int p0 = blockIdx.x * C;
+    const int nc = min(C, nx - p0);
+    for (int e = threadIdx.x; e < ny * nc; e += blockDim.x) {
+        const int jj = e / nc, c = e % nc;
+        lines[(size_t)c * ny + dct2_load_slot<S>(jj, T)] = spec[(size_t)jj * nx + p0 + c];
+    }
+    __syncthreads();
+    for (int c = 0; c < nc; c++) {
+        cplx_t<S> *x = lines + (size_t)c * ny;
+        dct2_line<S>(x, tmp, T);
+        const double cxp = cosx[p0 + c];
+        for (int qq = threadIdx.x; qq < ny; qq += blockDim.x) {   // OpticalFlowCurvature.cpp:24, :135-136
+            const double lap = -4 + cxp + cosy[qq];
+            const double eig = 1.0f / (1.0f + tau_alpha * (lap * lap));
+            cplx_t<S> v = x[qq];
+            v.x = (S)((double)v.x * eig); v.y = (S)((double)v.y * eig);
+            x[qq] = v;
+        }
+        __syncthreads();
+        dct3_line<S>(x, tmp, T);
+    }
+    for (int e = threadIdx.x; e < ny * nc; e += blockDim.x) {
+        const int jj = e / nc, c = e % nc;
+        spec[(size_t)jj * nx + p0 + c] = lines[(size_t)c * ny + dct3_store_slot<S>(jj, T)];
+    }
+}
+
+// ---- P3: rows.  DCT-III along x, u' = rhs / (4 N) (OpticalFlowCurvature.cpp:116-117) ----------------
+template <class R, class S>
+__global__ void __launch_bounds__(FFT_THREADS) k_curv_rows_inv(int nx, int ny, const cplx_t<S> *__restrict__ spec, vec2_t<R> *__restrict__ unew, R fourN,
+                                                               LineTables T) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx_t<S> *x = reinterpret_cast<cplx_t<S> *>(smem_raw);
+    cplx_t<S> *tmp = x + nx;
+    const int j = blockIdx.x;
+    const size_t row = (size_t)j * nx;
+    for (int p = threadIdx.x; p < nx; p += blockDim.x) x[p] = spec[row + p];
+    __syncthreads();
+    dct3_line<S>(x, tmp, T);
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+        const cplx_t<S> v = x[dct3_store_slot<S>(i, T)];
+        unew[row + i] = mk2<R>((R)v.x / fourN, (R)v.y / fourN);
+    }
+}
+
+// ---- stand-alone 2-D transform of a row-major n0 x n1 real array (one component; imaginary lane idle)
+template <class S>
+__global__ void __launch_bounds__(FFT_THREADS) k_dct_lines(int nlines, int n, size_t line_stride, size_t elem_stride, int kind, double *__restrict__ data,
+                                                           LineTables T) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx_t<S> *x = reinterpret_cast<cplx_t<S> *>(smem_raw);
+    cplx_t<S> *tmp = x + n;
+    double *line = data + (size_t)blockIdx.x * line_stride;
+    for (int m = threadIdx.x; m < n; m += blockDim.x) {
+        cplx_t<S> v; v.x = (S)line[(size_t)m * elem_stride]; v.y = (S)0;
+        x[kind == 2 ? dct2_load_slot<S>(m, T) : m] = v;
+    }
+    __syncthreads();
+    if (kind == 2) dct2_line<S>(x, tmp, T); else dct3_line<S>(x, tmp, T);
+    for (int m = threadIdx.x; m < n; m += blockDim.x)
+        line[(size_t)m * elem_stride] = (double)x[kind == 2 ? m : dct3_store_slot<S>(m, T)].x;
+}
+
+// ---- host-side tables ---------------------------------------------------------------------------
+const double kPi = 3.14159265358979323846264338327950288;
+
+template <class S>
+int build_tables(int n, LineTables *T, void **d_blob) {
+    memset(T, 0, sizeof(*T));
+    T->n = n;
+    T->pow2 = n >= 2 && (n & (n - 1)) == 0;
+    *d_blob = nullptr;
+    if (T->pow2) {
+        int l = 0;
+        while ((1 << l) < n) l++;
+        T->log2n = l;
+        const size_t ntw = n / 2, nq = n;
+        cplx_t<S> *h = (cplx_t<S> *)malloc(sizeof(cplx_t<S>) * (ntw + nq));
+        for (size_t k = 0; k < ntw; k++) { h[k].x = (S)cos(-2.0 * kPi * k / n); h[k].y = (S)sin(-2.0 * kPi * k / n); }
+        for (size_t k = 0; k < nq; k++) { h[ntw + k].x = (S)cos(-kPi * k / (2.0 * n)); h[ntw + k].y = (S)sin(-kPi * k / (2.0 * n)); }
+        cudaError_t e = cudaMalloc(d_blob, sizeof(cplx_t<S>) * (ntw + nq));
+        if (e == cudaSuccess) e = cudaMemcpy(*d_blob, h, sizeof(cplx_t<S>) * (ntw + nq), cudaMemcpyHostToDevice);
+        free(h);
+        if (e != cudaSuccess) { of2d_set_error("dct tables: %s", cudaGetErrorString(e)); return OF2D_ERR_CUDA; }
+        T->tw = *d_blob;
+        T->q = (const cplx_t<S> *)*d_blob + ntw;
+    } else {
+        double *h = (double *)malloc(sizeof(double) * 4 * (size_t)n);
+        for (int m = 0; m < 4 * n; m++) h[m] = cos(kPi * m / (2.0 * n));
+        cudaError_t e = cudaMalloc(d_blob, sizeof(double) * 4 * (size_t)n);
+        if (e == cudaSuccess) e = cudaMemcpy(*d_blob, h, sizeof(double) * 4 * (size_t)n, cudaMemcpyHostToDevice);
+        free(h);
+        if (e != cudaSuccess) { of2d_set_error("dct tables: %s", cudaGetErrorString(e)); return OF2D_ERR_CUDA; }
+        T->costab = (const double *)*d_blob;
+    }
+    return OF2D_SUCCESS;
+}
+
+constexpr size_t kMaxSmem = 227 * 1024;
+
+}  // namespace
+
+struct of2d_curvature_plan {
+    of2d_ctx *ctx;
+    int nx, ny, real_is_double, spec_is_double;
+    double tau, alpha, tau_alpha;
+    LineTables Tx, Ty;
+    void *blob_x, *blob_y;
+    double *d_cosx, *d_cosy;
+    void *d_spec;
+    int cols_per_cta;
+    size_t smem_rows, smem_cols;
+};
+
+namespace {
+
+template <class R, class S>
+int curvature_step_impl(of2d_curvature_plan *P, const R *u, R *unew, const R *gradI, const R *It) {
+    of2d_ctx *ctx = P->ctx;
+    const int nx = P->nx, ny = P->ny;
+    cplx_t<S> *spec = (cplx_t<S> *)P->d_spec;
+    static bool configured = false;
+    if (!configured) {
+        OF2D_CUDA_TRY(cudaFuncSetAttribute(k_curv_rows_fwd<R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        OF2D_CUDA_TRY(cudaFuncSetAttribute(k_curv_rows_inv<R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        OF2D_CUDA_TRY(cudaFuncSetAttribute(k_curv_cols<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        configured = true;
+    }
+    k_curv_rows_fwd<R, S><<<ny, FFT_THREADS, P->smem_rows, ctx->stream>>>(nx, ny, (const vec2_t<R> *)u, (const vec2_t<R> *)gradI, It, (R)P->tau, spec, P->Tx);
+    OF2D_LAUNCH_CHECK(ctx);
+    k_curv_cols<S><<<ceil_div(nx, P->cols_per_cta), FFT_THREADS, P->smem_cols, ctx->stream>>>(nx, ny, P->cols_per_cta, spec, P->d_cosx, P->d_cosy, P->tau_alpha, P->Ty);
+    OF2D_LAUNCH_CHECK(ctx);
+    const R fourN = (R)4.0f * (R)(unsigned)(nx * ny);
+    k_curv_rows_inv<R, S><<<ny, FFT_THREADS, P->smem_rows, ctx->stream>>>(nx, ny, spec, (vec2_t<R> *)unew, fourN, P->Tx);
+    OF2D_LAUNCH_CHECK(ctx);
+    return OF2D_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+int of2d_curvature_plan_create(of2d_ctx *ctx, int nx, int ny, double alpha, double tau, int real_is_double, of2d_curvature_plan **out) {
+    *out = nullptr;
+    OF2D_REQUIRE(nx > 0 && ny > 0, "bad dimensions");
+    of2d_curvature_plan *P = new of2d_curvature_plan();
+    memset(P, 0, sizeof(*P));
+    P->ctx = ctx; P->nx = nx; P->ny = ny; P->real_is_double = real_is_double; P->spec_is_double = 1;
+    P->alpha = alpha; P->tau = tau;
+    // the reference multiplies tau*alpha in `float` (fp32 build) before promoting (OpticalFlowCurvature.cpp:24)
+    P->tau_alpha = real_is_double ? tau * alpha : (double)((float)tau * (float)alpha);
+    int st = build_tables<double>(nx, &P->Tx, &P->blob_x);
+    if (st == OF2D_SUCCESS) st = build_tables<double>(ny, &P->Ty, &P->blob_y);
+    if (st != OF2D_SUCCESS) { of2d_curvature_plan_destroy(P); return st; }
+    // 2 cos(p PI / n) with the reference's truncated PI (OpticalFlowCurvature.cpp:4), evaluated by the host libm
+    const double REF_PI = 3.14159265;
+    double *hx = (double *)malloc(sizeof(double) * nx), *hy = (double *)malloc(sizeof(double) * ny);
+    for (int p = 0; p < nx; p++) hx[p] = 2 * cos((unsigned)p * REF_PI / (unsigned)nx);
+    for (int q = 0; q < ny; q++) hy[q] = 2 * cos((unsigned)q * REF_PI / (unsigned)ny);
+    cudaError_t e = cudaMalloc(&P->d_cosx, sizeof(double) * nx);
+    if (e == cudaSuccess) e = cudaMalloc(&P->d_cosy, sizeof(double) * ny);
+    if (e == cudaSuccess) e = cudaMemcpy(P->d_cosx, hx, sizeof(double) * nx, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(P->d_cosy, hy, sizeof(double) * ny, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&P->d_spec, sizeof(double2) * (size_t)nx * ny);
+    free(hx); free(hy);
+    if (e != cudaSuccess) {
+        of2d_set_error("curvature plan: %s", cudaGetErrorString(e));
+        of2d_curvature_plan_destroy(P);
+        return OF2D_ERR_CUDA;
+    }
+    const size_t cs = sizeof(double2);
+    P->smem_rows = cs * (size_t)nx * (P->Tx.pow2 ? 1 : 2);
+    const size_t per_col = cs * (size_t)ny, extra = P->Ty.pow2 ? 0 : per_col;
+    int C = 4;
+    while (C > 1 && per_col * C + extra > kMaxSmem) C >>= 1;
+    P->cols_per_cta = C;
+    P->smem_cols = per_col * C + extra;
+    if (P->smem_rows > kMaxSmem || P->smem_cols > kMaxSmem) {
+        of2d_set_error("curvature plan: a %d x %d line does not fit in shared memory", nx, ny);
+        of2d_curvature_plan_destroy(P);
+        return OF2D_ERR_UNSUPPORTED;
+    }
+    *out = P;
+    return OF2D_SUCCESS;
+}
+
+void of2d_curvature_plan_destroy(of2d_curvature_plan *P) {
+    if (!P) return;
+    cudaStreamSynchronize(P->ctx->stream);
+    cudaFree(P->blob_x); cudaFree(P->blob_y); cudaFree(P->d_cosx); cudaFree(P->d_cosy); cudaFree(P->d_spec);
+    delete P;
+}
+
+int of2d_curvature_step_f32(of2d_curvature_plan *P, const float *u, float *unew, const float *g, const float *It) {
+    OF2D_REQUIRE(!P->real_is_double, "plan was created for double fields");
+    OF2D_REQUIRE(u != unew, "curvature step is out of place");
+    return curvature_step_impl<float, double>(P, u, unew, g, It);
+}
+int of2d_curvature_step_f64(of2d_curvature_plan *P, const double *u, double *unew, const double *g, const double *It) {
+    OF2D_REQUIRE(P->real_is_double, "plan was created for float fields");
+    OF2D_REQUIRE(u != unew, "curvature step is out of place");
+    return curvature_step_impl<double, double>(P, u, unew, g, It);
+}
+
+int of2d_dct2d_f64(of2d_ctx *ctx, int n0, int n1, int kind, double *d) {
+    OF2D_REQUIRE(n0 > 0 && n1 > 0 && (kind == 2 || kind == 3), "bad arguments");
+    LineTables T0, T1;
+    void *b0 = nullptr, *b1 = nullptr;
+    int st = build_tables<double>(n0, &T0, &b0);
+    if (st == OF2D_SUCCESS) st = build_tables<double>(n1, &T1, &b1);
+    if (st == OF2D_SUCCESS) {
+        const size_t s1 = sizeof(double2) * (size_t)n1 * 2, s0 = sizeof(double2) * (size_t)n0 * 2;
+        if (s0 > kMaxSmem || s1 > kMaxSmem) { of2d_set_error("of2d_dct2d_f64: line too long for shared memory"); st = OF2D_ERR_UNSUPPORTED; }
+        else {
+            cudaFuncSetAttribute(k_dct_lines<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+            k_dct_lines<double><<<n0, FFT_THREADS, s1, ctx->stream>>>(n0, n1, (size_t)n1, 1, kind, d, T1);   // dimension 1 (contiguous)
+            ctx->launches++;
+            k_dct_lines<double><<<n1, FFT_THREADS, s0, ctx->stream>>>(n1, n0, 1, (size_t)n1, kind, d, T0);   // dimension 0 (stride n1)
+            ctx->launches++;
+            cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { of2d_set_error("of2d_dct2d_f64: %s", cudaGetErrorString(e)); st = OF2D_ERR_CUDA; }
+        }
+    }
+    cudaFree(b0); cudaFree(b1);
+    return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// device_math.cuh -- per-pixel device functions shared by the primitive and the fused solver
+// kernels.  Each one evaluates the reference's expression for a single pixel in the reference's
+// operation order (the library is built with -fmad=false), so fused kernels and stand-alone
+// primitives give identical bits.
+#pragma once
+
+#include "common.cuh"
+
+// ---- gradients.h:9-32 on a scalar image ----------------------------------------------------------
+template <class R>
+__device__ __forceinline__ R partial_x(const R *__restrict__ f, int idx, int i, int nx) {
+    if (i == 0) return f[idx + 1] - f[idx];
+    if (i == nx - 1) return f[idx] - f[idx - 1];
+    return (f[idx + 1] - f[idx - 1]) / (R)2.0f;
+}
+template <class R>
+__device__ __forceinline__ R partial_y(const R *__restrict__ f, int idx, int j, int nx, int ny) {
+    if (j == 0) return f[idx + nx] - f[idx];
+    if (j == ny - 1) return f[idx] - f[idx - nx];
+    return (f[idx + nx] - f[idx - nx]) / (R)2.0f;
+}
+// ---- the same templates on vector2d ----------------------------------------------------------------
+template <class R>
+__device__ __forceinline__ vec2_t<R> partial_x_v(const vec2_t<R> *__restrict__ f, int idx, int i, int nx) {
+    if (i == 0) { const vec2_t<R> a = f[idx + 1], b = f[idx]; return mk2<R>(a.x - b.x, a.y - b.y); }
+    if (i == nx - 1) { const vec2_t<R> a = f[idx], b = f[idx - 1]; return mk2<R>(a.x - b.x, a.y - b.y); }
+    const vec2_t<R> a = f[idx + 1], b = f[idx - 1];
+    return mk2<R>((a.x - b.x) / (R)2.0f, (a.y - b.y) / (R)2.0f);
+}
+template <class R>
+__device__ __forceinline__ vec2_t<R> partial_y_v(const vec2_t<R> *__restrict__ f, int idx, int j, int nx, int ny) {
+    if (j == 0) { const vec2_t<R> a = f[idx + nx], b = f[idx]; return mk2<R>(a.x - b.x, a.y - b.y); }
+    if (j == ny - 1) { const vec2_t<R> a = f[idx], b = f[idx - nx]; return mk2<R>(a.x - b.x, a.y - b.y); }
+    const vec2_t<R> a = f[idx + nx], b = f[idx - nx];
+    return mk2<R>((a.x - b.x) / (R)2.0f, (a.y - b.y) / (R)2.0f);
+}
+
+// ---- Image::jacobian, Image.cpp:205-214 ------------------------------------------------------------
+template <class R>
+__device__ __forceinline__ R jacobian_pixel(const vec2_t<R> *__restrict__ u, int idx, int i, int j, int nx, int ny) {
+    const vec2_t<R> dudx = partial_x_v<R>(u, idx, i, nx);
+    const vec2_t<R> dudy = partial_y_v<R>(u, idx, j, nx, ny);
+    return ((R)1.0f + dudx.x) * ((R)1.0f + dudy.y) - dudx.y * dudy.x;
+}
+
+// ---- bilinear sampling geometry shared by warp2d / accumulate (Image.cpp:144-151, Motion.cpp:137-144)
+template <class R>
+struct Bilin {
+    int idxO;
+    R fx, fy;
+    bool inside, hx, hy;
+};
+template <class R>
+__device__ __forceinline__ Bilin<R> bilin_setup(int i, int j, R ux, R uy, int nx, int ny) {
+    Bilin<R> b;
+    const R px = (R)i + ux; const int dx = (int)r_floor(px); b.fx = px - (R)dx;
+    const R py = (R)j + uy; const int dy = (int)r_floor(py); b.fy = py - (R)dy;
+    b.inside = !(dx < 0 || dx >= nx || dy < 0 || dy >= ny);
+    b.idxO = dx + dy * nx;
+    b.hx = dx < nx - 1;
+    b.hy = dy < ny - 1;
+    return b;
+}
+
+// Image::warp2d for one pixel; `keep` is the value the pixel has before the warp (Image.cpp:148-173)
+template <class R>
+__device__ __forceinline__ R warp_pixel(const R *__restrict__ src, int nx, int ny, int i, int j, vec2_t<R> u, R keep) {
+    const Bilin<R> b = bilin_setup<R>(i, j, u.x, u.y, nx, ny);
+    if (!b.inside) return keep;
+    const R one = (R)1;
+    R val = src[b.idxO] * (one - b.fx) * (one - b.fy);
+    R weight = (one - b.fx) * (one - b.fy);
+    if (b.hx) { val += src[b.idxO + 1] * b.fx * (one - b.fy); weight += b.fx * (one - b.fy); }
+    if (b.hy) { val += src[b.idxO + nx] * (one - b.fx) * b.fy; weight += (one - b.fx) * b.fy; }
+    if (b.hx && b.hy) { val += src[b.idxO + 1 + nx] * b.fx * b.fy; weight += b.fx * b.fy; }
+    return weight != 0 ? val / weight : keep;
+}
+
+// Motion::accumulate for one pixel: v + u o (id + v); `keep` = u at this pixel (Motion.cpp:141-169)
+template <class R>
+__device__ __forceinline__ vec2_t<R> compose_pixel(const vec2_t<R> *__restrict__ u, int nx, int ny, int i, int j, vec2_t<R> v, vec2_t<R> keep) {
+    const Bilin<R> b = bilin_setup<R>(i, j, v.x, v.y, nx, ny);
+    if (!b.inside) return keep;
+    const R one = (R)1;
+    vec2_t<R> s = u[b.idxO];
+    R vx = s.x * (one - b.fx) * (one - b.fy), vy = s.y * (one - b.fx) * (one - b.fy);
+    R weight = (one - b.fx) * (one - b.fy);
+    if (b.hx) { s = u[b.idxO + 1]; vx += s.x * b.fx * (one - b.fy); vy += s.y * b.fx * (one - b.fy); weight += b.fx * (one - b.fy); }
+    if (b.hy) { s = u[b.idxO + nx]; vx += s.x * (one - b.fx) * b.fy; vy += s.y * (one - b.fx) * b.fy; weight += (one - b.fx) * b.fy; }
+    if (b.hx && b.hy) { s = u[b.idxO + 1 + nx]; vx += s.x * b.fx * b.fy; vy += s.y * b.fx * b.fy; weight += b.fx * b.fy; }
+    if (weight != 0) return mk2<R>(v.x + vx / weight, v.y + vy / weight);
+    return v;
+}
+
+// ---- reductions' per-pixel terms --------------------------------------------------------------------
+// Motion::norm addend, Motion.cpp:45: sqrt(pow(x,2)+pow(y,2)) evaluated in double
+template <class R>
+__device__ __forceinline__ double vec_norm_d(vec2_t<R> v) {
+    const double x = (double)v.x, y = (double)v.y;
+    return sqrt(x * x + y * y);
+}
+// Motion::maxabs term, Motion.cpp:54: pow(y,2)+pow(y,2) (x is ignored), rounded to real
+template <class R>
+__device__ __forceinline__ R maxabs_term(vec2_t<R> v) {
+    const double y = (double)v.y;
+    return (R)(y * y + y * y);
+}
+
+// ---- OpticalFlow::get_force, OpticalFlow.cpp:33 -------------------------------------------------------
+template <class R>
+__device__ __forceinline__ vec2_t<R> lssd_force(vec2_t<R> dI, R It, vec2_t<R> u) {
+    const R s = It + u.x * dI.x + u.y * dI.y;
+    return mk2<R>(dI.x * s, dI.y * s);
+}

@@ -1,0 +1,228 @@
+// mex_harness.cpp -- in-process stand-in for the interpreter side of the MEX API plus the C entry
+// points declared in include/of2d_host.h.  Lets tests and bench.py drive mexFunction() and the C++
+// classes through ctypes exactly as Octave would, and read back what the reference only prints.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <mex.h>
+#include <of2d_host.h>
+
+#include <src/DeviceRuntime.h>
+#include <src/Image.h>
+#include <src/ImageRegistrationDemons.h>
+#include <src/ImageRegistrationFluid.h>
+#include <src/ImageRegistrationOpticalFlow.h>
+#include <src/Motion.h>
+
+struct mxArray_tag {
+    double* data;
+    mwSize ndim;
+    mwSize dims[4];
+    mwSize numel;
+};
+
+ImageRegistration* of2d_wrapper_registration();
+
+namespace {
+std::string g_error;
+std::string g_printed;
+bool g_capture = false;
+
+template <class F>
+int guarded(F&& body) {
+    try {
+        body();
+        return OF2D_HOST_OK;
+    } catch (const std::invalid_argument& e) {
+        g_error = e.what();
+        return OF2D_HOST_EINVAL;
+    } catch (const std::runtime_error& e) {
+        g_error = e.what();
+        return OF2D_HOST_ERUNTIME;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return OF2D_HOST_EOTHER;
+    }
+}
+
+const RegistrationTrace* trace_of(const ImageRegistration* r) { return r ? &r->get_trace() : nullptr; }
+
+int copy_out(const std::vector<double>& v, double* out, int cap) {
+    const int n = (int)v.size() < cap ? (int)v.size() : cap;
+    if (out && n > 0) memcpy(out, v.data(), sizeof(double) * (size_t)n);
+    return (int)v.size();
+}
+}  // namespace
+
+// ---- interpreter side of the MEX API -----------------------------------------------------------
+extern "C" {
+
+double* mxGetPr(const mxArray* a) { return a->data; }
+
+mxArray* mxCreateNumericArray(mwSize ndim, const mwSize* dims, mxClassID, mxComplexity) {
+    mxArray* a = new mxArray_tag();
+    a->ndim = ndim;
+    a->numel = 1;
+    for (int d = 0; d < 4; d++) a->dims[d] = 1;
+    for (mwSize d = 0; d < ndim && d < 4; d++) { a->dims[d] = dims[d]; a->numel *= dims[d]; }
+    a->data = static_cast<double*>(calloc(a->numel ? a->numel : 1, sizeof(double)));
+    return a;
+}
+
+void mxDestroyArray(mxArray* a) {
+    if (!a) return;
+    free(a->data);
+    delete a;
+}
+
+int mexPrintf(const char* fmt, ...) {
+    if (!g_capture) return 0;
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    const int n = vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (g_printed.size() < (1u << 22)) g_printed += buf;
+    return n;
+}
+
+void mexErrMsgTxt(const char* msg) { throw std::runtime_error(std::string("mexErrMsgTxt: ") + msg); }
+
+// ---- include/of2d_host.h -------------------------------------------------------------------------
+int of2d_host_real_bits(void) { return (int)sizeof(of2d_real) * 8; }
+const char* of2d_host_last_error(void) { return g_error.c_str(); }
+void of2d_host_capture_printf(int on) { g_capture = on != 0; g_printed.clear(); }
+const char* of2d_host_printed(void) { return g_printed.c_str(); }
+int of2d_host_set_strict(int strict) {
+    return guarded([&] { of2d::check(of2d_ctx_set_fast_math(of2d::context(), strict ? 0 : 1)); });
+}
+int of2d_host_set_stream(void* cuda_stream) {
+    return guarded([&] { of2d::check(of2d_ctx_set_stream(of2d::context(), cuda_stream)); });
+}
+int of2d_host_sync(void) {
+    return guarded([&] { of2d::check(of2d_ctx_sync(of2d::context())); });
+}
+unsigned long long of2d_host_launch_count(void) {
+    unsigned long long n = 0;
+    guarded([&] { n = of2d_ctx_launch_count(of2d::context()); });
+    return n;
+}
+void of2d_host_shutdown(void) { of2d::release_context(); }
+
+void* of2d_mx_create(int ndim, const size_t* dims) { return mxCreateNumericArray((mwSize)ndim, dims, mxDOUBLE_CLASS, mxREAL); }
+double* of2d_mx_data(void* mx) { return static_cast<mxArray*>(mx)->data; }
+size_t of2d_mx_numel(void* mx) { return static_cast<mxArray*>(mx)->numel; }
+int of2d_mx_ndim(void* mx) { return (int)static_cast<mxArray*>(mx)->ndim; }
+size_t of2d_mx_dim(void* mx, int d) { return static_cast<mxArray*>(mx)->dims[d]; }
+void of2d_mx_free(void* mx) { mxDestroyArray(static_cast<mxArray*>(mx)); }
+
+int of2d_mex_call(int nlhs, void** plhs, int nrhs, void** prhs) {
+    return guarded([&] { mexFunction(nlhs, reinterpret_cast<mxArray**>(plhs), nrhs, const_cast<const mxArray**>(reinterpret_cast<mxArray**>(prhs))); });
+}
+
+// ---- session API: the C++ classes without the singleton ---------------------------------------------
+struct of2d_session {
+    std::unique_ptr<ImageRegistration> reg;
+    dim grid;
+};
+
+int of2d_session_create(int dimx, int dimy, int nscales, const int* niter, int nrefine, int reg, const double* regparams, int nparams, int verbose,
+                        of2d_session** out) {
+    *out = nullptr;
+    return guarded([&] {
+        std::vector<of2d_real> p((size_t)(nparams > 0 ? nparams : 1));
+        for (int k = 0; k < nparams; k++) p[(size_t)k] = (of2d_real)regparams[k];
+        const dim grid((unsigned int)dimx, (unsigned int)dimy);
+        const Regularisation r = static_cast<Regularisation>(reg);
+        const Verbose v = static_cast<Verbose>(verbose);
+        std::unique_ptr<of2d_session> s(new of2d_session());
+        s->grid = grid;
+        if (reg >= 0 && reg <= 2) s->reg.reset(new ImageRegistrationOpticalFlow(grid, nscales, niter, nrefine, r, p.data(), (unsigned)nparams, v));
+        else if (reg == 3 || reg == 4) s->reg.reset(new ImageRegistrationDemons(grid, nscales, niter, nrefine, r, p.data(), (unsigned)nparams, v));
+        else if (reg == 5) s->reg.reset(new ImageRegistrationFluid(grid, nscales, niter, nrefine, r, p.data(), (unsigned)nparams, v));
+        else mexErrMsgTxt("Error: invalid regularisation given\n");
+        *out = s.release();
+    });
+}
+void of2d_session_destroy(of2d_session* s) { delete s; }
+
+int of2d_session_set_images(of2d_session* s, const double* Iref, const double* Imov) {
+    return guarded([&] {
+        Image r(s->grid), m(s->grid);
+        r.set_image(Iref);
+        s->reg->set_reference_image(r);
+        m.set_image(Imov);
+        s->reg->set_moving_image(m);
+    });
+}
+int of2d_session_estimate(of2d_session* s) {
+    return guarded([&] { s->reg->estimate_motion(); });
+}
+int of2d_session_get_motion(of2d_session* s, double* planar_out) {
+    return guarded([&] {
+        Motion m(s->grid);
+        s->reg->copy_estimated_motion(m);
+        m.copy_motion_to_input(planar_out);
+    });
+}
+int of2d_session_get_motion_aos(of2d_session* s, void* out_real) {
+    return guarded([&] {
+        const Motion* m = s->reg->get_estimated_motion();
+        memcpy(out_real, m->get_motion(), sizeof(vector2d) * m->get_size());
+    });
+}
+int of2d_session_warp(of2d_session* s, const double* img, double* out) {
+    return guarded([&] {
+        Image m(s->grid);
+        m.set_image(img);
+        m.warp2d(*s->reg->get_estimated_motion());
+        m.copy_image_to_input(out);
+    });
+}
+
+// ---- trace access: `s` may be NULL to address the MEX singleton -------------------------------------
+static const RegistrationTrace* pick_trace(of2d_session* s) { return trace_of(s ? s->reg.get() : of2d_wrapper_registration()); }
+
+int of2d_trace_num_levels(of2d_session* s) {
+    const RegistrationTrace* t = pick_trace(s);
+    return t ? (int)t->levels.size() : 0;
+}
+long of2d_trace_total_iterations(of2d_session* s) {
+    const RegistrationTrace* t = pick_trace(s);
+    return t ? t->total_iterations() : 0;
+}
+int of2d_trace_level_info(of2d_session* s, int level, int* scale, int* refine, int* iterations, int* nregrid) {
+    const RegistrationTrace* t = pick_trace(s);
+    if (!t || level < 0 || level >= (int)t->levels.size()) return OF2D_HOST_EINVAL;
+    const RegistrationTrace::Level& l = t->levels[(size_t)level];
+    if (scale) *scale = l.scale;
+    if (refine) *refine = l.refine;
+    if (iterations) *iterations = l.iterations;
+    if (nregrid) *nregrid = (int)l.regrid_iteration.size();
+    return OF2D_HOST_OK;
+}
+/* which: 0 error, 1 regrid iteration, 2 regrid min-Jacobian, 3 fluid maxabs, 4 fluid dt; returns the full length */
+int of2d_trace_level_series(of2d_session* s, int level, int which, double* out, int cap) {
+    const RegistrationTrace* t = pick_trace(s);
+    if (!t || level < 0 || level >= (int)t->levels.size()) return 0;
+    const RegistrationTrace::Level& l = t->levels[(size_t)level];
+    switch (which) {
+        case 0: return copy_out(l.error, out, cap);
+        case 1: {
+            std::vector<double> v(l.regrid_iteration.begin(), l.regrid_iteration.end());
+            return copy_out(v, out, cap);
+        }
+        case 2: return copy_out(l.regrid_minjac, out, cap);
+        case 3: return copy_out(l.fluid_maxabs, out, cap);
+        case 4: return copy_out(l.fluid_dt, out, cap);
+    }
+    return 0;
+}
+
+}  // extern "C"
