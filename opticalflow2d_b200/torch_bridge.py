@@ -56,6 +56,10 @@ class Device:
         if isinstance(a, np.ndarray):
             assert a.flags["C_CONTIGUOUS"]
             return a.ctypes.data_as(C.c_void_p)
+        if isinstance(a, np.floating):
+            return float(a)
+        if isinstance(a, np.integer):
+            return int(a)
         return a
 
     def call(self, name: str, dtype, *args):
