@@ -44,8 +44,11 @@ typedef struct of2d_ctx of2d_ctx;
 int of2d_device_count(int *count);
 int of2d_ctx_create(int device, of2d_ctx **out);
 void of2d_ctx_destroy(of2d_ctx *ctx);
-/* run on an externally owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL restores the ctx's own */
+/* run on an externally owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); a NULL handle is the
+   legacy default stream, exactly as in the CUDA runtime */
 int of2d_ctx_set_stream(of2d_ctx *ctx, void *cuda_stream);
+/* back to the context's own non-blocking stream (the state after of2d_ctx_create) */
+int of2d_ctx_use_own_stream(of2d_ctx *ctx);
 void *of2d_ctx_get_stream(of2d_ctx *ctx);
 int of2d_ctx_sync(of2d_ctx *ctx);
 /* 1: FMA contraction allowed in the flop-heavy kernels (default); 0: reproduce the reference's

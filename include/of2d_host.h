@@ -31,7 +31,8 @@ const char *of2d_host_last_error(void);
 void of2d_host_capture_printf(int on);         /* collect mexPrintf output instead of dropping it */
 const char *of2d_host_printed(void);
 int of2d_host_set_strict(int strict);          /* 1: no FMA contraction anywhere (bit-exact parity mode) */
-int of2d_host_set_stream(void *cuda_stream);   /* run on the caller's cudaStream_t */
+int of2d_host_set_stream(void *cuda_stream);   /* run on the caller's cudaStream_t (NULL = legacy default stream) */
+int of2d_host_use_own_stream(void);
 int of2d_host_sync(void);
 unsigned long long of2d_host_launch_count(void);
 void of2d_host_shutdown(void);

@@ -64,7 +64,11 @@ void of2d_ctx_destroy(of2d_ctx *c) {
 }
 
 int of2d_ctx_set_stream(of2d_ctx *c, void *s) {
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    c->stream = (cudaStream_t)s;
+    return OF2D_SUCCESS;
+}
+int of2d_ctx_use_own_stream(of2d_ctx *c) {
+    c->stream = c->own_stream;
     return OF2D_SUCCESS;
 }
 void *of2d_ctx_get_stream(of2d_ctx *c) { return (void *)c->stream; }

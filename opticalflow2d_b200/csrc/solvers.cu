@@ -346,16 +346,17 @@ int sor_sweep_impl(of2d_ctx *ctx, int nx, int ny, int batch, R *x, const R *ufor
         ctx->progress_epoch = 0;
         OF2D_CUDA_TRY(cudaMemsetAsync(ctx->d_progress, 0, sizeof(unsigned) * ntasks, ctx->stream));
     }
-    // Counters are monotone across sweeps: every launch gets a fresh window [base, base + ny + 2) above
-    // everything published before, so no reset is needed between launches (only on wrap-around).
+    // Counters are monotone across sweeps: every launch gets a fresh window [base, base + ny + 2) strictly
+    // above everything published before (whatever the previous grid size was), so no reset is needed
+    // between launches -- only on wrap-around.
     const unsigned span = (unsigned)ny + 2u;
     if ((uint64_t)ctx->progress_epoch + 2ull * span >= 0x7fffffffull) {
         OF2D_CUDA_TRY(cudaMemsetAsync(ctx->d_progress, 0, sizeof(unsigned) * ctx->progress_cap, ctx->stream));
         ctx->progress_epoch = 0;
     }
-    ctx->progress_epoch += span;
     A.progress = ctx->d_progress;
-    A.base = ctx->progress_epoch;
+    A.base = ctx->progress_epoch + 1;
+    ctx->progress_epoch += span;
 
     const size_t smem = sizeof(vec2_t<R>) * (size_t)SOR_RING * (SOR_PITCH + 32);
     static bool configured[2][64] = {};

@@ -105,6 +105,9 @@ int of2d_host_set_strict(int strict) {
 int of2d_host_set_stream(void* cuda_stream) {
     return guarded([&] { of2d::check(of2d_ctx_set_stream(of2d::context(), cuda_stream)); });
 }
+int of2d_host_use_own_stream(void) {
+    return guarded([&] { of2d::check(of2d_ctx_use_own_stream(of2d::context())); });
+}
 int of2d_host_sync(void) {
     return guarded([&] { of2d::check(of2d_ctx_sync(of2d::context())); });
 }
