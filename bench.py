@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- OpticalFlow2d registration-solve benchmark (B200, one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size 2048]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json metric "Mpixel.iter/s ... per method at 2048^2"): one STEP runs the complete
+`estimate_motion()` of every registration method (Diffusion/Horn-Schunck, Curvature, Elastic, Thirion
+Demons, Diffeomorphic Demons, Fluid) on a synthetic 2048x2048 lattice pair, fp32,
+nscales=0, nrefine=1, iteration caps NITER below, cold start.  value = sum(pixels x iterations
+executed) / sum(device time); `methods` carries the per-method numbers.  N > 1: every rank runs the
+same step on its own pair (weak scaling, no collective in the solve); value = sum over ranks / max time.
+
+`value`  : images resident in HBM, CUDA-event time around estimate_motion() only.
+`e2e`    : the same step through the C-ABI session (include/of2d_host.h) with HOST double buffers:
+           H2D of both images, estimate, D2H of the planar double motion inside the timed region.
+`roofline`: the dominant kernel of the step, timed alone on L2-flushed 2048^2 inputs.
+`cpu_baseline` / `--impl reference`: the reference's own sources (oracle/_ref, compiled unchanged)
+           timed on the host cores on a bounded sample (few iterations per method).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METHODS = ["diffusion", "curvature", "elastic", "thirion", "diffeomorphic", "fluid"]
+REG = {"diffusion": 0, "curvature": 1, "elastic": 2, "thirion": 3, "diffeomorphic": 4, "fluid": 5}
+# SURVEY.md 8(d) parameters
+PARAMS = {
+    "diffusion": [0.5],
+    "curvature": [0.25, 1.0],
+    "elastic": [1.0, 0.25],
+    "thirion": [1.0, 0.25, 1.5, 1.5, 5, 0],
+    "diffeomorphic": [1.0, 2.0, 1.5, 1.5, 5],
+    "fluid": [0.1, 0.0],
+}
+NITER = {"diffusion": 50, "curvature": 50, "elastic": 50, "thirion": 50, "diffeomorphic": 50, "fluid": 100}
+SIGMA_B = {"fluid": 6.0}
+# algorithmic bytes per pixel per iteration, fp32 (SURVEY.md 8d / DESIGN.md)
+BYTES_PER_PX_ITER = {"diffusion": 28, "curvature": 92, "elastic": 28, "thirion": 48, "diffeomorphic": 48, "fluid": 60}
+
+
+def make_inputs(method: str, size: int):
+    from opticalflow2d_b200 import synthetic as S
+    return S.make_pair(size, size, kind="lattice", shift=(1.5, -0.75), smooth=False, sigma_b=SIGMA_B.get(method, 8.0))
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the compiled reference on host cores, bounded sample
+# --------------------------------------------------------------------------------------------------
+def _cpu_one(args):
+    method, size, niter = args
+    from oracle import refapi
+    kind = "ref" if refapi.available("ref", 32) else "oracle"
+    lib = refapi.get(kind, 32)
+    R, T = make_inputs(method, size)
+    t0 = time.perf_counter()
+    out = lib.register(R, T, REG[method], PARAMS[method], [niter], nscales=0, nrefine=1, verbose=1)
+    dt = time.perf_counter() - t0
+    return method, len(out["err"]), dt, kind
+
+
+def cpu_reference_step(size: int, niter: int, workers: int):
+    """One bounded CPU sample: every method for `niter` iterations (the reference always runs >= 3).
+    The reference is single-threaded per pair; the six methods run in `workers` processes."""
+    import multiprocessing as mp
+    jobs = [(m, size, niter) for m in METHODS]
+    t0 = time.perf_counter()
+    if workers > 1:
+        with mp.get_context("fork").Pool(workers) as pool:
+            res = pool.map(_cpu_one, jobs)
+    else:
+        res = [_cpu_one(j) for j in jobs]
+    wall = time.perf_counter() - t0
+    pxit = sum(r[1] for r in res) * size * size
+    return {"wall_s": wall, "pixel_iters": pxit, "per_method": {r[0]: {"iterations": r[1], "seconds": r[2]} for r in res}, "kind": res[0][3]}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ncpu = os.cpu_count() or 1
+    workers = max(1, min(len(METHODS), ncpu))
+    niter = 3
+    for _ in range(args.warmup if args.warmup < 2 else 1):   # one warm-up pass is enough to page the library in
+        cpu_reference_step(min(args.size, 512), niter, workers)
+    tot_t, tot_px, last = 0.0, 0, None
+    for _ in range(args.steps):
+        last = cpu_reference_step(args.size, niter, workers)
+        tot_t += last["wall_s"]; tot_px += last["pixel_iters"]
+    value = tot_px / tot_t / 1e6
+    sample = f"{niter} iterations of each of the 6 methods at {args.size}^2 per step (reference always runs >= 3), {workers} processes"
+    line = {
+        "impl": "reference", "metric": "Mpixel*iter/s (6 registration methods, aggregate)", "value": value, "unit": "Mpixel*iter/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.size),
+        "cpu_baseline": {"value": value, "unit": "Mpixel*iter/s", "cores": workers, "kind": "reference" if last["kind"] == "ref" else "port",
+                         "sample": sample, "curvature_dct": "stand-in O(N log N) DCT (fftw3 not installed offline)"},
+        "e2e": {"value": value, "unit": "Mpixel*iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "methods": {m: {"mpix_iter_s": args.size * args.size * v["iterations"] / v["seconds"] / 1e6} for m, v in last["per_method"].items()},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(size: int) -> dict:
+    return {"workload": f"c4_all_methods_{size}x{size}_f32", "size": [size, size], "nscales": 0, "nrefine": 1,
+            "niter_cap": NITER, "regparams": PARAMS, "input": "lattice sigma_b=8 (fluid: 6) + texture, shift (1.5,-0.75) px",
+            "l2": "six sessions (about 1 GB of fields) are cycled every step, so each method starts from HBM; no extra flush"}
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def kernel_microbench(size: int, reps: int = 5) -> dict:
+    """Times the main kernels alone through the raw C ABI (include/of2d_cuda.h) on L2-flushed inputs."""
+    import torch
+    from opticalflow2d_b200.torch_bridge import Device
+    dev = Device(strict=False)
+    n = size * size
+    g = torch.Generator(device="cuda").manual_seed(7)
+    f32 = torch.float32
+    img_a = torch.rand(n, device="cuda", dtype=f32, generator=g)
+    img_b = torch.rand(n, device="cuda", dtype=f32, generator=g)
+    u = (torch.rand(2 * n, device="cuda", dtype=f32, generator=g) - 0.5) * 3.0
+    v = (torch.rand(2 * n, device="cuda", dtype=f32, generator=g) - 0.5) * 0.5
+    out2 = torch.empty(2 * n, device="cuda", dtype=f32)
+    out1 = torch.empty(n, device="cuda", dtype=f32)
+    grad = torch.rand(2 * n, device="cuda", dtype=f32, generator=g) - 0.5
+    It = torch.rand(n, device="cuda", dtype=f32, generator=g) - 0.5
+    flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
+    ax = np.arange(5, dtype=np.float64) - 2.0
+    kern = np.exp(-(ax[:, None] ** 2 + ax[None, :] ** 2) / (2 * 1.5 * 1.5))
+    kern = np.ascontiguousarray(kern / kern.sum())
+    import ctypes as C
+    plan = C.c_void_p()
+    dev._check(dev.lib.of2d_curvature_plan_create(dev.ctx, size, size, 0.25, 1.0, 0, C.byref(plan)))
+    hm, hd = np.zeros(1, np.float32), np.zeros(1, np.float32)
+
+    cases = {
+        "diffusion_step": (28, lambda: dev.call("diffusion_step", f32, size, size, 1, u, out2, grad, It, 0.5, None)),
+        "convolute_motion_5x5": (16, lambda: dev.call("convolute_motion", f32, size, size, 1, u, out2, kern, 5, 5)),
+        "demons_force": (24, lambda: dev.call("demons_force", f32, size, size, 1, img_a, img_b, v, out2, 1.0, 0.25, None)),
+        "compose": (24, lambda: dev.call("compose", f32, size, size, 1, u, v, out2)),
+        "warp2d": (16, lambda: dev.call("warp2d", f32, size, size, 1, img_a, v, out1)),
+        "derivatives": (20, lambda: dev.call("derivatives", f32, size, size, 1, img_a, img_b, out2, out1)),
+        "elastic_step_sor": (28, lambda: dev.call("elastic_step", f32, size, size, 1, u, grad, It, 1.0, 0.25, 0.66)),
+        "fluid_step": (60, lambda: dev.call("fluid_step", f32, size, size, v, u, out2, grad, It, 0.1, 0.0, 0.66, hm, hd)),
+        "curvature_step": (92, lambda: dev._check(dev.lib.of2d_curvature_step_f32(plan, C.c_void_p(u.data_ptr()), C.c_void_p(out2.data_ptr()),
+                                                                                  C.c_void_p(grad.data_ptr()), C.c_void_p(It.data_ptr())))),
+        "logger_update": (24, lambda: dev.call("logger_update", f32, n, u, out2, hm)),
+    }
+    res = {}
+    for name, (bpp, fn) in cases.items():
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sum(ts) / len(ts)
+        res[name] = {"ms": ms, "bytes_per_px": bpp, "gbs": bpp * n / (ms * 1e-3) / 1e9}
+    dev.lib.of2d_curvature_plan_destroy(plan)
+    dev.close()
+    return res
+
+
+# kernels launched per iteration by each method (for the dominant-kernel estimate)
+METHOD_KERNELS = {
+    "diffusion": {"diffusion_step": 1, "logger_update": 1},
+    "curvature": {"curvature_step": 1, "logger_update": 1},
+    "elastic": {"elastic_step_sor": 1, "logger_update": 1},
+    "thirion": {"demons_force": 1, "convolute_motion_5x5": 2, "compose": 1, "logger_update": 1},
+    "diffeomorphic": {"demons_force": 1, "convolute_motion_5x5": 2, "compose": 3, "logger_update": 1},
+    "fluid": {"fluid_step": 1, "logger_update": 1},
+}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    os.environ.setdefault("OF2D_DEVICE", str(local))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import opticalflow2d_b200 as of
+    size = args.size
+    n = size * size
+    of.set_stream(torch.cuda.current_stream().cuda_stream, 32)
+
+    # host inputs (pinned doubles, as the MEX boundary delivers them) and resident sessions
+    sessions, pinned = {}, {}
+    for m in METHODS:
+        R, T = make_inputs(m, size)
+        pr = torch.from_numpy(R).pin_memory(); pt = torch.from_numpy(T).pin_memory()
+        pout = torch.empty(2 * n, dtype=torch.float64).pin_memory()
+        pinned[m] = (pr, pt, pout)
+        s = of.Session((size, size), [NITER[m]], 0, REG[m], PARAMS[m], nrefine=1, verbose=0, bits=32)
+        s.set_images_raw(pr.data_ptr(), pt.data_ptr())
+        sessions[m] = s
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(e2e: bool, per_method=None):
+        iters = {}
+        for m in METHODS:
+            s = sessions[m]
+            pr, pt, pout = pinned[m]
+            s.reset()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if e2e:
+                s.set_images_raw(pr.data_ptr(), pt.data_ptr())
+            s.estimate()
+            if e2e:
+                s.motion_raw(pout.data_ptr())
+            e1.record()
+            iters[m] = s.trace()["total_iterations"]
+            if per_method is not None:
+                per_method.setdefault(m, []).append((e0, e1))
+        return iters
+
+    def timed(e2e: bool):
+        for _ in range(args.warmup):
+            step(e2e)
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        per = {}
+        l0 = of.launch_count(32)
+        t0 = time.perf_counter()
+        iters = None
+        for _ in range(args.steps):
+            iters = step(e2e, per)
+        barrier()
+        wall = time.perf_counter() - t0
+        launches = of.launch_count(32) - l0
+        clocks = sampler.stop()
+        ms = {m: sum(a.elapsed_time(b) for a, b in per[m]) / args.steps for m in METHODS}
+        return iters, ms, wall, launches, clocks
+
+    iters, ms, wall, launches, clocks = timed(False)
+    iters_e, ms_e, wall_e, _, _ = timed(True)
+
+    def agg(ms_map, it_map):
+        t = sum(ms_map.values()) * 1e-3
+        px = sum(it_map[m] for m in METHODS) * n
+        return px, t
+
+    px, t = agg(ms, iters)
+    pxe, te = agg(ms_e, iters_e)
+    # max over ranks of the step time, sum over ranks of the work
+    if world > 1:
+        v = torch.tensor([t, te], device="cuda", dtype=torch.float64)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        t, te = float(v[0]), float(v[1])
+        w = torch.tensor([px, pxe], device="cuda", dtype=torch.float64)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        px, pxe = float(w[0]), float(w[1])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        kern = kernel_microbench(size)
+        # dominant kernel = largest estimated share of the step
+        share = {}
+        for m in METHODS:
+            for k, c in METHOD_KERNELS[m].items():
+                share[k] = share.get(k, 0.0) + c * iters[m] * kern[k]["ms"]
+        dom = max(share, key=share.get)
+        methods = {}
+        for m in METHODS:
+            mp = n * iters[m] / (ms[m] * 1e-3) / 1e6
+            gbs = mp * 1e6 * BYTES_PER_PX_ITER[m] / 1e9
+            methods[m] = {"iterations": iters[m], "ms": ms[m], "mpix_iter_s": mp, "gbs_algorithmic": gbs, "frac_of_hbm_peak": gbs / peak,
+                          "e2e_ms": ms_e[m]}
+        cpu = None
+        if True:
+            ncpu = os.cpu_count() or 1
+            workers = max(1, min(len(METHODS), ncpu))
+            c = cpu_reference_step(size, 3, workers)
+            cpu = {"value": c["pixel_iters"] / c["wall_s"] / 1e6, "unit": "Mpixel*iter/s", "cores": workers,
+                   "kind": "reference" if c["kind"] == "ref" else "port",
+                   "sample": f"3 iterations of each of the 6 methods at {size}^2, {workers} processes, {c['wall_s']:.1f} s wall",
+                   "per_method_mpix_iter_s": {m: n * v["iterations"] / v["seconds"] / 1e6 for m, v in c["per_method"].items()}}
+        line = {
+            "metric": "Mpixel*iter/s (6 registration methods, aggregate)", "value": px / t / 1e6, "unit": "Mpixel*iter/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(size),
+            "e2e": {"value": pxe / te / 1e6, "unit": "Mpixel*iter/s", "h2d_bytes_per_step": len(METHODS) * 2 * n * 8,
+                    "d2h_bytes_per_step": len(METHODS) * 2 * n * 8, "ms_per_step": 1e3 * te},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": kern[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                         "share_of_step_estimate": share[dom] / max(sum(share.values()), 1e-12)},
+            "kernels": kern,
+            "methods": methods,
+            "cpu_baseline": cpu,
+            "wall_s_timed_region": wall,
+            "loaded_libraries": [os.path.relpath(p, ROOT) for p in of.loaded_libraries()],
+        }
+        print(json.dumps(line), flush=True)
+    for s in sessions.values():
+        s.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--size", type=int, default=2048)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

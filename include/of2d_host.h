@@ -55,6 +55,8 @@ int of2d_session_create(int dimx, int dimy, int nscales, const int *niter, int n
 void of2d_session_destroy(of2d_session *s);
 int of2d_session_set_images(of2d_session *s, const double *Iref, const double *Imov);
 int of2d_session_estimate(of2d_session *s);
+/* extension: cold start for the next estimate (zero motion pyramid and the fluid velocity; the reference warm-starts) */
+int of2d_session_reset(of2d_session *s);
 int of2d_session_get_motion(of2d_session *s, double *planar_out);      /* 2*N doubles: x plane, y plane */
 int of2d_session_get_motion_aos(of2d_session *s, void *out_real);       /* N {x,y} pairs in the field precision */
 int of2d_session_warp(of2d_session *s, const double *img, double *out);

@@ -232,6 +232,10 @@ class Session:
         """Host pointers to dimx*dimy doubles each (e.g. pinned torch tensors)."""
         _check(self.lib, self.lib.of2d_session_set_images(self.handle, C.c_void_p(Iref_ptr), C.c_void_p(Imov_ptr)))
 
+    def reset(self):
+        """Extension: cold start (the reference warm-starts a second estimate from the previous result)."""
+        _check(self.lib, self.lib.of2d_session_reset(self.handle))
+
     def estimate(self):
         _check(self.lib, self.lib.of2d_session_estimate(self.handle))
 

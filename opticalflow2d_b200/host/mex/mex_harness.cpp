@@ -164,6 +164,9 @@ int of2d_session_set_images(of2d_session* s, const double* Iref, const double* I
         s->reg->set_moving_image(m);
     });
 }
+int of2d_session_reset(of2d_session* s) {
+    return guarded([&] { s->reg->reset_state(); });
+}
 int of2d_session_estimate(of2d_session* s) {
     return guarded([&] { s->reg->estimate_motion(); });
 }

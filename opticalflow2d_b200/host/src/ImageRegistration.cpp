@@ -109,6 +109,13 @@ void ImageRegistration::set_moving_image(const Image& im) {
 Motion* ImageRegistration::get_estimated_motion() const { return motion[0]; }
 void ImageRegistration::copy_estimated_motion(Motion& mo) const { mo = *motion[0]; }
 
+void ImageRegistration::reset_state() {
+    for (int s = nscales; s >= 0; s--) {
+        motion[s]->reset();
+        if (solver && solver[s]) solver[s]->reset_state();
+    }
+}
+
 // reference :133-156.  motion[nscales] is neither reset nor re-downsampled, so a second call on the
 // same object warm-starts from the previous result, exactly as the reference does.
 void ImageRegistration::estimate_motion() {

@@ -45,6 +45,10 @@ public:
 
     void estimate_motion();
 
+    // extension: zero every level's motion and the solvers' carried state, so the next estimate_motion()
+    // starts cold (the reference warm-starts from the previous result)
+    void reset_state();
+
     const RegistrationTrace& get_trace() const { return trace; }
 
 protected:

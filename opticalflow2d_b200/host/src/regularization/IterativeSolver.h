@@ -20,6 +20,9 @@ public:
     // one iteration of the scheme, in place on `motion`
     virtual void get_update(Motion* motion, const Image* Iref = NULL, const Image* Imov = NULL) {}
 
+    // extension: forget state carried between calls (only the fluid velocity)
+    virtual void reset_state() {}
+
 protected:
     dim dimin;
     dim step;

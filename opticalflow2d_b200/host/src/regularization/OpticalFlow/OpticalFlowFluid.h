@@ -13,6 +13,8 @@ public:
 
     void get_update(Motion* motion, const Image* Iref = NULL, const Image* Imov = NULL);
 
+    void reset_state() { velocity->reset(); }
+
     of2d_real last_timestep() const { return timestep; }
     of2d_real last_maxabs() const { return maxabs_increment; }
 
