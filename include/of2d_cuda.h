@@ -54,6 +54,7 @@ int of2d_ctx_sync(of2d_ctx *ctx);
 /* 1: FMA contraction allowed in the flop-heavy kernels (default); 0: reproduce the reference's
    unfused mul/add sequence bit for bit (used by the parity tests) */
 int of2d_ctx_set_fast_math(of2d_ctx *ctx, int on);
+int of2d_ctx_get_fast_math(of2d_ctx *ctx);
 const char *of2d_last_error(void);
 /* how many of this library's kernels have been launched through ctx since creation */
 uint64_t of2d_ctx_launch_count(of2d_ctx *ctx);
@@ -180,6 +181,45 @@ int of2d_curvature_step_f64(of2d_curvature_plan *plan, const double *d_u, double
 /* unnormalised 2-D DCT-II (kind 2) / DCT-III (kind 3) of a row-major n0 x n1 double array, the
    transform fftw_plan_r2r_2d(REDFT10 / REDFT01) computes in the reference; in place on the device */
 int of2d_dct2d_f64(of2d_ctx *ctx, int n0, int n1, int kind, double *d_data);
+
+/* ---- iteration engine ----
+ * One refine pass of the reference's driver loops for `batch` independent pairs, entirely enqueued on
+ * the device: Iaux = Imov o (id + motion); [derivatives]; up to niter x get_update + Logger::update_error
+ * with the break `err < 0.001 && iter > 1`; Fluid: Jacobian-triggered regridding; finally
+ * motion <- estimate + motion o (id + estimate).
+ *   ImageRegistrationOpticalFlow.cpp:97-151, ImageRegistrationDemons.cpp:86-137, ImageRegistrationFluid.cpp:67-142.
+ * Decisions (break, time step, regrid, number of squarings) are taken by device-side reductions; the host
+ * only polls a counter of running pairs.  Arithmetic is the fast mode (FMA in the convolution; Elastic /
+ * Fluid sweep as overlapped tiles, see csrc/sor_tile.cuh); the per-step entry points above stay bit-exact. */
+typedef struct of2d_engine of2d_engine;
+typedef struct {
+    int method;                 /* enum Regularisation, src/SolverOptions.h:4: 0 Diffusion .. 5 Fluid */
+    int dimx, dimy, batch;      /* fields of the batch are stored back to back */
+    int real_is_double;
+    int max_iter;               /* largest niter that will be passed to of2d_engine_refine (trace capacity) */
+    double alpha, tau;          /* Diffusion: alpha; Curvature: alpha, tau */
+    double mu, lambda, omega;   /* Elastic, Fluid */
+    double sigma_i, sigma_x;    /* Demons */
+    int kernel_w;               /* Demons: width of both Gaussian kernels */
+    const double *kernel_fluid;      /* HOST, kernel_w * kernel_w doubles as Kernel::get_kernel() (smooths the correspondence) */
+    const double *kernel_diffusion;  /* HOST (smooths the motion) */
+    int accumulation;           /* Thirion: 0 composition, 1 addition (enum MotionAccumulation) */
+} of2d_engine_desc;
+/* OF2D_ERR_UNSUPPORTED: the parameters need the exact (per-step) path -- callers fall back to the *_step entry points */
+int of2d_engine_create(of2d_ctx *ctx, const of2d_engine_desc *desc, of2d_engine **out);
+void of2d_engine_destroy(of2d_engine *engine);
+/* zeroes the state the reference carries between calls (the Fluid velocity) */
+int of2d_engine_reset_state(of2d_engine *engine);
+/* d_Iref, d_Imov: batch images; d_motion: batch level motions, updated in place.  Synchronises before returning.
+   OF2D_ERR_DIVZERO when a pixel hit the reference's divide-by-zero throw. */
+int of2d_engine_refine_f32(of2d_engine *engine, const float *d_Iref, const float *d_Imov, float *d_motion, int niter);
+int of2d_engine_refine_f64(of2d_engine *engine, const double *d_Iref, const double *d_Imov, double *d_motion, int niter);
+/* what the last refine did for one pair: iterations executed, regrid events, last Logger error */
+int of2d_engine_pair_result(of2d_engine *engine, int pair, int *iterations, int *nregrid, double *last_err);
+/* per-iteration series of the last refine: which = 0 Logger error, 1 maxabs (fluid increment / demons correspondence),
+   2 fluid time step, 3 fluid min Jacobian, 4 fluid regrid flag, 5 diffeomorphic squarings */
+int of2d_engine_trace(of2d_engine *engine, int pair, int which, double *h_out, int count);
+uint64_t of2d_engine_iterations_enqueued(of2d_engine *engine);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,7 @@ int of2d_ctx_set_fast_math(of2d_ctx *c, int on) {
     c->fast_math = on != 0;
     return OF2D_SUCCESS;
 }
+int of2d_ctx_get_fast_math(of2d_ctx *c) { return c->fast_math ? 1 : 0; }
 uint64_t of2d_ctx_launch_count(of2d_ctx *c) { return c->launches; }
 
 int of2d_malloc(of2d_ctx *c, size_t bytes, void **p) {

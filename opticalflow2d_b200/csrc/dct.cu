@@ -25,8 +25,19 @@
 #include <string.h>
 
 #include "device_math.cuh"
+#include "engine_internal.cuh"
 
 namespace {
+
+// engine hook: gating by the pair control block, ping-pong selection and the Logger epilogue (enabled = 0: plain step)
+struct CurvHook {
+    PairCtl *ctl;
+    int *n_active;
+    double *partials;
+    size_t pstride;
+    TraceDev tr;
+    int enabled;
+};
 
 template <class S> struct Cplx;
 template <> struct Cplx<float> { using type = float2; };
@@ -191,12 +202,20 @@ __device__ void dct3_line(cplx_t<S> *x, cplx_t<S> *tmp, const LineTables &T) {
 
 // ---- P1: rows.  One CTA per row j: rhs = u - tau f, DCT-II along x, spectrum row out -----------------
 template <class R, class S>
-__global__ void __launch_bounds__(FFT_THREADS) k_curv_rows_fwd(int nx, int ny, const vec2_t<R> *__restrict__ u, const vec2_t<R> *__restrict__ gradI,
-                                                               const R *__restrict__ It, R tau, cplx_t<S> *__restrict__ spec, LineTables T) {
+__global__ void __launch_bounds__(FFT_THREADS) k_curv_rows_fwd(int nx, int ny, const vec2_t<R> *est0, const vec2_t<R> *est1, const vec2_t<R> *__restrict__ gradI,
+                                                               const R *__restrict__ It, R tau, cplx_t<S> *__restrict__ spec, LineTables T, CurvHook H) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx_t<S> *x = reinterpret_cast<cplx_t<S> *>(smem_raw);
     cplx_t<S> *tmp = x + nx;
     const int j = blockIdx.x;
+    const size_t pair_off = (size_t)blockIdx.y * nx * ny;
+    const vec2_t<R> *__restrict__ u = est0;
+    if (H.enabled) {
+        const PairCtl *c = H.ctl + blockIdx.y;
+        if (!__ldcg(&c->active)) return;
+        u = __ldcg(&c->sel) ? est1 : est0;
+    }
+    u += pair_off; gradI += pair_off; It += pair_off; spec += pair_off;
     const size_t row = (size_t)j * nx;
     for (int i = threadIdx.x; i < nx; i += blockDim.x) {
         const vec2_t<R> uu = u[row + i];
@@ -214,8 +233,10 @@ __global__ void __launch_bounds__(FFT_THREADS) k_curv_rows_fwd(int nx, int ny, c
 // ---- P2: columns.  One CTA per group of C adjacent columns p: DCT-II along y, eigenvalue, DCT-III ----
 template <class S>
 __global__ void __launch_bounds__(FFT_THREADS) k_curv_cols(int nx, int ny, int C, cplx_t<S> *__restrict__ spec, const double *__restrict__ cosx,
-                                                           const double *__restrict__ cosy, double tau_alpha, LineTables T) {
+                                                           const double *__restrict__ cosy, double tau_alpha, LineTables T, CurvHook H) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (H.enabled && !__ldcg(&H.ctl[blockIdx.y].active)) return;
+    spec += (size_t)blockIdx.y * nx * ny;
     cplx_t<S> *lines = reinterpret_cast<cplx_t<S> *>(smem_raw);   // [C][ny]
     cplx_t<S> *tmp = lines + (size_t)C * ny;                      // [ny] (direct path only)
     const int p0 = blockIdx.x * C;
@@ -247,19 +268,48 @@ __global__ void __launch_bounds__(FFT_THREADS) k_curv_cols(int nx, int ny, int C
 
 // ---- P3: rows.  DCT-III along x, u' = rhs / (4 N) (OpticalFlowCurvature.cpp:116-117) ----------------
 template <class R, class S>
-__global__ void __launch_bounds__(FFT_THREADS) k_curv_rows_inv(int nx, int ny, const cplx_t<S> *__restrict__ spec, vec2_t<R> *__restrict__ unew, R fourN,
-                                                               LineTables T) {
+__global__ void __launch_bounds__(FFT_THREADS) k_curv_rows_inv(int nx, int ny, const cplx_t<S> *__restrict__ spec, vec2_t<R> *est0, vec2_t<R> *est1, R fourN,
+                                                               LineTables T, CurvHook H) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx_t<S> *x = reinterpret_cast<cplx_t<S> *>(smem_raw);
     cplx_t<S> *tmp = x + nx;
-    const int j = blockIdx.x;
+    const int j = blockIdx.x, pair = blockIdx.y;
+    const size_t pair_off = (size_t)pair * nx * ny;
+    vec2_t<R> *__restrict__ unew = est1;
+    const vec2_t<R> *__restrict__ uold = est0;
+    PairCtl *c = nullptr;
+    if (H.enabled) {
+        c = H.ctl + pair;
+        if (!__ldcg(&c->active)) return;
+        if (__ldcg(&c->sel)) { unew = est0; uold = est1; }
+    }
+    unew += pair_off; uold += pair_off; spec += pair_off;
     const size_t row = (size_t)j * nx;
     for (int p = threadIdx.x; p < nx; p += blockDim.x) x[p] = spec[row + p];
     __syncthreads();
     dct3_line<S>(x, tmp, T);
+    double sd = 0.0, sp = 0.0;
     for (int i = threadIdx.x; i < nx; i += blockDim.x) {
         const cplx_t<S> v = x[dct3_store_slot<S>(i, T)];
-        unew[row + i] = mk2<R>((R)v.x / fourN, (R)v.y / fourN);
+        const vec2_t<R> o = mk2<R>((R)v.x / fourN, (R)v.y / fourN);
+        unew[row + i] = o;
+        if (H.enabled) {   // Logger.cpp:32-51: prev is the estimate this iteration started from
+            const vec2_t<R> old = uold[row + i];
+            sd += vec_norm_d<R>(mk2<R>(o.x - old.x, o.y - old.y));
+            sp += vec_norm_d<R>(old);
+        }
+    }
+    if (!H.enabled) return;
+    block_sum2(sd, sp);
+    const double vals[2] = {sd, sp};
+    double *part = H.partials + (size_t)pair * H.pstride;
+    if (publish_partials<2>(vals, part, &c->ticket[0], ny, j)) {
+        double out[2];
+        reduce_partials<2>(part, ny, out, 0u, 0u);
+        if (threadIdx.x == 0) {
+            c->sel ^= 1;
+            finalize_logger<R>(c, H.tr, pair, out[0], out[1], (unsigned)(nx * ny), H.n_active);
+        }
     }
 }
 
@@ -316,7 +366,7 @@ int build_tables(int n, LineTables *T, void **d_blob) {
     return OF2D_SUCCESS;
 }
 
-constexpr size_t kMaxSmem = 227 * 1024;
+constexpr size_t kMaxSmem = 220 * 1024;   // dynamic budget: leaves room for the static reduction scratch
 
 }  // namespace
 
@@ -330,28 +380,35 @@ struct of2d_curvature_plan {
     void *d_spec;
     int cols_per_cta;
     size_t smem_rows, smem_cols;
+    int batch;
 };
 
 namespace {
 
 template <class R, class S>
-int curvature_step_impl(of2d_curvature_plan *P, const R *u, R *unew, const R *gradI, const R *It) {
+int curvature_step_impl(of2d_curvature_plan *P, const R *u, R *unew, const R *gradI, const R *It, const CurvHook &H) {
     of2d_ctx *ctx = P->ctx;
+    const int batch = H.enabled ? P->batch : 1;
     const int nx = P->nx, ny = P->ny;
     cplx_t<S> *spec = (cplx_t<S> *)P->d_spec;
-    static bool configured = false;
-    if (!configured) {
-        OF2D_CUDA_TRY(cudaFuncSetAttribute(k_curv_rows_fwd<R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-        OF2D_CUDA_TRY(cudaFuncSetAttribute(k_curv_rows_inv<R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-        OF2D_CUDA_TRY(cudaFuncSetAttribute(k_curv_cols<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-        configured = true;
+    static size_t configured_rows = 0, configured_cols = 0;   // per template instance: largest dynamic size set so far
+    if (P->smem_rows > configured_rows) {
+        OF2D_CUDA_TRY(cudaFuncSetAttribute(k_curv_rows_fwd<R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_rows));
+        OF2D_CUDA_TRY(cudaFuncSetAttribute(k_curv_rows_inv<R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_rows));
+        configured_rows = P->smem_rows;
     }
-    k_curv_rows_fwd<R, S><<<ny, FFT_THREADS, P->smem_rows, ctx->stream>>>(nx, ny, (const vec2_t<R> *)u, (const vec2_t<R> *)gradI, It, (R)P->tau, spec, P->Tx);
+    if (P->smem_cols > configured_cols) {
+        OF2D_CUDA_TRY(cudaFuncSetAttribute(k_curv_cols<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_cols));
+        configured_cols = P->smem_cols;
+    }
+    k_curv_rows_fwd<R, S><<<dim3(ny, batch), FFT_THREADS, P->smem_rows, ctx->stream>>>(nx, ny, (const vec2_t<R> *)u, (const vec2_t<R> *)unew, (const vec2_t<R> *)gradI, It,
+                                                                                      (R)P->tau, spec, P->Tx, H);
     OF2D_LAUNCH_CHECK(ctx);
-    k_curv_cols<S><<<ceil_div(nx, P->cols_per_cta), FFT_THREADS, P->smem_cols, ctx->stream>>>(nx, ny, P->cols_per_cta, spec, P->d_cosx, P->d_cosy, P->tau_alpha, P->Ty);
+    k_curv_cols<S><<<dim3(ceil_div(nx, P->cols_per_cta), batch), FFT_THREADS, P->smem_cols, ctx->stream>>>(nx, ny, P->cols_per_cta, spec, P->d_cosx, P->d_cosy,
+                                                                                                       P->tau_alpha, P->Ty, H);
     OF2D_LAUNCH_CHECK(ctx);
     const R fourN = (R)4.0f * (R)(unsigned)(nx * ny);
-    k_curv_rows_inv<R, S><<<ny, FFT_THREADS, P->smem_rows, ctx->stream>>>(nx, ny, spec, (vec2_t<R> *)unew, fourN, P->Tx);
+    k_curv_rows_inv<R, S><<<dim3(ny, batch), FFT_THREADS, P->smem_rows, ctx->stream>>>(nx, ny, spec, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN, P->Tx, H);
     OF2D_LAUNCH_CHECK(ctx);
     return OF2D_SUCCESS;
 }
@@ -366,7 +423,7 @@ int of2d_curvature_plan_create(of2d_ctx *ctx, int nx, int ny, double alpha, doub
     of2d_curvature_plan *P = new of2d_curvature_plan();
     memset(P, 0, sizeof(*P));
     P->ctx = ctx; P->nx = nx; P->ny = ny; P->real_is_double = real_is_double; P->spec_is_double = 1;
-    P->alpha = alpha; P->tau = tau;
+    P->alpha = alpha; P->tau = tau; P->batch = 1;
     // the reference multiplies tau*alpha in `float` (fp32 build) before promoting (OpticalFlowCurvature.cpp:24)
     P->tau_alpha = real_is_double ? tau * alpha : (double)((float)tau * (float)alpha);
     int st = build_tables<double>(nx, &P->Tx, &P->blob_x);
@@ -414,13 +471,38 @@ void of2d_curvature_plan_destroy(of2d_curvature_plan *P) {
 int of2d_curvature_step_f32(of2d_curvature_plan *P, const float *u, float *unew, const float *g, const float *It) {
     OF2D_REQUIRE(!P->real_is_double, "plan was created for double fields");
     OF2D_REQUIRE(u != unew, "curvature step is out of place");
-    return curvature_step_impl<float, double>(P, u, unew, g, It);
+    CurvHook H; memset(&H, 0, sizeof(H));
+    return curvature_step_impl<float, double>(P, u, unew, g, It, H);
 }
 int of2d_curvature_step_f64(of2d_curvature_plan *P, const double *u, double *unew, const double *g, const double *It) {
     OF2D_REQUIRE(P->real_is_double, "plan was created for float fields");
     OF2D_REQUIRE(u != unew, "curvature step is out of place");
-    return curvature_step_impl<double, double>(P, u, unew, g, It);
+    CurvHook H; memset(&H, 0, sizeof(H));
+    return curvature_step_impl<double, double>(P, u, unew, g, It, H);
 }
+
+}  // extern "C"
+
+// engine entry points (engine_internal.cuh)
+int of2d_curvature_plan_set_batch(of2d_curvature_plan *P, int batch) {
+    if (batch == P->batch) return OF2D_SUCCESS;
+    OF2D_CUDA_TRY(cudaStreamSynchronize(P->ctx->stream));
+    OF2D_CUDA_TRY(cudaFree(P->d_spec));
+    P->d_spec = nullptr;
+    OF2D_CUDA_TRY(cudaMalloc(&P->d_spec, sizeof(double2) * (size_t)P->nx * P->ny * batch));
+    P->batch = batch;
+    return OF2D_SUCCESS;
+}
+
+int of2d_curvature_engine_step(of2d_curvature_plan *P, PairCtl *ctl, int *n_active, double *partials, size_t pstride, TraceDev tr, void *est0, void *est1,
+                               const void *gradI, const void *It) {
+    CurvHook H;
+    H.ctl = ctl; H.n_active = n_active; H.partials = partials; H.pstride = pstride; H.tr = tr; H.enabled = 1;
+    if (P->real_is_double) return curvature_step_impl<double, double>(P, (const double *)est0, (double *)est1, (const double *)gradI, (const double *)It, H);
+    return curvature_step_impl<float, double>(P, (const float *)est0, (float *)est1, (const float *)gradI, (const float *)It, H);
+}
+
+extern "C" {
 
 int of2d_dct2d_f64(of2d_ctx *ctx, int n0, int n1, int kind, double *d) {
     OF2D_REQUIRE(n0 > 0 && n1 > 0 && (kind == 2 || kind == 3), "bad arguments");

@@ -12,20 +12,21 @@
 
 #include "common.cuh"
 
-constexpr int kMaxIter = 4096;       // trace capacity per refine
-constexpr int kNsqMax = 10;          // scaling-and-squaring steps enqueued per diffeomorphic iteration
-
 struct alignas(16) PairCtl {
     int active;          // 1 while the inner loop of this pair is running
     int iter;            // iterations completed so far in this refine (Logger::iter)
     int niter;           // cap
-    unsigned flags;      // OF2D_FLAG_*
+    unsigned flags;      // OF2D_FLAG_* (sticky until the host reads them)
+    int sel;             // which of the two estimate buffers holds the current estimate
     int regrid;          // fluid: regrid requested by the iteration that just finished
     int skip;            // fluid: integration skipped (dt >= 65)
     int nsquares;        // diffeomorphic: squarings of the current iteration
-    int nregrid;         // fluid: regrid events so far
+    int nregrid;         // fluid: regrid events so far in this refine
     int msel;            // fluid: which of the two level-motion buffers is current
-    int overflow;        // nsquares > kNsqMax or iter trace overflow: host must take over
+    int overflow;        // nsquares above the enqueued squarings: host must not trust the result
+    int vsel;            // fluid: which velocity buffer is current (persists across refines and calls, like the velocity)
+    int prev_other;      // fluid: Logger's prev is the other estimate buffer (set by a regrid, which zeroes the estimate)
+    int pad0[3];
     unsigned ticket[4];  // last-block tickets (one per reduction kind)
     double err;          // last Logger error
     double maxabs;       // fluid / diffeo: sqrt(max(2 y^2))
@@ -34,25 +35,26 @@ struct alignas(16) PairCtl {
     double minjac;
 };
 
-// per-iteration traces of one pair (device arrays of kMaxIter entries each)
-struct PairTrace {
-    float *err;       // Logger error as `real`-rounded double
-    float *maxabs;    // fluid
-    float *dt;        // fluid
-    float *minjac;    // fluid (only meaningful where regrid == 1)
+// per-iteration traces, [batch][cap] each
+struct TraceDev {
+    double *err;      // Logger error (rounded to `real` first)
+    double *maxabs;   // fluid increment maxabs / diffeo correspondence maxabs
+    double *dt;       // fluid
+    double *minjac;   // fluid (meaningful where regrid == 1)
     int *regrid;      // fluid: 1 if a regrid followed this iteration
-    int *nsquares;    // diffeo
+    int *nsq;         // diffeo
+    int cap;
 };
 
-// Publishes NV per-CTA partial values and returns true (for every thread of the CTA) in the CTA that
-// arrived last; that CTA may then read all `nblocks` partials of this pair.
+// Publishes NV per-CTA partial values (valid in thread 0) and returns true, for every thread of the
+// CTA, in the CTA that arrived last; that CTA may then read all `nblocks` partials of this pair.
 template <int NV>
 __device__ __forceinline__ bool publish_partials(const double (&vals)[NV], double *__restrict__ partials, unsigned *ticket, int nblocks, int bid) {
     __shared__ int s_last;
     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
     if (tid == 0) {
 #pragma unroll
-        for (int v = 0; v < NV; v++) partials[(size_t)bid * NV + v] = vals[v];
+        for (int v = 0; v < NV; v++) __stcg(&partials[(size_t)bid * NV + v], vals[v]);
         __threadfence();
         const unsigned t = atomicAdd(ticket, 1u);
         s_last = (t == (unsigned)nblocks - 1u);
@@ -62,8 +64,8 @@ __device__ __forceinline__ bool publish_partials(const double (&vals)[NV], doubl
     return s_last != 0;
 }
 
-// fixed-order reduction of the published partials by the last CTA: sums for value indices in SUM_MASK,
-// max for MAX_MASK, min for MIN_MASK.  Result valid in thread 0.
+// fixed-order reduction of the published partials by the last CTA: max for value indices in max_mask,
+// min for min_mask, sum otherwise.  Result valid in thread 0.
 template <int NV>
 __device__ __forceinline__ void reduce_partials(const double *__restrict__ partials, int nblocks, double (&out)[NV], unsigned max_mask, unsigned min_mask) {
     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
@@ -90,13 +92,19 @@ __device__ __forceinline__ void reduce_partials(const double *__restrict__ parti
 
 // Logger::update_error + the drivers' break test (Logger.cpp:32-51, ImageRegistrationOpticalFlow.cpp:131-134).
 // `sum_diff`, `sum_prev` are the double sums of |u - prev| and |prev| over the n pixels of the pair.
+// Called by ONE thread.  Returns true if the loop of this pair goes on.
 template <class R>
-__device__ __forceinline__ void finalize_logger(PairCtl *c, const PairTrace &tr, double sum_diff, double sum_prev, unsigned n) {
+__device__ __forceinline__ bool finalize_logger(PairCtl *c, const TraceDev &tr, int pair, double sum_diff, double sum_prev, unsigned n, int *n_active) {
     const R diffnorm = (R)sum_diff / (R)n, prevnorm = (R)sum_prev / (R)n;     // Motion.cpp:47
     const R err = prevnorm == 0 ? (R)0.0f : diffnorm / prevnorm;               // Logger.cpp:39
     const int it = c->iter;
     c->err = (double)err;
-    if (it < kMaxIter) tr.err[it] = (float)err; else c->overflow = 1;
+    if (it < tr.cap) tr.err[(size_t)pair * tr.cap + it] = (double)err;
     c->iter = it + 1;
-    if ((err < (R)0.001f && it > 1) || it + 1 >= c->niter) c->active = 0;
+    if ((err < (R)0.001f && it > 1) || it + 1 >= c->niter) {
+        c->active = 0;
+        atomicSub(n_active, 1);
+        return false;
+    }
+    return true;
 }

@@ -1,0 +1,346 @@
+// sor_tile.cuh -- the lexicographic SOR sweep of OpticalFlowElastic::SOR_iteration /
+// OpticalFlowFluid::SOR_iteration (OpticalFlowElastic.cpp:21-55, OpticalFlowFluid.cpp:7-41) as
+// independent overlapped tiles.
+//
+// The sweep updates in place with x (i) outer and y (j) inner, so cell (i,j) sees NEW values at
+// (i-1, j-1..j+1) and (i, j-1).  It is a lower-triangular solve whose off-diagonal weights are
+//     a  = |c_relax| mu                 (south, same column)
+//     aW = |c_relax| (2 mu + lambda)    (west)         aD = |c_relax| (mu + lambda) / 4   (north-/south-west)
+// With the reference's under-relaxation (omega = 0.66) these sum to < 0.4, so the influence of a cell on
+// cells further along the sweep decays geometrically: about 0.33 per column and 0.14 per row.  A tile
+// that starts the same sequential sweep HW columns to the west / HS rows to the south / HN rows to the
+// north of the cells it owns, taking OLD values on that outer ring, reproduces the exact sweep on its
+// own cells up to eps = 2^-34 (fp32) / 2^-62 (fp64) of the iteration's step size -- below half an ulp,
+// i.e. bit-identical in practice (tests/test_engine_gpu.py compares with the exact wavefront kernel).
+// sor_plan() derives HW / HS / HN / M from the parameters and refuses (-> exact wavefront path) when
+// they do not contract fast enough.
+//
+// Work layout (fields are in the transposed layout, element (i,j) at i*P + j, so a column is contiguous):
+//   CTA = NT threads, thread t owns RPT consecutive rows; the CTA walks its columns west -> east.
+//   Per column: TMA bulk copies (cp.async.bulk, one per field) stream the column segments of x_old,
+//   gradI, It (and the motion the force is evaluated on) into an NS-stage shared-memory ring, each
+//   stage guarded by an mbarrier.  A thread forms, for its rows, everything that does not depend on the
+//   cell below (d), solves its RPT-row recurrence x_r = a x_{r-1} + d_r with a zero carry, publishes its
+//   top value; after ONE __syncthreads per column it adds the carry from the threads below
+//   (sum_q a^(RPT q) x_top[t-q], M terms).
+#pragma once
+
+#include "device_math.cuh"
+#include "engine_ctl.cuh"
+
+struct SorPlan {
+    int nx, ny, P, batch;
+    int NT, RPT, NS;
+    int BX, BY, HW, HS, HN, M;
+    int nbands, nstrips;
+    double c_keep, c_relax, mu, mupl;
+    size_t nT;
+    int supported;
+};
+
+namespace {
+
+constexpr int SOR_NS = 6;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    unsigned ok = 0;
+    const unsigned addr = smem_u32(bar);
+    while (!ok) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    }
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <class R>
+struct SorTileArgs {
+    int nx, ny, P;
+    size_t nT, n;
+    int BX, BY, HW, HS, HN, M, LR;
+    int which;                     // 0: x = estimate (sel, Logger epilogue); 1: x = velocity (vsel)
+    vec2_t<R> *x[2];
+    const vec2_t<R> *uf[2];        // fluid: the estimate the force is evaluated on (picked by sel)
+    const vec2_t<R> *gradI;
+    const R *It;
+    R ck, cr, mu, mupl, a;
+    PairCtl *ctl;
+    int *n_active;
+    double *partials;
+    size_t pstride;
+    TraceDev tr;
+};
+
+template <class R, int RPT, bool FLUID>
+__global__ void __launch_bounds__(256) k_sor_tile(SorTileArgs<R> A) {
+    using V = vec2_t<R>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full[SOR_NS];
+    const int pair = blockIdx.z;
+    PairCtl *c = A.ctl + pair;
+    if (!__ldcg(&c->active)) return;
+
+    const int NT = blockDim.x, t = threadIdx.x;
+    const int nx = A.nx, ny = A.ny, P = A.P, LR = A.LR;
+    const int is = 1 + blockIdx.x * A.BX, ie = min(is + A.BX, nx - 1);
+    const int js = 1 + blockIdx.y * A.BY, je = min(js + A.BY, ny - 1);
+    const int ic0 = max(1, is - A.HW);
+    const int jc0 = max(1, js - A.HS), jc1 = min(ny - 1, je + A.HN);
+    const int jl0 = (jc0 - 1) & ~3;
+    const int ncols = ie - ic0 + 2;              // loaded columns ic0-1 .. ie
+
+    const int xsel = A.which ? __ldcg(&c->vsel) : __ldcg(&c->sel);
+    const V *__restrict__ xin = A.x[xsel] + (size_t)pair * A.nT;
+    V *__restrict__ xout = A.x[xsel ^ 1] + (size_t)pair * A.nT;
+    const V *__restrict__ ufp = FLUID ? A.uf[__ldcg(&c->sel)] + (size_t)pair * A.nT : nullptr;
+    const V *__restrict__ gp = A.gradI + (size_t)pair * A.nT;
+    const R *__restrict__ tp = A.It + (size_t)pair * A.nT;
+
+    // stage layout: [x LR][gradI LR][uf LR (fluid)][It LR]
+    const size_t stage_bytes = (size_t)LR * (sizeof(V) * (FLUID ? 3 : 2) + sizeof(R));
+    auto st_x = [&](int s) { return reinterpret_cast<V *>(smem_raw + s * stage_bytes); };
+    auto st_g = [&](int s) { return reinterpret_cast<V *>(smem_raw + s * stage_bytes) + LR; };
+    auto st_u = [&](int s) { return reinterpret_cast<V *>(smem_raw + s * stage_bytes) + 2 * LR; };
+    auto st_t = [&](int s) { return reinterpret_cast<R *>(smem_raw + s * stage_bytes + (size_t)LR * sizeof(V) * (FLUID ? 3 : 2)); };
+    struct Pub { V top, d0; };
+    Pub *pub = reinterpret_cast<Pub *>(smem_raw + SOR_NS * stage_bytes);   // [2][NT]
+
+    auto issue = [&](int k) {   // thread 0: loaded column k -> stage k % NS
+        const int s = k % SOR_NS;
+        const size_t g = (size_t)(ic0 - 1 + k) * P + jl0;
+        mbar_expect_tx(&full[s], (unsigned)stage_bytes);
+        bulk_g2s(st_x(s), xin + g, (unsigned)(LR * sizeof(V)), &full[s]);
+        bulk_g2s(st_g(s), gp + g, (unsigned)(LR * sizeof(V)), &full[s]);
+        if (FLUID) bulk_g2s(st_u(s), ufp + g, (unsigned)(LR * sizeof(V)), &full[s]);
+        bulk_g2s(st_t(s), tp + g, (unsigned)(LR * sizeof(R)), &full[s]);
+    };
+
+    if (t == 0) {
+        for (int s = 0; s < SOR_NS; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (t == 0) {
+        const int pre = ncols < SOR_NS ? ncols : SOR_NS;
+        for (int k = 0; k < pre; k++) issue(k);
+    }
+
+    const int j0 = jl0 + 1 + t * RPT;            // first row of this thread; its smem row index is t*RPT + 1
+    bool comp[RPT];
+    bool allcomp = true;
+#pragma unroll
+    for (int r = 0; r < RPT; r++) { comp[r] = (j0 + r >= jc0) && (j0 + r < jc1); allcomp = allcomp && comp[r]; }
+    const bool above_comp = (j0 + RPT >= jc0) && (j0 + RPT < jc1);
+    R aR = (R)1;
+#pragma unroll
+    for (int r = 0; r < RPT; r++) aR *= A.a;
+
+    V newW[RPT + 2], oldC[RPT + 1], oldCm1;
+    mbar_wait(&full[0], 0);
+    mbar_wait(&full[1 % SOR_NS], 0);
+    {
+        const V *x0 = st_x(0), *x1 = st_x(1 % SOR_NS);
+#pragma unroll
+        for (int r = 0; r < RPT + 2; r++) newW[r] = x0[t * RPT + r];
+        oldCm1 = x1[t * RPT];
+#pragma unroll
+        for (int r = 0; r < RPT + 1; r++) oldC[r] = x1[t * RPT + 1 + r];
+    }
+
+    double sd = 0.0, sp = 0.0;
+    for (int k = 1; k <= ncols - 2; k++) {
+        const int i = ic0 - 1 + k;
+        const int sC = k % SOR_NS, sE = (k + 1) % SOR_NS;
+        mbar_wait(&full[sE], (unsigned)(((k + 1) / SOR_NS) & 1));
+        V oldE[RPT + 2];
+        {
+            const V *xe = st_x(sE);
+#pragma unroll
+            for (int r = 0; r < RPT + 2; r++) oldE[r] = xe[t * RPT + r];
+        }
+        V d[RPT], xt[RPT];
+        R gk[RPT];
+        {
+            const V *gs = st_g(sC);
+            const R *ts = st_t(sC);
+            const V *us = st_u(sC);
+#pragma unroll
+            for (int r = 0; r < RPT; r++) {
+                const V Cc = oldC[r], N = oldC[r + 1];
+                const V W = newW[r + 1], SW = newW[r], NW = newW[r + 2];
+                const V E = oldE[r + 1], SE = oldE[r], NE = oldE[r + 2];
+                const V b = lssd_force<R>(gs[t * RPT + 1 + r], ts[t * RPT + 1 + r], FLUID ? us[t * RPT + 1 + r] : Cc);
+                V dd;
+                dd.x = A.ck * Cc.x + A.cr * (b.x - A.mu * ((E.x + W.x) + N.x) - A.mupl * (E.x + W.x + (R)0.25f * (NE.y - NW.y - SE.y + SW.y)));
+                dd.y = A.ck * Cc.y + A.cr * (b.y - A.mu * ((E.y + W.y) + N.y) - A.mupl * (E.y + W.y + (R)0.25f * (NE.x - NW.x - SE.x + SW.x)));
+                d[r] = comp[r] ? dd : Cc;
+            }
+        }
+        // zero-carry recurrence over the thread's rows
+        xt[0] = d[0];
+        gk[0] = comp[0] ? A.a : (R)0;
+#pragma unroll
+        for (int r = 1; r < RPT; r++) {
+            if (comp[r]) { xt[r] = mk2<R>(A.a * xt[r - 1].x + d[r].x, A.a * xt[r - 1].y + d[r].y); gk[r] = A.a * gk[r - 1]; }
+            else { xt[r] = d[r]; gk[r] = (R)0; }
+        }
+        Pub *pb = pub + (k & 1) * NT;
+        {
+            Pub me;
+            me.top = xt[RPT - 1];
+            if (t == 0) { me.top.x += gk[RPT - 1] * oldCm1.x; me.top.y += gk[RPT - 1] * oldCm1.y; }   // thread 0 knows its carry
+            me.d0 = d[0];
+            pb[t] = me;
+        }
+        __syncthreads();
+        if (t == 0) {   // stage sC (and stage 0 after the first step) is free: stream the next column(s) in
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (k == 1 && SOR_NS < ncols) issue(SOR_NS);
+            if (k + SOR_NS < ncols) issue(k + SOR_NS);
+        }
+        V carry;
+        if (t == 0) {
+            carry = oldCm1;
+        } else {
+            carry = mk2<R>((R)0, (R)0);
+            R coef = (R)1;
+            for (int q = 1; q <= A.M; q++) {
+                const int tq = t - q;
+                if (tq < 0) break;
+                const V tv = pb[tq].top;
+                carry.x += coef * tv.x; carry.y += coef * tv.y;
+                if (tq == 0) break;
+                const int jq = jl0 + 1 + tq * RPT;
+                if (!(jq >= jc0 && jq + RPT - 1 < jc1)) break;
+                coef *= aR;
+            }
+        }
+        V xn[RPT];
+#pragma unroll
+        for (int r = 0; r < RPT; r++) xn[r] = mk2<R>(xt[r].x + gk[r] * carry.x, xt[r].y + gk[r] * carry.y);
+        V ntop;
+        if (t + 1 < NT) {
+            const V d0 = pb[t + 1].d0;
+            ntop = above_comp ? mk2<R>(A.a * xn[RPT - 1].x + d0.x, A.a * xn[RPT - 1].y + d0.y) : d0;
+        } else {
+            ntop = oldC[RPT];
+        }
+        if (i >= is) {
+#pragma unroll
+            for (int r = 0; r < RPT; r++) {
+                const int j = j0 + r;
+                if (j >= js && j < je) {
+                    xout[(size_t)i * P + j] = xn[r];
+                    if (!FLUID) {
+                        sd += vec_norm_d<R>(mk2<R>(xn[r].x - oldC[r].x, xn[r].y - oldC[r].y));
+                        sp += vec_norm_d<R>(oldC[r]);
+                    }
+                }
+            }
+        }
+        newW[0] = carry;
+#pragma unroll
+        for (int r = 0; r < RPT; r++) newW[r + 1] = xn[r];
+        newW[RPT + 1] = ntop;
+        oldCm1 = oldE[0];
+#pragma unroll
+        for (int r = 0; r < RPT + 1; r++) oldC[r] = oldE[r + 1];
+    }
+
+    if (FLUID) return;
+    block_sum2(sd, sp);
+    const double vals[2] = {sd, sp};
+    const int nblocks = gridDim.x * gridDim.y, bid = blockIdx.x + blockIdx.y * gridDim.x;
+    double *part = A.partials + (size_t)pair * A.pstride;
+    if (publish_partials<2>(vals, part, &c->ticket[0], nblocks, bid)) {
+        double out[2];
+        reduce_partials<2>(part, nblocks, out, 0u, 0u);
+        if (t == 0) {
+            c->sel ^= 1;
+            finalize_logger<R>(c, A.tr, pair, out[0], out[1], (unsigned)A.n, A.n_active);
+        }
+    }
+}
+
+}  // namespace
+
+// halo widths from the contraction of the sweep; supported = 0 when the parameters do not contract
+static inline SorPlan sor_plan(int nx, int ny, int batch, double mu, double lambda, double omega, bool dbl) {
+    SorPlan S;
+    memset(&S, 0, sizeof(S));
+    S.nx = nx; S.ny = ny; S.batch = batch;
+    S.P = (ny + 3) & ~3;
+    S.NS = SOR_NS;
+    const double den = -6.0 * mu - 2.0 * lambda;
+    S.c_keep = 1.0 - omega; S.c_relax = den != 0 ? omega / den : 0.0; S.mu = mu; S.mupl = mu + lambda;
+    if (den == 0 || nx < 3 || ny < 3) { S.supported = 0; return S; }
+    const double cr = fabs(S.c_relax);
+    const double a = cr * fabs(mu), aW = cr * (fabs(mu) + fabs(mu + lambda)), aD = 0.25 * cr * fabs(mu + lambda);
+    const double eps = dbl ? ldexp(1.0, -62) : ldexp(1.0, -34);
+    S.supported = 1;
+    if (!(a < 0.6) || !(aW + 2 * aD < 0.6) || !(1.0 - a - aW - aD > 0.15)) { S.supported = 0; return S; }
+    const double rx = (aW + 2 * aD) / (1.0 - a), rs = a / (1.0 - aW - 2 * aD), rn = aD / (1.0 - a - aW - aD);
+    auto halo = [&](double rho) { return rho <= 1e-12 ? 1 : (int)ceil(log(eps) / log(rho)) + 1; };
+    S.HW = halo(rx); S.HS = halo(rs); S.HN = halo(rn);
+    S.RPT = 2;
+    S.NT = 128;
+    S.M = a <= 1e-12 ? 1 : (int)ceil(log(eps) / (S.RPT * log(a))) + 1;
+    if (S.HW > 96 || S.HS + S.HN > S.NT * S.RPT / 2 || S.M > 16) { S.supported = 0; return S; }
+    S.BY = S.NT * S.RPT - S.HS - S.HN - 4;
+    // column bands: wide enough to amortise the west halo, narrow enough to fill the GPU
+    S.BX = 64;
+    const long tiles_needed = 148L * 2;
+    while (S.BX > 32 && (long)batch * ceil_div(ny - 2, S.BY) * ceil_div(nx - 2, S.BX) < tiles_needed) S.BX -= 16;
+    while ((long)batch * ceil_div(ny - 2, S.BY) * ceil_div(nx - 2, S.BX * 2) >= tiles_needed * 2 && S.BX < 256) S.BX *= 2;
+    S.nbands = ceil_div(nx - 2, S.BX);
+    S.nstrips = ceil_div(ny - 2, S.BY);
+    S.nT = (size_t)nx * S.P + 1024;
+    return S;
+}
+
+template <class R>
+static int sor_tile_launch(of2d_ctx *ctx, const SorPlan &S, PairCtl *ctl, int *n_active, double *partials, size_t pstride, const TraceDev &tr, int which,
+                           vec2_t<R> *x0, vec2_t<R> *x1, const vec2_t<R> *uf0, const vec2_t<R> *uf1, const vec2_t<R> *gradI, const R *It) {
+    SorTileArgs<R> A;
+    A.nx = S.nx; A.ny = S.ny; A.P = S.P; A.nT = S.nT; A.n = (size_t)S.nx * S.ny;
+    A.BX = S.BX; A.BY = S.BY; A.HW = S.HW; A.HS = S.HS; A.HN = S.HN; A.M = S.M;
+    A.LR = S.NT * S.RPT + 4;
+    A.which = which;
+    A.x[0] = x0; A.x[1] = x1; A.uf[0] = uf0; A.uf[1] = uf1; A.gradI = gradI; A.It = It;
+    A.ck = (R)S.c_keep; A.cr = (R)S.c_relax; A.mu = (R)S.mu; A.mupl = (R)S.mupl;
+    A.a = (R)(-S.c_relax * S.mu);
+    A.ctl = ctl; A.n_active = n_active; A.partials = partials; A.pstride = pstride; A.tr = tr;
+    const bool fluid = which == 1;
+    const size_t stage = (size_t)A.LR * (sizeof(vec2_t<R>) * (fluid ? 3 : 2) + sizeof(R));
+    const size_t smem = SOR_NS * stage + 2 * (size_t)S.NT * 2 * sizeof(vec2_t<R>);
+    const dim3 grid(S.nbands, S.nstrips, S.batch);
+    static bool configured[2][2] = {};
+    const int pi = sizeof(R) == 8;
+    if (fluid) {
+        if (!configured[pi][1]) {
+            OF2D_CUDA_TRY(cudaFuncSetAttribute(k_sor_tile<R, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured[pi][1] = true;
+        }
+        k_sor_tile<R, 2, true><<<grid, S.NT, smem, ctx->stream>>>(A);
+    } else {
+        if (!configured[pi][0]) {
+            OF2D_CUDA_TRY(cudaFuncSetAttribute(k_sor_tile<R, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured[pi][0] = true;
+        }
+        k_sor_tile<R, 2, false><<<grid, S.NT, smem, ctx->stream>>>(A);
+    }
+    OF2D_LAUNCH_CHECK(ctx);
+    return OF2D_SUCCESS;
+}

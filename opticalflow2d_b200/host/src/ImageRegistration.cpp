@@ -51,8 +51,10 @@ void ImageRegistration::display_registration_parameters(const Regularisation reg
 // reference src/ImageRegistration.cpp:49-84
 ImageRegistration::ImageRegistration(const dim dimin_, const int nscales_, const int* niter_, const int nrefine_, const Regularisation reg,
                                      const of2d_real* regparams, const unsigned int nparams, const Verbose verbose_)
-    : nscales(nscales_), nrefine(nrefine_), solver(nullptr), verbose(verbose_) {
+    : nscales(nscales_), nrefine(nrefine_), solver(nullptr), verbose(verbose_), method(reg), method_params(regparams, regparams + nparams) {
     const int levels = nscales + 1;
+    engines.assign((size_t)levels, nullptr);
+    engine_refused.assign((size_t)levels, 0);
     dimin = new dim[levels];
     sizein = new int[levels];
     for (int s = nscales; s >= 0; s--) {
@@ -83,6 +85,7 @@ void ImageRegistration::release_solvers() {
 
 ImageRegistration::~ImageRegistration() {
     release_solvers();
+    release_engines();
     for (int s = nscales; s >= 0; s--) {
         delete Iref[s];
         delete Imov[s];
@@ -113,6 +116,7 @@ void ImageRegistration::reset_state() {
     for (int s = nscales; s >= 0; s--) {
         motion[s]->reset();
         if (solver && solver[s]) solver[s]->reset_state();
+        if (engines[(size_t)s]) of2d::check(of2d_engine_reset_state(engines[(size_t)s]));
     }
 }
 
@@ -132,7 +136,103 @@ void ImageRegistration::estimate_motion() {
 // ImageRegistrationFluid.cpp:67-142.  Differences between the families: OpticalFlow and Fluid fix the
 // derivatives once per refine, Demons hands (Iref, Iaux) to every get_update; Fluid regrids when the
 // Jacobian of the running estimate drops below 0.5.
+void ImageRegistration::release_engines() {
+    for (of2d_engine*& e : engines) {
+        if (e) of2d_engine_destroy(e);
+        e = nullptr;
+    }
+}
+
+// Engine description from the registration parameters, with the defaults of the solver constructors
+// (OpticalFlowCurvature.h:10 tau = 1; OpticalFlowElastic.h:9 / OpticalFlowFluid.h:10 omega = 0.66).
+of2d_engine* ImageRegistration::engine_for_level(int level) {
+    const size_t L = (size_t)level;
+    if (engines[L] || engine_refused[L]) return engines[L];
+    const std::vector<of2d_real>& p = method_params;
+    of2d_engine_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.method = (int)method;
+    d.dimx = (int)dimin[level].x; d.dimy = (int)dimin[level].y; d.batch = 1;
+    d.real_is_double = sizeof(of2d_real) == 8;
+    d.max_iter = niter[level];
+    const of2d_real omega_default = 0.66;
+    Kernel kf(1u), kd(1u);
+    switch (method) {
+        case Regularisation::Diffusion: d.alpha = p[0]; break;
+        case Regularisation::Curvature: d.alpha = p[0]; d.tau = p.size() > 1 ? p[1] : (of2d_real)1; break;
+        case Regularisation::Elastic:
+        case Regularisation::Fluid: d.mu = p[0]; d.lambda = p[1]; d.omega = p.size() > 2 ? p[2] : omega_default; break;
+        case Regularisation::ThirionsDemons:
+        case Regularisation::DiffeomorphicDemons: {
+            d.sigma_i = p[0]; d.sigma_x = p[1];
+            const unsigned int width = static_cast<unsigned int>(p[4]);
+            d.kernel_w = (int)width;
+            kd = Kernel(width); kd.set_gaussian(p[2]);    // sigma_diffusion smooths the motion
+            kf = Kernel(width); kf.set_gaussian(p[3]);    // sigma_fluid smooths the correspondence
+            d.kernel_diffusion = kd.get_kernel();
+            d.kernel_fluid = kf.get_kernel();
+            d.accumulation = method == Regularisation::ThirionsDemons ? (int)p[5] : 0;
+            break;
+        }
+    }
+    of2d_engine* e = nullptr;
+    const int st = of2d_engine_create(of2d::context(), &d, &e);
+    if (st == OF2D_ERR_UNSUPPORTED) { engine_refused[L] = 1; return nullptr; }
+    of2d::check(st);
+    engines[L] = e;
+    return e;
+}
+
+// One level on the device-resident engine; returns false when the per-iteration path has to run instead.
+// mexPrintf output is reconstructed from the device traces in the reference's order: the Fluid time-step
+// line (OpticalFlowFluid.cpp:94), the Logger line when verbose (Logger.cpp:62-69), the regrid line
+// (ImageRegistrationFluid.cpp:110).
+bool ImageRegistration::run_level_on_engine(LoopKind kind, Motion* level_motion, const Image* ref, Image* mov, const int iterations, const dim d) {
+    if (!of2d_ctx_get_fast_math(of2d::context())) return false;
+    if (method == Regularisation::ThirionsDemons && method_params.size() > 5 && (int)method_params[5] != 0 && (int)method_params[5] != 1) return false;
+    of2d_engine* eng = engine_for_level(current_scale);
+    if (!eng) return false;
+    for (int refine = 0; refine < nrefine; refine++) {
+        RegistrationTrace::Level rec;
+        rec.scale = current_scale;
+        rec.refine = refine;
+        const int st = sizeof(of2d_real) == 8
+                           ? of2d_engine_refine_f64(eng, (const double*)ref->device(), (const double*)mov->device(), (double*)level_motion->device_mut(), iterations)
+                           : of2d_engine_refine_f32(eng, (const float*)ref->device(), (const float*)mov->device(), (float*)level_motion->device_mut(), iterations);
+        of2d::check(st);
+        int its = 0, nreg = 0;
+        of2d::check(of2d_engine_pair_result(eng, 0, &its, &nreg, nullptr));
+        rec.iterations = its;
+        std::vector<double> err((size_t)its), ma, dt, mj, rg;
+        of2d::check(of2d_engine_trace(eng, 0, 0, err.data(), its));
+        if (kind == LoopKind::Fluid) {
+            ma.resize((size_t)its); dt.resize((size_t)its); mj.resize((size_t)its); rg.resize((size_t)its);
+            of2d::check(of2d_engine_trace(eng, 0, 1, ma.data(), its));
+            of2d::check(of2d_engine_trace(eng, 0, 2, dt.data(), its));
+            of2d::check(of2d_engine_trace(eng, 0, 3, mj.data(), its));
+            of2d::check(of2d_engine_trace(eng, 0, 4, rg.data(), its));
+        }
+        for (int it = 0; it < its; it++) {
+            if (kind == LoopKind::Fluid) {
+                mexPrintf("Dumax: %.3f\tMaxabs increment: %.3f\t Timestep: %.3f\n", (of2d_real)0.65f, (of2d_real)ma[(size_t)it], (of2d_real)dt[(size_t)it]);
+                rec.fluid_maxabs.push_back(ma[(size_t)it]);
+                rec.fluid_dt.push_back(dt[(size_t)it]);
+            }
+            if (verbose == Verbose::On) mexPrintf("Iteration: %d\tError:%.4f\n", it, (of2d_real)err[(size_t)it]);
+            rec.error.push_back(err[(size_t)it]);
+            if (kind == LoopKind::Fluid && rg[(size_t)it] != 0) {
+                mexPrintf("Regridding on iteration: %d\tMin Jacobian: %.3f\n", it, (of2d_real)mj[(size_t)it]);
+                rec.regrid_iteration.push_back(it);
+                rec.regrid_minjac.push_back(mj[(size_t)it]);
+            }
+        }
+        trace.levels.push_back(rec);
+    }
+    return true;
+}
+
 void ImageRegistration::run_level(LoopKind kind, Motion* level_motion, const Image* ref, Image* mov, IterativeSolver* slv, const int iterations, const dim d) {
+    if (run_level_on_engine(kind, level_motion, ref, mov, iterations, d)) return;
     Image aux(d);
     Motion estimate(d);
     for (int refine = 0; refine < nrefine; refine++) {

@@ -64,6 +64,13 @@ protected:
     void run_level(LoopKind kind, Motion* motion, const Image* Iref, Image* Imov, IterativeSolver* solver, const int niter, const dim dimin);
     void release_solvers();
 
+    // device-resident iteration engine (include/of2d_cuda.h), one per pyramid level, created on first use.
+    // Used in the default (fast) mode; strict mode and parameter sets the engine refuses run the
+    // per-iteration loop through the solvers' get_update().
+    of2d_engine* engine_for_level(int level);
+    bool run_level_on_engine(LoopKind kind, Motion* motion, const Image* Iref, Image* Imov, const int niter, const dim dimin);
+    void release_engines();
+
     dim* dimin;
     int* sizein;
     int nscales;
@@ -78,6 +85,11 @@ protected:
     Verbose verbose;
     RegistrationTrace trace;
     int current_scale = 0;
+
+    Regularisation method;
+    std::vector<of2d_real> method_params;
+    std::vector<of2d_engine*> engines;        // [nscales + 1]
+    std::vector<char> engine_refused;         // [nscales + 1]
 };
 
 #endif
