@@ -318,6 +318,12 @@ def run_ours(args):
         return iters, ms, wall, launches, clocks
 
     iters, ms, wall, launches, clocks = timed(False)
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms": ms, "iterations": iters, "gpu_launches": int(launches)}), flush=True)
+        for s in sessions.values():
+            s.close()
+        return 0
     iters_e, ms_e, wall_e, _, _ = timed(True)
 
     def agg(ms_map, it_map):
@@ -399,7 +405,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--quick", action="store_true", help="timed region only (no e2e leg, kernel microbench or CPU baseline): for ncu launch lists")
+    ap.add_argument("--methods", default=",".join(list(METHODS)), help="comma-separated subset (profiling only; the default is the benchmark)")
     args = ap.parse_args()
+    METHODS[:] = [m for m in args.methods.split(",") if m]
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)

@@ -1,0 +1,725 @@
+// engine_kernels.cuh -- kernels of the iteration engine (included by engine.cu only).
+//
+// Shape shared by all of them: grid = (CTAs per pair, batch).  A CTA of 32 x 8 threads walks 32 x 32
+// pixel tiles of ITS pair in a grid-stride loop (x fastest, so neighbouring CTAs stream neighbouring
+// memory), reads the pair's control block once (one 64-byte load) and publishes ONE partial per
+// reduction, so the fixed cost of the device-side control protocol is paid per CTA, not per tile.
+// Arithmetic is written in the reference's operation order and the library is compiled with
+// -fmad=false, so every field value is bit-identical to the per-step (strict) path; only the reduction
+// order of the norms differs (double partial sums instead of one sequential float accumulator).
+#pragma once
+
+#include "device_math.cuh"
+#include "engine_ctl.cuh"
+
+namespace {
+
+constexpr int TX = 32, TY = 8, PY = 4;
+constexpr int TILE = 32;
+
+enum Buf { B_C0 = 0, B_C1 = 1, B_EST_CUR = 2, B_EST_NEXT = 3, B_CRES = 4, B_CTMP = 5, B_LVL_CUR = 6, B_LVL_NEXT = 7, B_ESTN = 8, B_EXT = 9 };
+enum Gate { G_NONE = 0, G_ACTIVE = 1, G_REGRID = 2 };
+
+template <class R>
+struct EngK {
+    int nx, ny, batch, P;          // P: pitch of the transposed layout (0 when unused)
+    size_t n;                      // nx * ny
+    size_t nT;                     // elements per pair in the transposed layout
+    PairCtl *ctl;
+    int *n_active;
+    double *partials;
+    size_t pstride;                // doubles per pair in `partials`
+    TraceDev tr;
+    vec2_t<R> *est[2];
+    vec2_t<R> *c[2];
+    vec2_t<R> *lvl[2];
+    vec2_t<R> *estN;
+    vec2_t<R> *ext;                // caller-provided field (set per launch)
+};
+
+// the integer head of PairCtl in registers (one L2 round trip)
+struct CtlHot {
+    int active, iter, niter;
+    unsigned flags;
+    int sel, regrid, skip, nsquares;
+    int nregrid, msel, overflow, vsel;
+    int prev_other;
+};
+__device__ __forceinline__ CtlHot load_ctl(const PairCtl *c) {
+    const int4 *p = reinterpret_cast<const int4 *>(c);
+    const int4 a = __ldcg(p), b = __ldcg(p + 1), d = __ldcg(p + 2), e = __ldcg(p + 3);
+    CtlHot h;
+    h.active = a.x; h.iter = a.y; h.niter = a.z; h.flags = (unsigned)a.w;
+    h.sel = b.x; h.regrid = b.y; h.skip = b.z; h.nsquares = b.w;
+    h.nregrid = d.x; h.msel = d.y; h.overflow = d.z; h.vsel = d.w;
+    h.prev_other = e.x;
+    return h;
+}
+static_assert(offsetof(PairCtl, sel) == 16 && offsetof(PairCtl, nregrid) == 32 && offsetof(PairCtl, prev_other) == 48, "CtlHot mirrors the head of PairCtl");
+
+template <class R>
+__device__ __forceinline__ vec2_t<R> *pick(const EngK<R> &K, int which, const CtlHot &h, int pair, bool transposed = false) {
+    const size_t off = (size_t)pair * (transposed ? K.nT : K.n);
+    switch (which) {
+        case B_C0: return K.c[0] + off;
+        case B_C1: return K.c[1] + off;
+        case B_EST_CUR: return K.est[h.sel] + off;
+        case B_EST_NEXT: return K.est[h.sel ^ 1] + off;
+        case B_CRES: return K.c[(h.nsquares & 1) ? 0 : 1] + off;
+        case B_CTMP: return K.c[(h.nsquares & 1) ? 1 : 0] + off;
+        case B_LVL_CUR: return K.lvl[h.msel] + off;
+        case B_LVL_NEXT: return K.lvl[h.msel ^ 1] + off;
+        case B_ESTN: return K.estN + off;
+        default: return K.ext + off;
+    }
+}
+
+__device__ __forceinline__ bool gate_open(const CtlHot &h, int gate) {
+    if (gate == G_ACTIVE) return h.active != 0;
+    if (gate == G_REGRID) return h.regrid != 0;
+    return true;
+}
+
+// Motion::norm addend (Motion.cpp:45).  The reference takes the square root in double of float data;
+// the fp32 build of the engine takes it in float (1 ulp of a term that is then averaged over all pixels).
+__device__ __forceinline__ double norm_term(float2 v) { return (double)sqrtf(v.x * v.x + v.y * v.y); }
+__device__ __forceinline__ double norm_term(double2 v) { return sqrt(v.x * v.x + v.y * v.y); }
+
+struct TileWalk {
+    int tiles_x, ntiles;
+    __device__ __forceinline__ TileWalk(int fast_extent, int slow_extent) {
+        tiles_x = (fast_extent + TILE - 1) / TILE;
+        ntiles = tiles_x * ((slow_extent + TILE - 1) / TILE);
+    }
+};
+
+// Logger epilogue shared by the kernels that produce the next estimate
+template <class R>
+__device__ __forceinline__ void logger_epilogue(const EngK<R> &K, PairCtl *c, int pair, double sd, double sp) {
+    block_sum2(sd, sp);
+    const double vals[2] = {sd, sp};
+    double *part = K.partials + (size_t)pair * K.pstride;
+    if (publish_partials<2>(vals, part, &c->ticket[0], gridDim.x, blockIdx.x)) {
+        double out[2];
+        reduce_partials<2>(part, gridDim.x, out, 0u, 0u);
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            c->sel ^= 1;
+            finalize_logger<R>(c, K.tr, pair, out[0], out[1], (unsigned)K.n, K.n_active);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// control
+// ---------------------------------------------------------------------------------------------
+__global__ void k_ctl_begin(PairCtl *ctl, int batch, int niter, int *n_active) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) *n_active = niter > 0 ? batch : 0;
+    if (p >= batch) return;
+    PairCtl *c = ctl + p;
+    c->active = niter > 0;
+    c->iter = 0;
+    c->niter = niter;
+    c->sel = 0;
+    c->regrid = 0;
+    c->skip = 0;
+    c->nsquares = 0;
+    c->nregrid = 0;
+    c->msel = 0;
+    c->overflow = 0;
+    c->prev_other = 0;
+    for (int k = 0; k < 4; k++) c->ticket[k] = 0u;
+    c->err = 0.0;
+}
+
+__global__ void k_regrid_commit(PairCtl *ctl, int batch) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    PairCtl *c = ctl + p;
+    if (!c->regrid) return;
+    c->msel ^= 1;
+    c->sel ^= 1;          // the zeroed buffer becomes the running estimate; the other one is Logger's prev
+    c->prev_other = 1;
+    c->regrid = 0;
+    c->nregrid += 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Horn-Schunck Jacobi step + Logger (OpticalFlowDiffusion.cpp:19-84, Logger.cpp:32-51)
+// ---------------------------------------------------------------------------------------------
+template <class R>
+__global__ void __launch_bounds__(TX *TY) k_hs_iter(EngK<R> K, const vec2_t<R> *__restrict__ gradI_all, const R *__restrict__ It_all, R alphasq) {
+    const int pair = blockIdx.y;
+    PairCtl *c = K.ctl + pair;
+    const CtlHot h = load_ctl(c);
+    if (!h.active) return;
+    const int nx = K.nx, ny = K.ny;
+    const vec2_t<R> *__restrict__ u = pick(K, B_EST_CUR, h, pair);
+    vec2_t<R> *__restrict__ un = pick(K, B_EST_NEXT, h, pair);
+    const vec2_t<R> *__restrict__ gradI = gradI_all + (size_t)pair * K.n;
+    const R *__restrict__ It = It_all + (size_t)pair * K.n;
+    const TileWalk T(nx, ny);
+    double sd = 0.0, sp = 0.0;
+    bool divzero = false;
+    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
+        const int i = (tile % T.tiles_x) * TILE + threadIdx.x;
+        const int jb = (tile / T.tiles_x) * TILE + threadIdx.y;
+        if (i >= nx) continue;
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int j = jb + p * TY;
+            if (j < ny) {
+                const int idx = i + j * nx;
+                const vec2_t<R> old = u[idx];
+                vec2_t<R> q;
+                if (i == 0 || i == nx - 1 || j == 0 || j == ny - 1) {
+                    q = mk2<R>((R)0.0f, (R)0.0f);
+                } else {   // gradients.h:78
+                    const vec2_t<R> a = u[idx - 1], b = u[idx + 1], cc = u[idx - nx], d = u[idx + nx];
+                    q = mk2<R>((((a.x + b.x) + cc.x) + d.x) / (R)4.0f, (((a.y + b.y) + cc.y) + d.y) / (R)4.0f);
+                }
+                const vec2_t<R> dI = gradI[idx];
+                const vec2_t<R> f = lssd_force<R>(dI, It[idx], q);
+                const R den = alphasq + dI.x * dI.x + dI.y * dI.y;
+                vec2_t<R> o;
+                if (den == 0) { divzero = true; o = q; }
+                else o = mk2<R>(q.x - f.x / den, q.y - f.y / den);
+                un[idx] = o;
+                sd += norm_term(mk2<R>(o.x - old.x, o.y - old.y));
+                sp += norm_term(old);
+            }
+        }
+    }
+    if (divzero) atomicOr(&c->flags, OF2D_FLAG_DIVZERO);
+    logger_epilogue<R>(K, c, pair, sd, sp);
+}
+
+// ---------------------------------------------------------------------------------------------
+// gated primitives of the loops
+// ---------------------------------------------------------------------------------------------
+template <class R>
+__global__ void __launch_bounds__(TX *TY) k_e_warp(EngK<R> K, int gate, const R *__restrict__ src_all, int u_buf, R *__restrict__ dst_all) {
+    const int pair = blockIdx.y;
+    const CtlHot h = load_ctl(K.ctl + pair);
+    if (!gate_open(h, gate)) return;
+    const int nx = K.nx, ny = K.ny;
+    const R *__restrict__ src = src_all + (size_t)pair * K.n;
+    R *__restrict__ dst = dst_all + (size_t)pair * K.n;
+    const vec2_t<R> *__restrict__ u = pick(K, u_buf, h, pair);
+    const TileWalk T(nx, ny);
+    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
+        const int i = (tile % T.tiles_x) * TILE + threadIdx.x;
+        const int jb = (tile / T.tiles_x) * TILE + threadIdx.y;
+        if (i >= nx) continue;
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int j = jb + p * TY;
+            if (j < ny) {
+                const int idx = i + j * nx;
+                dst[idx] = warp_pixel<R>(src, nx, ny, i, j, u[idx], src[idx]);
+            }
+        }
+    }
+}
+
+// out = v + u o (id + v)   (Motion::accumulate, Motion.cpp:113-178); add_only: out = u + v (Field::operator+=)
+template <class R>
+__global__ void __launch_bounds__(TX *TY) k_e_compose(EngK<R> K, int gate, int u_buf, int v_buf, int out_buf, int add_only) {
+    const int pair = blockIdx.y;
+    const CtlHot h = load_ctl(K.ctl + pair);
+    if (!gate_open(h, gate)) return;
+    const int nx = K.nx, ny = K.ny;
+    const vec2_t<R> *__restrict__ u = pick(K, u_buf, h, pair);
+    const vec2_t<R> *__restrict__ v = pick(K, v_buf, h, pair);
+    vec2_t<R> *__restrict__ out = pick(K, out_buf, h, pair);
+    const TileWalk T(nx, ny);
+    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
+        const int i = (tile % T.tiles_x) * TILE + threadIdx.x;
+        const int jb = (tile / T.tiles_x) * TILE + threadIdx.y;
+        if (i >= nx) continue;
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int j = jb + p * TY;
+            if (j < ny) {
+                const int idx = i + j * nx;
+                const vec2_t<R> vv = v[idx], uu = u[idx];
+                out[idx] = add_only ? mk2<R>(uu.x + vv.x, uu.y + vv.y) : compose_pixel<R>(u, nx, ny, i, j, vv, uu);
+            }
+        }
+    }
+}
+
+// one squaring of Motion::exp (Motion.cpp:262-274): dst = w + w o (id + w), w = scale * src (scale only at s == 0;
+// a power of two, so scaling the taps on the fly is exact)
+template <class R>
+__global__ void __launch_bounds__(TX *TY) k_e_square(EngK<R> K, int s) {
+    const int pair = blockIdx.y;
+    const PairCtl *c = K.ctl + pair;
+    const CtlHot h = load_ctl(c);
+    if (!h.active || s >= h.nsquares) return;
+    const int nx = K.nx, ny = K.ny;
+    const size_t off = (size_t)pair * K.n;
+    const vec2_t<R> *__restrict__ src = K.c[(s & 1) ? 0 : 1] + off;
+    vec2_t<R> *__restrict__ dst = K.c[(s & 1) ? 1 : 0] + off;
+    const R sc = s == 0 ? (R)__ldcg(&c->scale) : (R)1;
+    const TileWalk T(nx, ny);
+    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
+        const int i = (tile % T.tiles_x) * TILE + threadIdx.x;
+        const int jb = (tile / T.tiles_x) * TILE + threadIdx.y;
+        if (i >= nx) continue;
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int j = jb + p * TY;
+            if (j >= ny) continue;
+            const int idx = i + j * nx;
+            vec2_t<R> v = src[idx];
+            v.x *= sc; v.y *= sc;
+            const Bilin<R> b = bilin_setup<R>(i, j, v.x, v.y, nx, ny);
+            vec2_t<R> o = v;   // out of bounds: keeps the (scaled) value
+            if (b.inside) {
+                const R one = (R)1;
+                vec2_t<R> t = src[b.idxO];
+                R vx = (t.x * sc) * (one - b.fx) * (one - b.fy), vy = (t.y * sc) * (one - b.fx) * (one - b.fy);
+                R weight = (one - b.fx) * (one - b.fy);
+                if (b.hx) { t = src[b.idxO + 1]; vx += (t.x * sc) * b.fx * (one - b.fy); vy += (t.y * sc) * b.fx * (one - b.fy); weight += b.fx * (one - b.fy); }
+                if (b.hy) { t = src[b.idxO + nx]; vx += (t.x * sc) * (one - b.fx) * b.fy; vy += (t.y * sc) * (one - b.fx) * b.fy; weight += (one - b.fx) * b.fy; }
+                if (b.hx && b.hy) { t = src[b.idxO + 1 + nx]; vx += (t.x * sc) * b.fx * b.fy; vy += (t.y * sc) * b.fx * b.fy; weight += b.fx * b.fy; }
+                if (weight != 0) o = mk2<R>(v.x + vx / weight, v.y + vy / weight);
+            }
+            dst[idx] = o;
+        }
+    }
+}
+
+// Demons force: warp + derivatives + demons_iteration (DemonsThirions.cpp:18-27, Demons.cpp:34-63).
+// The warped image of a 32 x 32 tile (+1 halo) is evaluated once into shared memory.
+template <class R>
+__global__ void __launch_bounds__(TX *TY) k_e_demons_force(EngK<R> K, const R *__restrict__ Iref_all, const R *__restrict__ Imov_all, R sigma_isq, R sigma_xsq) {
+    __shared__ R sw[TILE + 2][TILE + 2 + 1];
+    const int pair = blockIdx.y;
+    PairCtl *c = K.ctl + pair;
+    const CtlHot h = load_ctl(c);
+    if (!h.active) return;
+    const int nx = K.nx, ny = K.ny;
+    const R *__restrict__ Iref = Iref_all + (size_t)pair * K.n;
+    const R *__restrict__ Imov = Imov_all + (size_t)pair * K.n;
+    const vec2_t<R> *__restrict__ u = pick(K, B_EST_CUR, h, pair);
+    vec2_t<R> *__restrict__ corr = K.c[0] + (size_t)pair * K.n;
+    const int tid = threadIdx.x + threadIdx.y * TX;
+    const TileWalk T(nx, ny);
+    bool divzero = false;
+    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
+        const int i0 = (tile % T.tiles_x) * TILE, j0 = (tile / T.tiles_x) * TILE;
+        __syncthreads();
+        for (int e = tid; e < (TILE + 2) * (TILE + 2); e += TX * TY) {
+            const int r = e / (TILE + 2), cc = e - r * (TILE + 2);
+            const int i = i0 + cc - 1, j = j0 + r - 1;
+            R w = (R)0;
+            if (i >= 0 && i < nx && j >= 0 && j < ny) { const int idx = i + j * nx; w = warp_pixel<R>(Imov, nx, ny, i, j, u[idx], Imov[idx]); }
+            sw[r][cc] = w;
+        }
+        __syncthreads();
+        const int i = i0 + threadIdx.x;
+        if (i >= nx) continue;
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int jl = threadIdx.y + p * TY, j = j0 + jl;
+            if (j >= ny) continue;
+            const int idx = i + j * nx;
+            const int r = jl + 1, cc = threadIdx.x + 1;
+            const R ce = sw[r][cc];
+            R gx, gy;   // gradients.h:9-32 on the warped image
+            if (i == 0) gx = sw[r][cc + 1] - ce;
+            else if (i == nx - 1) gx = ce - sw[r][cc - 1];
+            else gx = (sw[r][cc + 1] - sw[r][cc - 1]) / (R)2.0f;
+            if (j == 0) gy = sw[r + 1][cc] - ce;
+            else if (j == ny - 1) gy = ce - sw[r - 1][cc];
+            else gy = (sw[r + 1][cc] - sw[r - 1][cc]) / (R)2.0f;
+            const R It = ce - Iref[idx];
+            const R den = gx * gx + gy * gy + It * It * sigma_isq / sigma_xsq;
+            if (den == 0) { divzero = true; corr[idx] = mk2<R>((R)0, (R)0); continue; }
+            corr[idx] = mk2<R>(gx * It / den * (R)-1, gy * It / den * (R)-1);
+        }
+    }
+    if (divzero) atomicOr(&c->flags, OF2D_FLAG_DIVZERO);
+}
+
+// ---------------------------------------------------------------------------------------------
+// convolution (Field.tpp:210-269) on a shared-memory tile.  The bounds test of the reference is on
+// the LINEAR index, so a tile is simply rows of the flattened array: element (row r, column c) of the
+// halo is in[r*nx + c] whenever that flat index is inside [0, n) -- columns outside [0, nx) land in
+// the neighbouring row exactly as in the reference.  Each thread produces 4 vertically adjacent
+// outputs from a sliding column window; per output the taps are accumulated in the reference's order
+// (ii outer, jj inner, unfused multiply-add), so the result is bit-identical.
+//   EPI 0: none   EPI 1: Logger epilogue (result is the next estimate)   EPI 2: maxabs epilogue
+//   KW > 0: odd kernel width known at compile time; KW == 0: any width (slower)
+// ---------------------------------------------------------------------------------------------
+constexpr int kConvMaxW = 15;
+template <class R>
+struct ConvW {
+    R w[kConvMaxW * kConvMaxW];   // (real) weights, [kw*kh] column-major as Kernel::get_kernel()
+    const double *taps_d;         // the same weights in double (renormalisation of truncated windows)
+    double full_weight;           // sum over the visiting order
+    int kw;
+};
+
+template <class R, int EPI, int KW>
+__global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int dst_buf, const __grid_constant__ ConvW<R> W, int nsq_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int pair = blockIdx.y;
+    PairCtl *c = K.ctl + pair;
+    const CtlHot h = load_ctl(c);
+    if (!h.active) return;
+    const int nx = K.nx, ny = K.ny;
+    const long n = (long)K.n;
+    const vec2_t<R> *__restrict__ in = pick(K, src_buf, h, pair);
+    vec2_t<R> *__restrict__ out = pick(K, dst_buf, h, pair);
+    const vec2_t<R> *__restrict__ est_cur = pick(K, B_EST_CUR, h, pair);
+    const int kw = KW > 0 ? KW : W.kw;
+    const int cx = (kw - 1) / 2;
+    const int SW = TILE + 2 * cx, SH = TILE + 2 * cx;
+    vec2_t<R> *tile_s = reinterpret_cast<vec2_t<R> *>(smem_raw);   // [SH][SW]
+    const int tid = threadIdx.x + threadIdx.y * TX;
+    const TileWalk T(nx, ny);
+    double sd = 0.0, sp = 0.0;
+    R mx = (R)0;
+    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
+        const int i0 = (tile % T.tiles_x) * TILE, j0 = (tile / T.tiles_x) * TILE;
+        __syncthreads();
+        for (int e = tid; e < SH * SW; e += TX * TY) {
+            const int r = e / SW, cc = e - r * SW;
+            const long lin = (long)(j0 + r - cx) * nx + (i0 + cc - cx);
+            vec2_t<R> v = mk2<R>((R)0, (R)0);
+            if (lin >= 0 && lin < n) v = in[lin];
+            tile_s[e] = v;
+        }
+        __syncthreads();
+        const int i = i0 + threadIdx.x;
+        const int jl0 = 4 * threadIdx.y;
+        // every tap of every pixel of the tile inside [0, n)?  (first / last flat index of the tile's windows)
+        const long lo = (long)(j0 - cx) * nx + (i0 - cx), hi = (long)(min(j0 + TILE, ny) - 1 + cx) * nx + (min(i0 + TILE, nx) - 1 + cx);
+        const bool tile_interior = lo >= 0 && hi < n;
+        vec2_t<R> o[4];
+        if (KW > 0 && tile_interior) {
+            R ax[4], ay[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { ax[q] = (R)0; ay[q] = (R)0; }
+#pragma unroll
+            for (int ii = 0; ii < KW; ii++) {
+                vec2_t<R> col[4 + (KW > 0 ? KW : 1) - 1];
+#pragma unroll
+                for (int r = 0; r < 4 + KW - 1; r++) col[r] = tile_s[(jl0 + r) * SW + threadIdx.x + ii];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+#pragma unroll
+                    for (int jj = 0; jj < KW; jj++) {
+                        const R t = W.w[ii + jj * KW];
+                        ax[q] = ax[q] + col[q + jj].x * t;
+                        ay[q] = ay[q] + col[q + jj].y * t;
+                    }
+                }
+            }
+            const R wgt = (R)W.full_weight;
+#pragma unroll
+            for (int q = 0; q < 4; q++) o[q] = W.full_weight != 0 ? mk2<R>(ax[q] / wgt, ay[q] / wgt) : tile_s[(jl0 + q + cx) * SW + threadIdx.x + cx];
+        } else {
+#pragma unroll 1
+            for (int q = 0; q < 4; q++) {
+                const int j = j0 + jl0 + q;
+                const long idx = i + (long)j * nx;
+                R ax = (R)0, ay = (R)0;
+                double weight = 0.0;
+                for (int ii = -cx; ii <= cx; ii++) {
+                    for (int jj = -cx; jj <= cx; jj++) {
+                        const long lin = idx + ii + (long)jj * nx;
+                        if (lin < 0 || lin >= n) continue;
+                        const int ik = (ii + cx) + (jj + cx) * kw;
+                        weight += W.taps_d[ik];
+                        const vec2_t<R> f = tile_s[(jl0 + q + jj + cx) * SW + (threadIdx.x + ii + cx)];
+                        const R t = W.w[ik];
+                        ax = ax + f.x * t;
+                        ay = ay + f.y * t;
+                    }
+                }
+                if (weight != 0) { const R wg = (R)weight; o[q] = mk2<R>(ax / wg, ay / wg); }
+                else o[q] = tile_s[(jl0 + q + cx) * SW + threadIdx.x + cx];
+            }
+        }
+        if (i < nx) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int j = j0 + jl0 + q;
+                if (j >= ny) continue;
+                const long idx = i + (long)j * nx;
+                out[idx] = o[q];
+                if (EPI == 1) {
+                    const vec2_t<R> old = est_cur[idx];
+                    sd += norm_term(mk2<R>(o[q].x - old.x, o[q].y - old.y));
+                    sp += norm_term(old);
+                } else if (EPI == 2) {
+                    const R s = maxabs_term<R>(o[q]);
+                    mx = mx < s ? s : mx;
+                }
+            }
+        }
+    }
+    if (EPI == 0) return;
+    if (EPI == 1) {
+        logger_epilogue<R>(K, c, pair, sd, sp);
+    } else {
+        mx = block_extreme<R, true>(mx);
+        const double vals[1] = {(double)mx};
+        double *part = K.partials + (size_t)pair * K.pstride;
+        if (publish_partials<1>(vals, part, &c->ticket[1], gridDim.x, blockIdx.x)) {
+            double o1[1];
+            reduce_partials<1>(part, gridDim.x, o1, 1u, 0u);
+            if (tid == 0) {   // Motion::exp, Motion.cpp:253-260
+                const R ma = sizeof(R) == 4 ? (R)sqrtf((float)o1[0]) : (R)sqrt(o1[0]);
+                int nsq = 0;
+                if (ma != 0) {
+                    nsq = sizeof(R) == 4 ? (int)ceilf(1 + log2f((float)ma)) : (int)ceil(1 + log2((double)ma));
+                    if (nsq < 0) nsq = 0;
+                }
+                if (nsq > nsq_cap) { c->overflow = 1; nsq = nsq_cap; }
+                c->nsquares = nsq;
+                c->maxabs = (double)ma;
+                c->scale = (double)(R)pow(2.0, (double)-nsq);
+                const int it = c->iter;
+                if (it < K.tr.cap) { K.tr.nsq[(size_t)pair * K.tr.cap + it] = nsq; K.tr.maxabs[(size_t)pair * K.tr.cap + it] = (double)ma; }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// derivatives (IterativeSolver.cpp:22-56), normal and transposed output
+// ---------------------------------------------------------------------------------------------
+template <class R>
+__global__ void __launch_bounds__(TX *TY) k_e_derivatives(EngK<R> K, int gate, const R *__restrict__ Iref_all, const R *__restrict__ Imov_all,
+                                                          vec2_t<R> *__restrict__ gradI_all, R *__restrict__ It_all, int transposed) {
+    __shared__ vec2_t<R> sg[TILE][TILE + 1];
+    __shared__ R st[TILE][TILE + 1];
+    const int pair = blockIdx.y;
+    const CtlHot h = load_ctl(K.ctl + pair);
+    if (!gate_open(h, gate)) return;
+    const int nx = K.nx, ny = K.ny;
+    const R *__restrict__ Iref = Iref_all + (size_t)pair * K.n;
+    const R *__restrict__ Imov = Imov_all + (size_t)pair * K.n;
+    const TileWalk T(nx, ny);
+    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
+        const int i0 = (tile % T.tiles_x) * TILE, j0 = (tile / T.tiles_x) * TILE;
+        const int i = i0 + threadIdx.x;
+        if (transposed) __syncthreads();
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int jl = threadIdx.y + p * TY, j = j0 + jl;
+            if (i < nx && j < ny) {
+                const int idx = i + j * nx;
+                const vec2_t<R> g = mk2<R>(partial_x<R>(Imov, idx, i, nx), partial_y<R>(Imov, idx, j, nx, ny));
+                const R t = Imov[idx] - Iref[idx];
+                if (!transposed) {
+                    gradI_all[(size_t)pair * K.n + idx] = g;
+                    It_all[(size_t)pair * K.n + idx] = t;
+                } else {
+                    sg[jl][threadIdx.x] = g;
+                    st[jl][threadIdx.x] = t;
+                }
+            }
+        }
+        if (!transposed) continue;
+        __syncthreads();
+        const int jt = j0 + threadIdx.x;   // fast thread index runs along j now
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int il = threadIdx.y + p * TY, it = i0 + il;
+            if (it < nx && jt < ny) {
+                const size_t o = (size_t)pair * K.nT + (size_t)it * K.P + jt;
+                gradI_all[o] = sg[threadIdx.x][il];
+                It_all[o] = st[threadIdx.x][il];
+            }
+        }
+    }
+}
+
+// transposed (i*P + j) -> normal (i + j*nx) copy of a vec2 field
+template <class R>
+__global__ void __launch_bounds__(TX *TY) k_e_untranspose(EngK<R> K, int gate, int src_buf, int dst_buf) {
+    __shared__ vec2_t<R> s[TILE][TILE + 1];
+    const int pair = blockIdx.y;
+    const CtlHot h = load_ctl(K.ctl + pair);
+    if (!gate_open(h, gate)) return;
+    const int nx = K.nx, ny = K.ny;
+    const vec2_t<R> *__restrict__ src = pick(K, src_buf, h, pair, true);
+    vec2_t<R> *__restrict__ dst = pick(K, dst_buf, h, pair, false);
+    const TileWalk T(nx, ny);
+    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
+        const int i0 = (tile % T.tiles_x) * TILE, j0 = (tile / T.tiles_x) * TILE;
+        __syncthreads();
+        const int jt = j0 + threadIdx.x;
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int il = threadIdx.y + p * TY, it = i0 + il;
+            if (it < nx && jt < ny) s[il][threadIdx.x] = src[(size_t)it * K.P + jt];
+        }
+        __syncthreads();
+        const int i = i0 + threadIdx.x;
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int jl = threadIdx.y + p * TY, j = j0 + jl;
+            if (i < nx && j < ny) dst[(size_t)i + (size_t)j * nx] = s[threadIdx.x][jl];
+        }
+    }
+}
+
+template <class R>
+__global__ void k_e_zero(EngK<R> K, int gate, int buf, int transposed) {
+    const int pair = blockIdx.y;
+    const CtlHot h = load_ctl(K.ctl + pair);
+    if (!gate_open(h, gate)) return;
+    vec2_t<R> *p = pick(K, buf, h, pair, transposed != 0);
+    const size_t cnt = transposed ? K.nT : K.n;
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < cnt; k += (size_t)gridDim.x * blockDim.x) p[k] = mk2<R>((R)0, (R)0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fluid in the transposed layout (element (i,j) at i*P + j; threadIdx.x runs along j)
+// ---------------------------------------------------------------------------------------------
+template <class R>
+__device__ __forceinline__ vec2_t<R> tdx(const vec2_t<R> *__restrict__ f, size_t o, int i, int nx, int P) {   // d/dx, gradients.h:9-19
+    if (i == 0) { const vec2_t<R> a = f[o + P], b = f[o]; return mk2<R>(a.x - b.x, a.y - b.y); }
+    if (i == nx - 1) { const vec2_t<R> a = f[o], b = f[o - P]; return mk2<R>(a.x - b.x, a.y - b.y); }
+    const vec2_t<R> a = f[o + P], b = f[o - P];
+    return mk2<R>((a.x - b.x) / (R)2.0f, (a.y - b.y) / (R)2.0f);
+}
+template <class R>
+__device__ __forceinline__ vec2_t<R> tdy(const vec2_t<R> *__restrict__ f, size_t o, int j, int ny) {          // d/dy, gradients.h:22-32
+    if (j == 0) { const vec2_t<R> a = f[o + 1], b = f[o]; return mk2<R>(a.x - b.x, a.y - b.y); }
+    if (j == ny - 1) { const vec2_t<R> a = f[o], b = f[o - 1]; return mk2<R>(a.x - b.x, a.y - b.y); }
+    const vec2_t<R> a = f[o + 1], b = f[o - 1];
+    return mk2<R>((a.x - b.x) / (R)2.0f, (a.y - b.y) / (R)2.0f);
+}
+
+// increment R = v - du/dx v.x - du/dy v.y (OpticalFlowFluid.cpp:60-90) + time step (:92-95, :135-137)
+template <class R>
+__global__ void __launch_bounds__(TX *TY) k_fl_increment(EngK<R> K, vec2_t<R> *const vel0, vec2_t<R> *const vel1, vec2_t<R> *__restrict__ incr_all) {
+    const int pair = blockIdx.y;
+    PairCtl *c = K.ctl + pair;
+    const CtlHot h = load_ctl(c);
+    if (!h.active) return;
+    const int nx = K.nx, ny = K.ny, P = K.P;
+    const vec2_t<R> *__restrict__ u = pick(K, B_EST_CUR, h, pair, true);
+    const vec2_t<R> *__restrict__ vel = (h.vsel ? vel0 : vel1) + (size_t)pair * K.nT;   // the buffer the sweep just wrote
+    vec2_t<R> *__restrict__ incr = incr_all + (size_t)pair * K.nT;
+    const TileWalk T(ny, nx);
+    R m = (R)0;
+    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
+        const int j = (tile % T.tiles_x) * TILE + threadIdx.x;
+        const int ib = (tile / T.tiles_x) * TILE + threadIdx.y;
+        if (j >= ny) continue;
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int i = ib + p * TY;
+            if (i < nx) {
+                const size_t o = (size_t)i * P + j;
+                const vec2_t<R> v = vel[o];
+                const vec2_t<R> dudx = tdx<R>(u, o, i, nx, P);
+                const vec2_t<R> dudy = tdy<R>(u, o, j, ny);
+                const vec2_t<R> r = mk2<R>(v.x - dudx.x * v.x - dudy.x * v.y, v.y - dudx.y * v.x - dudy.y * v.y);
+                incr[o] = r;
+                const R s = maxabs_term<R>(r);
+                m = m < s ? s : m;
+            }
+        }
+    }
+    m = block_extreme<R, true>(m);
+    const double vals[1] = {(double)m};
+    double *part = K.partials + (size_t)pair * K.pstride;
+    if (publish_partials<1>(vals, part, &c->ticket[1], gridDim.x, blockIdx.x)) {
+        double o1[1];
+        reduce_partials<1>(part, gridDim.x, o1, 1u, 0u);
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            const R maxabs = sizeof(R) == 4 ? (R)sqrtf((float)o1[0]) : (R)sqrt(o1[0]);   // Motion.cpp:57
+            const R dt = (R)0.65f / maxabs;                                              // OpticalFlowFluid.h:32, .cpp:93
+            c->maxabs = (double)maxabs;
+            c->dt = (double)dt;
+            c->skip = dt >= (R)65.0f;                                                    // .cpp:135-137
+            c->vsel ^= 1;
+            const int it = c->iter;
+            if (it < K.tr.cap) { K.tr.maxabs[(size_t)pair * K.tr.cap + it] = (double)maxabs; K.tr.dt[(size_t)pair * K.tr.cap + it] = (double)dt; }
+        }
+    }
+}
+
+// integrate u += dt R (OpticalFlowFluid.cpp:97-121) + Logger + Jacobian minimum of the new field
+// (Image.cpp:189-218, :96-104) + break / regrid decisions (ImageRegistrationFluid.cpp:99-124)
+template <class R>
+__global__ void __launch_bounds__(TX *TY) k_fl_integrate(EngK<R> K, const vec2_t<R> *__restrict__ incr_all) {
+    const int pair = blockIdx.y;
+    PairCtl *c = K.ctl + pair;
+    const CtlHot h = load_ctl(c);
+    if (!h.active) return;
+    const int nx = K.nx, ny = K.ny, P = K.P;
+    const vec2_t<R> *__restrict__ u = pick(K, B_EST_CUR, h, pair, true);
+    vec2_t<R> *un = pick(K, B_EST_NEXT, h, pair, true);
+    const vec2_t<R> *__restrict__ incr = incr_all + (size_t)pair * K.nT;
+    const bool skip = h.skip != 0;
+    const bool prev_other = h.prev_other != 0;
+    const R dt = (R)__ldcg(&c->dt);
+    auto unew_at = [&](size_t o) -> vec2_t<R> {
+        vec2_t<R> v = u[o];
+        if (!skip) { const vec2_t<R> r = incr[o]; v.x += r.x * dt; v.y += r.y * dt; }
+        return v;
+    };
+    const TileWalk T(ny, nx);
+    double sd = 0.0, sp = 0.0;
+    R mj = (R)INFINITY;
+    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
+        const int j = (tile % T.tiles_x) * TILE + threadIdx.x;
+        const int ib = (tile / T.tiles_x) * TILE + threadIdx.y;
+        if (j >= ny) continue;
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int i = ib + p * TY;
+            if (i >= nx) continue;
+            const size_t o = (size_t)i * P + j;
+            const vec2_t<R> nv = unew_at(o);
+            const vec2_t<R> prev = prev_other ? un[o] : u[o];   // after a regrid Logger's prev is the pre-reset estimate
+            sd += norm_term(mk2<R>(nv.x - prev.x, nv.y - prev.y));
+            sp += norm_term(prev);
+            // Jacobian of the new field (one-sided at the edges, gradients.h:9-32)
+            vec2_t<R> dx, dy;
+            if (i == 0) { const vec2_t<R> a = unew_at(o + P); dx = mk2<R>(a.x - nv.x, a.y - nv.y); }
+            else if (i == nx - 1) { const vec2_t<R> b = unew_at(o - P); dx = mk2<R>(nv.x - b.x, nv.y - b.y); }
+            else { const vec2_t<R> a = unew_at(o + P), b = unew_at(o - P); dx = mk2<R>((a.x - b.x) / (R)2.0f, (a.y - b.y) / (R)2.0f); }
+            if (j == 0) { const vec2_t<R> a = unew_at(o + 1); dy = mk2<R>(a.x - nv.x, a.y - nv.y); }
+            else if (j == ny - 1) { const vec2_t<R> b = unew_at(o - 1); dy = mk2<R>(nv.x - b.x, nv.y - b.y); }
+            else { const vec2_t<R> a = unew_at(o + 1), b = unew_at(o - 1); dy = mk2<R>((a.x - b.x) / (R)2.0f, (a.y - b.y) / (R)2.0f); }
+            const R J = ((R)1.0f + dx.x) * ((R)1.0f + dy.y) - dx.y * dy.x;
+            mj = J < mj ? J : mj;
+            un[o] = nv;
+        }
+    }
+    block_sum2(sd, sp);
+    mj = block_extreme<R, false>(mj);
+    const double vals[3] = {sd, sp, (double)mj};
+    double *part = K.partials + (size_t)pair * K.pstride;
+    if (publish_partials<3>(vals, part, &c->ticket[0], gridDim.x, blockIdx.x)) {
+        double o3[3];
+        reduce_partials<3>(part, gridDim.x, o3, 0u, 4u);
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            const int it = c->iter;
+            c->sel ^= 1;
+            c->prev_other = 0;
+            finalize_logger<R>(c, K.tr, pair, o3[0], o3[1], (unsigned)K.n, K.n_active);
+            const bool brk = (R)c->err < (R)0.001f && it > 1;
+            const R minjac = (R)o3[2];
+            int rg = 0;
+            if (!brk && minjac < (R)0.5) rg = 1;
+            c->regrid = rg;
+            c->minjac = (double)minjac;
+            if (it < K.tr.cap) { K.tr.regrid[(size_t)pair * K.tr.cap + it] = rg; K.tr.minjac[(size_t)pair * K.tr.cap + it] = (double)minjac; }
+        }
+    }
+}
+
+}  // namespace
