@@ -331,6 +331,12 @@ __global__ void __launch_bounds__(FFT_THREADS) k_dct_lines(int nlines, int n, si
         line[(size_t)m * elem_stride] = (double)x[kind == 2 ? m : dct3_store_slot<S>(m, T)].x;
 }
 
+}  // namespace
+
+#include "dct_fast.cuh"
+
+namespace {
+
 // ---- host-side tables ---------------------------------------------------------------------------
 const double kPi = 3.14159265358979323846264338327950288;
 
@@ -391,6 +397,32 @@ int curvature_step_impl(of2d_curvature_plan *P, const R *u, R *unew, const R *gr
     const int batch = H.enabled ? P->batch : 1;
     const int nx = P->nx, ny = P->ny;
     cplx_t<S> *spec = (cplx_t<S> *)P->d_spec;
+    const R fourN = (R)4.0f * (R)(unsigned)(nx * ny);
+    constexpr int LPC = 2;
+    const bool fast = P->Tx.pow2 && P->Ty.pow2 && P->Tx.log2n >= 6 && P->Ty.log2n >= 6 && sizeof(double2) * (size_t)nx * LPC <= kMaxSmem &&
+                      sizeof(double2) * (size_t)ny <= kMaxSmem;
+    if (fast) {   // dct_fast.cuh: transposed spectrum, radix-8/4 FFT
+        const size_t smem_r = sizeof(double2) * (size_t)nx * LPC, smem_c = sizeof(double2) * (size_t)ny;
+        static size_t cfg_r = 0, cfg_c = 0;
+        if (smem_r > cfg_r) {
+            OF2D_CUDA_TRY(cudaFuncSetAttribute(k_cf_rows_fwd<R, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+            OF2D_CUDA_TRY(cudaFuncSetAttribute(k_cf_rows_inv<R, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+            cfg_r = smem_r;
+        }
+        if (smem_c > cfg_c) {
+            OF2D_CUDA_TRY(cudaFuncSetAttribute(k_cf_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+            cfg_c = smem_c;
+        }
+        double2 *specT = (double2 *)P->d_spec;
+        k_cf_rows_fwd<R, LPC><<<dim3(ny / LPC, batch), FFT_THREADS, smem_r, ctx->stream>>>(nx, ny, (const vec2_t<R> *)u, (const vec2_t<R> *)unew, (const vec2_t<R> *)gradI, It,
+                                                                                          (R)P->tau, specT, P->Tx, H);
+        OF2D_LAUNCH_CHECK(ctx);
+        k_cf_cols<<<dim3(nx, batch), FFT_THREADS, smem_c, ctx->stream>>>(nx, ny, specT, P->d_cosx, P->d_cosy, P->tau_alpha, P->Ty, H);
+        OF2D_LAUNCH_CHECK(ctx);
+        k_cf_rows_inv<R, LPC><<<dim3(ny / LPC, batch), FFT_THREADS, smem_r, ctx->stream>>>(nx, ny, specT, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN, P->Tx, H);
+        OF2D_LAUNCH_CHECK(ctx);
+        return OF2D_SUCCESS;
+    }
     static size_t configured_rows = 0, configured_cols = 0;   // per template instance: largest dynamic size set so far
     if (P->smem_rows > configured_rows) {
         OF2D_CUDA_TRY(cudaFuncSetAttribute(k_curv_rows_fwd<R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_rows));
@@ -407,7 +439,6 @@ int curvature_step_impl(of2d_curvature_plan *P, const R *u, R *unew, const R *gr
     k_curv_cols<S><<<dim3(ceil_div(nx, P->cols_per_cta), batch), FFT_THREADS, P->smem_cols, ctx->stream>>>(nx, ny, P->cols_per_cta, spec, P->d_cosx, P->d_cosy,
                                                                                                        P->tau_alpha, P->Ty, H);
     OF2D_LAUNCH_CHECK(ctx);
-    const R fourN = (R)4.0f * (R)(unsigned)(nx * ny);
     k_curv_rows_inv<R, S><<<dim3(ny, batch), FFT_THREADS, P->smem_rows, ctx->stream>>>(nx, ny, spec, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN, P->Tx, H);
     OF2D_LAUNCH_CHECK(ctx);
     return OF2D_SUCCESS;

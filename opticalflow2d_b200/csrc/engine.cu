@@ -14,6 +14,7 @@
 // Elastic and Fluid keep their fields in a TRANSPOSED working layout (element (i,j) at i*P + j) for
 // the whole loop so that the column-sequential SOR sweep (sor_tile.cuh) streams contiguous memory.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -74,7 +75,9 @@ EngK<R> make_k(of2d_engine *E) {
 // grid = (CTAs per pair, batch): enough CTAs to fill the GPU about four deep, never more than there are tiles
 inline dim3 grid_tiles(const of2d_engine *E) {
     const int ntiles = ceil_div(E->d.dimx, TILE) * ceil_div(E->d.dimy, TILE);
-    int per_pair = ceil_div((long)E->ctx->sm_count * 4, E->d.batch);
+    static int per_sm = 0;
+    if (per_sm == 0) { const char *e = getenv("OF2D_CTAS_PER_SM"); per_sm = e && atoi(e) > 0 ? atoi(e) : 8; }
+    int per_pair = ceil_div((long)E->ctx->sm_count * per_sm, E->d.batch);
     if (per_pair > ntiles) per_pair = ntiles;
     if (per_pair < 1) per_pair = 1;
     return dim3(per_pair, E->d.batch);

@@ -164,29 +164,38 @@ __global__ void __launch_bounds__(TX *TY) k_hs_iter(EngK<R> K, const vec2_t<R> *
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
         const int i = (tile % T.tiles_x) * TILE + threadIdx.x;
         const int jb = (tile / T.tiles_x) * TILE + threadIdx.y;
-        if (i >= nx) continue;
+        // all loads of the thread's 4 pixels are issued before any arithmetic: indices are clamped into the
+        // field so that they are unconditional (the clamped values are never used)
+        const int ic = min(i, nx - 1);
+        vec2_t<R> old[PY], a[PY], b[PY], cc[PY], d[PY], dI[PY];
+        R it[PY];
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int jc = min(jb + p * TY, ny - 1);
+            const int idx = ic + jc * nx;
+            old[p] = u[idx];
+            a[p] = u[idx - (ic > 0)];
+            b[p] = u[idx + (ic < nx - 1)];
+            cc[p] = u[idx - (jc > 0 ? nx : 0)];
+            d[p] = u[idx + (jc < ny - 1 ? nx : 0)];
+            dI[p] = gradI[idx];
+            it[p] = It[idx];
+        }
 #pragma unroll
         for (int p = 0; p < PY; p++) {
             const int j = jb + p * TY;
-            if (j < ny) {
-                const int idx = i + j * nx;
-                const vec2_t<R> old = u[idx];
-                vec2_t<R> q;
-                if (i == 0 || i == nx - 1 || j == 0 || j == ny - 1) {
-                    q = mk2<R>((R)0.0f, (R)0.0f);
-                } else {   // gradients.h:78
-                    const vec2_t<R> a = u[idx - 1], b = u[idx + 1], cc = u[idx - nx], d = u[idx + nx];
-                    q = mk2<R>((((a.x + b.x) + cc.x) + d.x) / (R)4.0f, (((a.y + b.y) + cc.y) + d.y) / (R)4.0f);
-                }
-                const vec2_t<R> dI = gradI[idx];
-                const vec2_t<R> f = lssd_force<R>(dI, It[idx], q);
-                const R den = alphasq + dI.x * dI.x + dI.y * dI.y;
-                vec2_t<R> o;
-                if (den == 0) { divzero = true; o = q; }
-                else o = mk2<R>(q.x - f.x / den, q.y - f.y / den);
-                un[idx] = o;
-                sd += norm_term(mk2<R>(o.x - old.x, o.y - old.y));
-                sp += norm_term(old);
+            vec2_t<R> q;
+            if (i == 0 || i >= nx - 1 || j == 0 || j >= ny - 1) q = mk2<R>((R)0.0f, (R)0.0f);
+            else q = mk2<R>((((a[p].x + b[p].x) + cc[p].x) + d[p].x) / (R)4.0f, (((a[p].y + b[p].y) + cc[p].y) + d[p].y) / (R)4.0f);   // gradients.h:78
+            const vec2_t<R> f = lssd_force<R>(dI[p], it[p], q);
+            const R den = alphasq + dI[p].x * dI[p].x + dI[p].y * dI[p].y;
+            vec2_t<R> o;
+            if (den == 0) { divzero = divzero || (i < nx && j < ny); o = q; }
+            else o = mk2<R>(q.x - f.x / den, q.y - f.y / den);
+            if (i < nx && j < ny) {
+                un[i + j * nx] = o;
+                sd += norm_term(mk2<R>(o.x - old[p].x, o.y - old[p].y));
+                sp += norm_term(old[p]);
             }
         }
     }
@@ -365,7 +374,7 @@ struct ConvW {
 
 template <class R, int EPI, int KW>
 __global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int dst_buf, const __grid_constant__ ConvW<R> W, int nsq_cap) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int pair = blockIdx.y;
     PairCtl *c = K.ctl + pair;
     const CtlHot h = load_ctl(c);

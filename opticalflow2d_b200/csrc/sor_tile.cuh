@@ -25,6 +25,8 @@
 //   (sum_q a^(RPT q) x_top[t-q], M terms).
 #pragma once
 
+#include <stdlib.h>
+
 #include "device_math.cuh"
 #include "engine_ctl.cuh"
 
@@ -40,7 +42,10 @@ struct SorPlan {
 
 namespace {
 
-constexpr int SOR_NS = 6;
+#ifndef OF2D_SOR_NS
+#define OF2D_SOR_NS 6
+#endif
+constexpr int SOR_NS = OF2D_SOR_NS;
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
@@ -83,8 +88,9 @@ struct SorTileArgs {
 };
 
 template <class R, int RPT, bool FLUID>
-__global__ void __launch_bounds__(256) k_sor_tile(SorTileArgs<R> A) {
+__global__ void __launch_bounds__(128) k_sor_tile(SorTileArgs<R> A) {
     using V = vec2_t<R>;
+    static_assert(RPT == 4, "row blocks of 4: 32-byte aligned vector loads from the ring");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full[SOR_NS];
     const int pair = blockIdx.z;
@@ -97,7 +103,7 @@ __global__ void __launch_bounds__(256) k_sor_tile(SorTileArgs<R> A) {
     const int js = 1 + blockIdx.y * A.BY, je = min(js + A.BY, ny - 1);
     const int ic0 = max(1, is - A.HW);
     const int jc0 = max(1, js - A.HS), jc1 = min(ny - 1, je + A.HN);
-    const int jl0 = (jc0 - 1) & ~3;
+    const int jl0 = (jc0 - 1) & ~3;              // first loaded row (multiple of 4: 16/32-byte aligned bulk copies)
     const int ncols = ie - ic0 + 2;              // loaded columns ic0-1 .. ie
 
     const int xsel = A.which ? __ldcg(&c->vsel) : __ldcg(&c->sel);
@@ -107,19 +113,21 @@ __global__ void __launch_bounds__(256) k_sor_tile(SorTileArgs<R> A) {
     const V *__restrict__ gp = A.gradI + (size_t)pair * A.nT;
     const R *__restrict__ tp = A.It + (size_t)pair * A.nT;
 
-    // stage layout: [x LR][gradI LR][uf LR (fluid)][It LR]
-    const size_t stage_bytes = (size_t)LR * (sizeof(V) * (FLUID ? 3 : 2) + sizeof(R));
-    auto st_x = [&](int s) { return reinterpret_cast<V *>(smem_raw + s * stage_bytes); };
-    auto st_g = [&](int s) { return reinterpret_cast<V *>(smem_raw + s * stage_bytes) + LR; };
-    auto st_u = [&](int s) { return reinterpret_cast<V *>(smem_raw + s * stage_bytes) + 2 * LR; };
-    auto st_t = [&](int s) { return reinterpret_cast<R *>(smem_raw + s * stage_bytes + (size_t)LR * sizeof(V) * (FLUID ? 3 : 2)); };
+    // stage layout: [x LR + 4 (2 pad elements in front)][gradI LR][uf LR (fluid)][It LR]; row r of the tile at index r
+    const size_t x_bytes = (size_t)(LR + 4) * sizeof(V);
+    const size_t stage_bytes = x_bytes + (size_t)LR * (sizeof(V) * (FLUID ? 2 : 1) + sizeof(R));
+    auto st_x = [&](int s) { return reinterpret_cast<V *>(smem_raw + s * stage_bytes) + 2; };
+    auto st_g = [&](int s) { return reinterpret_cast<V *>(smem_raw + s * stage_bytes + x_bytes); };
+    auto st_u = [&](int s) { return reinterpret_cast<V *>(smem_raw + s * stage_bytes + x_bytes) + LR; };
+    auto st_t = [&](int s) { return reinterpret_cast<R *>(smem_raw + s * stage_bytes + x_bytes + (size_t)LR * sizeof(V) * (FLUID ? 2 : 1)); };
     struct Pub { V top, d0; };
     Pub *pub = reinterpret_cast<Pub *>(smem_raw + SOR_NS * stage_bytes);   // [2][NT]
+    const unsigned tx_bytes = (unsigned)((size_t)LR * (sizeof(V) * (FLUID ? 3 : 2) + sizeof(R)));
 
-    auto issue = [&](int k) {   // thread 0: loaded column k -> stage k % NS
+    auto issue = [&](int k) {   // thread 0: loaded column k -> stage k % NS (TMA bulk copies, one per field)
         const int s = k % SOR_NS;
         const size_t g = (size_t)(ic0 - 1 + k) * P + jl0;
-        mbar_expect_tx(&full[s], (unsigned)stage_bytes);
+        mbar_expect_tx(&full[s], tx_bytes);
         bulk_g2s(st_x(s), xin + g, (unsigned)(LR * sizeof(V)), &full[s]);
         bulk_g2s(st_g(s), gp + g, (unsigned)(LR * sizeof(V)), &full[s]);
         if (FLUID) bulk_g2s(st_u(s), ufp + g, (unsigned)(LR * sizeof(V)), &full[s]);
@@ -137,29 +145,51 @@ __global__ void __launch_bounds__(256) k_sor_tile(SorTileArgs<R> A) {
         for (int k = 0; k < pre; k++) issue(k);
     }
 
-    const int j0 = jl0 + 1 + t * RPT;            // first row of this thread; its smem row index is t*RPT + 1
+    const int r0 = t * RPT;                      // ring index of the thread's first row
+    const int j0 = jl0 + r0;                     // its image row
     bool comp[RPT];
     bool allcomp = true;
 #pragma unroll
     for (int r = 0; r < RPT; r++) { comp[r] = (j0 + r >= jc0) && (j0 + r < jc1); allcomp = allcomp && comp[r]; }
     const bool above_comp = (j0 + RPT >= jc0) && (j0 + RPT < jc1);
-    R aR = (R)1;
-#pragma unroll
-    for (int r = 0; r < RPT; r++) aR *= A.a;
+    const R a = A.a;
+    const R aR = (a * a) * (a * a);
 
-    V newW[RPT + 2], oldC[RPT + 1], oldCm1;
+    // rows j0-1 .. j0+RPT of the previous (new) column, rows j0-1 .. j0+RPT of the current (old) column
+    V newW[RPT + 2], oldC[RPT + 2];
     mbar_wait(&full[0], 0);
     mbar_wait(&full[1 % SOR_NS], 0);
     {
         const V *x0 = st_x(0), *x1 = st_x(1 % SOR_NS);
 #pragma unroll
-        for (int r = 0; r < RPT + 2; r++) newW[r] = x0[t * RPT + r];
-        oldCm1 = x1[t * RPT];
-#pragma unroll
-        for (int r = 0; r < RPT + 1; r++) oldC[r] = x1[t * RPT + 1 + r];
+        for (int r = 0; r < RPT + 2; r++) { newW[r] = x0[r0 - 1 + r]; oldC[r] = x1[r0 - 1 + r]; }
     }
 
-    double sd = 0.0, sp = 0.0;
+    // carry = sum_q cq[q] top[t-q]: the new value of the row below the thread's block from the zero-carry tops of the
+    // threads below (coefficients a^(RPT (q-1)) while those threads are fully computed blocks; constant over columns)
+    constexpr int MQ = 8;
+    R cq[MQ];
+    int tqi[MQ];
+    {
+        R coef = (R)1;
+        bool alive = t > 0;
+#pragma unroll
+        for (int q = 1; q <= MQ; q++) {
+            const int tq = t - q;
+            alive = alive && tq >= 0 && q <= A.M;
+            cq[q - 1] = alive ? coef : (R)0;
+            tqi[q - 1] = tq >= 0 ? tq : 0;
+            const int jq = jl0 + tq * RPT;
+            alive = alive && (jq >= jc0 && jq + RPT - 1 < jc1);
+            coef *= aR;
+        }
+    }
+    bool own[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; r++) own[r] = (j0 + r >= js) && (j0 + r < je);
+
+    float sdf = 0.0f, spf = 0.0f;
+    double sdd = 0.0, spd = 0.0;
     for (int k = 1; k <= ncols - 2; k++) {
         const int i = ic0 - 1 + k;
         const int sC = k % SOR_NS, sE = (k + 1) % SOR_NS;
@@ -167,40 +197,43 @@ __global__ void __launch_bounds__(256) k_sor_tile(SorTileArgs<R> A) {
         V oldE[RPT + 2];
         {
             const V *xe = st_x(sE);
+            oldE[0] = xe[r0 - 1];
 #pragma unroll
-            for (int r = 0; r < RPT + 2; r++) oldE[r] = xe[t * RPT + r];
+            for (int r = 0; r < RPT; r++) oldE[r + 1] = xe[r0 + r];
+            oldE[RPT + 1] = xe[r0 + RPT];
         }
-        V d[RPT], xt[RPT];
-        R gk[RPT];
+        // everything of the reference's expression that does not involve the cell below (S):
+        //   o = ck C + cr (b - mu (((E + W) + N) + S) - mupl (E + W + 0.25 (NE' - NW' - SE' + SW')))
+        V ckC[RPT], bb[RPT], sum3[RPT], k2[RPT], d[RPT], xt[RPT];
         {
             const V *gs = st_g(sC);
             const R *ts = st_t(sC);
             const V *us = st_u(sC);
 #pragma unroll
             for (int r = 0; r < RPT; r++) {
-                const V Cc = oldC[r], N = oldC[r + 1];
+                const V Cc = oldC[r + 1], N = oldC[r + 2];
                 const V W = newW[r + 1], SW = newW[r], NW = newW[r + 2];
                 const V E = oldE[r + 1], SE = oldE[r], NE = oldE[r + 2];
-                const V b = lssd_force<R>(gs[t * RPT + 1 + r], ts[t * RPT + 1 + r], FLUID ? us[t * RPT + 1 + r] : Cc);
-                V dd;
-                dd.x = A.ck * Cc.x + A.cr * (b.x - A.mu * ((E.x + W.x) + N.x) - A.mupl * (E.x + W.x + (R)0.25f * (NE.y - NW.y - SE.y + SW.y)));
-                dd.y = A.ck * Cc.y + A.cr * (b.y - A.mu * ((E.y + W.y) + N.y) - A.mupl * (E.y + W.y + (R)0.25f * (NE.x - NW.x - SE.x + SW.x)));
+                bb[r] = lssd_force<R>(gs[r0 + r], ts[r0 + r], FLUID ? us[r0 + r] : Cc);
+                const R ewx = E.x + W.x, ewy = E.y + W.y;
+                sum3[r] = mk2<R>(ewx + N.x, ewy + N.y);
+                k2[r] = mk2<R>(ewx + (R)0.25f * (NE.y - NW.y - SE.y + SW.y), ewy + (R)0.25f * (NE.x - NW.x - SE.x + SW.x));
+                ckC[r] = mk2<R>(A.ck * Cc.x, A.ck * Cc.y);
+                const V dd = mk2<R>(ckC[r].x + A.cr * (bb[r].x - A.mu * sum3[r].x - A.mupl * k2[r].x), ckC[r].y + A.cr * (bb[r].y - A.mu * sum3[r].y - A.mupl * k2[r].y));
                 d[r] = comp[r] ? dd : Cc;
             }
         }
-        // zero-carry recurrence over the thread's rows
+        // zero-carry estimate of the column recurrence x_r = a x_{r-1} + d_r over the thread's rows
         xt[0] = d[0];
-        gk[0] = comp[0] ? A.a : (R)0;
 #pragma unroll
         for (int r = 1; r < RPT; r++) {
-            if (comp[r]) { xt[r] = mk2<R>(A.a * xt[r - 1].x + d[r].x, A.a * xt[r - 1].y + d[r].y); gk[r] = A.a * gk[r - 1]; }
-            else { xt[r] = d[r]; gk[r] = (R)0; }
+            const R ar = comp[r] ? a : (R)0;
+            xt[r] = mk2<R>(ar * xt[r - 1].x + d[r].x, ar * xt[r - 1].y + d[r].y);
         }
         Pub *pb = pub + (k & 1) * NT;
         {
             Pub me;
             me.top = xt[RPT - 1];
-            if (t == 0) { me.top.x += gk[RPT - 1] * oldCm1.x; me.top.y += gk[RPT - 1] * oldCm1.y; }   // thread 0 knows its carry
             me.d0 = d[0];
             pb[t] = me;
         }
@@ -210,56 +243,58 @@ __global__ void __launch_bounds__(256) k_sor_tile(SorTileArgs<R> A) {
             if (k == 1 && SOR_NS < ncols) issue(SOR_NS);
             if (k + SOR_NS < ncols) issue(k + SOR_NS);
         }
-        V carry;
-        if (t == 0) {
-            carry = oldCm1;
-        } else {
-            carry = mk2<R>((R)0, (R)0);
-            R coef = (R)1;
-            for (int q = 1; q <= A.M; q++) {
-                const int tq = t - q;
-                if (tq < 0) break;
-                const V tv = pb[tq].top;
-                carry.x += coef * tv.x; carry.y += coef * tv.y;
-                if (tq == 0) break;
-                const int jq = jl0 + 1 + tq * RPT;
-                if (!(jq >= jc0 && jq + RPT - 1 < jc1)) break;
-                coef *= aR;
+        // the new value of the row below the thread's block
+        V carry = mk2<R>((R)0, (R)0);
+#pragma unroll
+        for (int q = 0; q < MQ; q++) {
+            const V tv = pb[tqi[q]].top;
+            carry.x += cq[q] * tv.x; carry.y += cq[q] * tv.y;
+        }
+        // the reference's expression, literally, with S = the (estimated) new value of the cell below
+        V xn[RPT];
+        {
+            V S = carry;
+#pragma unroll
+            for (int r = 0; r < RPT; r++) {
+                const V lit = mk2<R>(ckC[r].x + A.cr * (bb[r].x - A.mu * (sum3[r].x + S.x) - A.mupl * k2[r].x),
+                                     ckC[r].y + A.cr * (bb[r].y - A.mu * (sum3[r].y + S.y) - A.mupl * k2[r].y));
+                xn[r] = comp[r] ? lit : oldC[r + 1];
+                S = xn[r];
             }
         }
-        V xn[RPT];
-#pragma unroll
-        for (int r = 0; r < RPT; r++) xn[r] = mk2<R>(xt[r].x + gk[r] * carry.x, xt[r].y + gk[r] * carry.y);
         V ntop;
         if (t + 1 < NT) {
             const V d0 = pb[t + 1].d0;
-            ntop = above_comp ? mk2<R>(A.a * xn[RPT - 1].x + d0.x, A.a * xn[RPT - 1].y + d0.y) : d0;
+            ntop = above_comp ? mk2<R>(a * xn[RPT - 1].x + d0.x, a * xn[RPT - 1].y + d0.y) : d0;
         } else {
-            ntop = oldC[RPT];
+            ntop = oldC[RPT + 1];
         }
         if (i >= is) {
 #pragma unroll
             for (int r = 0; r < RPT; r++) {
                 const int j = j0 + r;
-                if (j >= js && j < je) {
+                if (own[r]) {
                     xout[(size_t)i * P + j] = xn[r];
                     if (!FLUID) {
-                        sd += vec_norm_d<R>(mk2<R>(xn[r].x - oldC[r].x, xn[r].y - oldC[r].y));
-                        sp += vec_norm_d<R>(oldC[r]);
+                        const V oc = oldC[r + 1];
+                        const R dx = xn[r].x - oc.x, dy = xn[r].y - oc.y;
+                        if (sizeof(R) == 4) { sdf += __fsqrt_rn((float)(dx * dx + dy * dy)); spf += __fsqrt_rn((float)(oc.x * oc.x + oc.y * oc.y)); }
+                        else { sdd += sqrt((double)(dx * dx + dy * dy)); spd += sqrt((double)(oc.x * oc.x + oc.y * oc.y)); }
                     }
                 }
             }
+            if (sizeof(R) == 4 && !FLUID && (k & 15) == 0) { sdd += (double)sdf; spd += (double)spf; sdf = 0.0f; spf = 0.0f; }
         }
         newW[0] = carry;
 #pragma unroll
         for (int r = 0; r < RPT; r++) newW[r + 1] = xn[r];
         newW[RPT + 1] = ntop;
-        oldCm1 = oldE[0];
 #pragma unroll
-        for (int r = 0; r < RPT + 1; r++) oldC[r] = oldE[r + 1];
+        for (int r = 0; r < RPT + 2; r++) oldC[r] = oldE[r];
     }
 
     if (FLUID) return;
+    double sd = sdd + (double)sdf, sp = spd + (double)spf;
     block_sum2(sd, sp);
     const double vals[2] = {sd, sp};
     const int nblocks = gridDim.x * gridDim.y, bid = blockIdx.x + blockIdx.y * gridDim.x;
@@ -288,24 +323,31 @@ static inline SorPlan sor_plan(int nx, int ny, int batch, double mu, double lamb
     if (den == 0 || nx < 3 || ny < 3) { S.supported = 0; return S; }
     const double cr = fabs(S.c_relax);
     const double a = cr * fabs(mu), aW = cr * (fabs(mu) + fabs(mu + lambda)), aD = 0.25 * cr * fabs(mu + lambda);
-    const double eps = dbl ? ldexp(1.0, -62) : ldexp(1.0, -34);
+    // eps: relative to the step of the iteration; 2^-46 puts the halo error ~2^-12 ulp below the field values
+    const double eps = dbl ? ldexp(1.0, -70) : ldexp(1.0, -40);
     S.supported = 1;
     if (!(a < 0.6) || !(aW + 2 * aD < 0.6) || !(1.0 - a - aW - aD > 0.15)) { S.supported = 0; return S; }
     const double rx = (aW + 2 * aD) / (1.0 - a), rs = a / (1.0 - aW - 2 * aD), rn = aD / (1.0 - a - aW - aD);
     auto halo = [&](double rho) { return rho <= 1e-12 ? 1 : (int)ceil(log(eps) / log(rho)) + 1; };
     S.HW = halo(rx); S.HS = halo(rs); S.HN = halo(rn);
-    S.RPT = 2;
-    S.NT = 128;
+    S.RPT = 4;
+    S.NT = 64;
+    { const char *e = getenv("OF2D_SOR_NT"); if (e && atoi(e) >= 32) S.NT = atoi(e) & ~31; }
     S.M = a <= 1e-12 ? 1 : (int)ceil(log(eps) / (S.RPT * log(a))) + 1;
-    if (S.HW > 96 || S.HS + S.HN > S.NT * S.RPT / 2 || S.M > 16) { S.supported = 0; return S; }
-    S.BY = S.NT * S.RPT - S.HS - S.HN - 4;
-    // column bands: wide enough to amortise the west halo, narrow enough to fill the GPU
-    S.BX = 64;
-    const long tiles_needed = 148L * 2;
-    while (S.BX > 32 && (long)batch * ceil_div(ny - 2, S.BY) * ceil_div(nx - 2, S.BX) < tiles_needed) S.BX -= 16;
-    while ((long)batch * ceil_div(ny - 2, S.BY) * ceil_div(nx - 2, S.BX * 2) >= tiles_needed * 2 && S.BX < 256) S.BX *= 2;
+    if (S.HW > 96 || S.HS + S.HN > S.NT * S.RPT / 2 || S.M > 8) { S.supported = 0; return S; }
+    const int by_max = S.NT * S.RPT - S.HS - S.HN - 8;
+    S.nstrips = ceil_div(ny - 2, by_max);
+    S.BY = ceil_div(ny - 2, S.nstrips);
+    // column bands: as many as keep the GPU about `waves` CTAs per SM deep, but not narrower than the west halo
+    int per_sm = 4;
+    { const char *e = getenv("OF2D_SOR_PER_SM"); if (e && atoi(e) > 0) per_sm = atoi(e); }
+    long want = 148L * per_sm / ((long)batch * S.nstrips);
+    if (want < 1) want = 1;
+    S.BX = ceil_div(nx - 2, (int)want);
+    if (S.BX < S.HW) S.BX = S.HW;
+    { const char *e = getenv("OF2D_SOR_BX"); if (e && atoi(e) > 0) S.BX = atoi(e); }
     S.nbands = ceil_div(nx - 2, S.BX);
-    S.nstrips = ceil_div(ny - 2, S.BY);
+    S.BX = ceil_div(nx - 2, S.nbands);
     S.nT = (size_t)nx * S.P + 1024;
     return S;
 }
@@ -316,30 +358,30 @@ static int sor_tile_launch(of2d_ctx *ctx, const SorPlan &S, PairCtl *ctl, int *n
     SorTileArgs<R> A;
     A.nx = S.nx; A.ny = S.ny; A.P = S.P; A.nT = S.nT; A.n = (size_t)S.nx * S.ny;
     A.BX = S.BX; A.BY = S.BY; A.HW = S.HW; A.HS = S.HS; A.HN = S.HN; A.M = S.M;
-    A.LR = S.NT * S.RPT + 4;
+    A.LR = S.NT * S.RPT + 8;
     A.which = which;
     A.x[0] = x0; A.x[1] = x1; A.uf[0] = uf0; A.uf[1] = uf1; A.gradI = gradI; A.It = It;
     A.ck = (R)S.c_keep; A.cr = (R)S.c_relax; A.mu = (R)S.mu; A.mupl = (R)S.mupl;
     A.a = (R)(-S.c_relax * S.mu);
     A.ctl = ctl; A.n_active = n_active; A.partials = partials; A.pstride = pstride; A.tr = tr;
     const bool fluid = which == 1;
-    const size_t stage = (size_t)A.LR * (sizeof(vec2_t<R>) * (fluid ? 3 : 2) + sizeof(R));
+    const size_t stage = (size_t)(A.LR + 4) * sizeof(vec2_t<R>) + (size_t)A.LR * (sizeof(vec2_t<R>) * (fluid ? 2 : 1) + sizeof(R));
     const size_t smem = SOR_NS * stage + 2 * (size_t)S.NT * 2 * sizeof(vec2_t<R>);
     const dim3 grid(S.nbands, S.nstrips, S.batch);
     static bool configured[2][2] = {};
     const int pi = sizeof(R) == 8;
     if (fluid) {
         if (!configured[pi][1]) {
-            OF2D_CUDA_TRY(cudaFuncSetAttribute(k_sor_tile<R, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            OF2D_CUDA_TRY(cudaFuncSetAttribute(k_sor_tile<R, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             configured[pi][1] = true;
         }
-        k_sor_tile<R, 2, true><<<grid, S.NT, smem, ctx->stream>>>(A);
+        k_sor_tile<R, 4, true><<<grid, S.NT, smem, ctx->stream>>>(A);
     } else {
         if (!configured[pi][0]) {
-            OF2D_CUDA_TRY(cudaFuncSetAttribute(k_sor_tile<R, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            OF2D_CUDA_TRY(cudaFuncSetAttribute(k_sor_tile<R, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             configured[pi][0] = true;
         }
-        k_sor_tile<R, 2, false><<<grid, S.NT, smem, ctx->stream>>>(A);
+        k_sor_tile<R, 4, false><<<grid, S.NT, smem, ctx->stream>>>(A);
     }
     OF2D_LAUNCH_CHECK(ctx);
     return OF2D_SUCCESS;
