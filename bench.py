@@ -177,70 +177,54 @@ def workload_config(size: int) -> dict:
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
-def kernel_microbench(size: int, reps: int = 5) -> dict:
-    """Times the main kernels alone through the raw C ABI (include/of2d_cuda.h) on L2-flushed inputs."""
-    import torch
-    from opticalflow2d_b200.torch_bridge import Device
-    dev = Device(strict=False)
-    n = size * size
-    g = torch.Generator(device="cuda").manual_seed(7)
-    f32 = torch.float32
-    img_a = torch.rand(n, device="cuda", dtype=f32, generator=g)
-    img_b = torch.rand(n, device="cuda", dtype=f32, generator=g)
-    u = (torch.rand(2 * n, device="cuda", dtype=f32, generator=g) - 0.5) * 3.0
-    v = (torch.rand(2 * n, device="cuda", dtype=f32, generator=g) - 0.5) * 0.5
-    out2 = torch.empty(2 * n, device="cuda", dtype=f32)
-    out1 = torch.empty(n, device="cuda", dtype=f32)
-    grad = torch.rand(2 * n, device="cuda", dtype=f32, generator=g) - 0.5
-    It = torch.rand(n, device="cuda", dtype=f32, generator=g) - 0.5
-    flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
-    ax = np.arange(5, dtype=np.float64) - 2.0
-    kern = np.exp(-(ax[:, None] ** 2 + ax[None, :] ** 2) / (2 * 1.5 * 1.5))
-    kern = np.ascontiguousarray(kern / kern.sum())
-    import ctypes as C
-    plan = C.c_void_p()
-    dev._check(dev.lib.of2d_curvature_plan_create(dev.ctx, size, size, 0.25, 1.0, 0, C.byref(plan)))
-    hm, hd = np.zeros(1, np.float32), np.zeros(1, np.float32)
-
-    cases = {
-        "diffusion_step": (28, lambda: dev.call("diffusion_step", f32, size, size, 1, u, out2, grad, It, 0.5, None)),
-        "convolute_motion_5x5": (16, lambda: dev.call("convolute_motion", f32, size, size, 1, u, out2, kern, 5, 5)),
-        "demons_force": (24, lambda: dev.call("demons_force", f32, size, size, 1, img_a, img_b, v, out2, 1.0, 0.25, None)),
-        "compose": (24, lambda: dev.call("compose", f32, size, size, 1, u, v, out2)),
-        "warp2d": (16, lambda: dev.call("warp2d", f32, size, size, 1, img_a, v, out1)),
-        "derivatives": (20, lambda: dev.call("derivatives", f32, size, size, 1, img_a, img_b, out2, out1)),
-        "elastic_step_sor": (28, lambda: dev.call("elastic_step", f32, size, size, 1, u, grad, It, 1.0, 0.25, 0.66)),
-        "fluid_step": (60, lambda: dev.call("fluid_step", f32, size, size, v, u, out2, grad, It, 0.1, 0.0, 0.66, hm, hd)),
-        "curvature_step": (92, lambda: dev._check(dev.lib.of2d_curvature_step_f32(plan, C.c_void_p(u.data_ptr()), C.c_void_p(out2.data_ptr()),
-                                                                                  C.c_void_p(grad.data_ptr()), C.c_void_p(It.data_ptr())))),
-        "logger_update": (24, lambda: dev.call("logger_update", f32, n, u, out2, hm)),
-    }
-    res = {}
-    for name, (bpp, fn) in cases.items():
-        fn(); torch.cuda.synchronize()
-        ts = []
-        for _ in range(reps):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); fn(); e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ms = sum(ts) / len(ts)
-        res[name] = {"ms": ms, "bytes_per_px": bpp, "gbs": bpp * n / (ms * 1e-3) / 1e9}
-    dev.lib.of2d_curvature_plan_destroy(plan)
-    dev.close()
-    return res
-
-
-# kernels launched per iteration by each method (for the dominant-kernel estimate)
-METHOD_KERNELS = {
-    "diffusion": {"diffusion_step": 1, "logger_update": 1},
-    "curvature": {"curvature_step": 1, "logger_update": 1},
-    "elastic": {"elastic_step_sor": 1, "logger_update": 1},
-    "thirion": {"demons_force": 1, "convolute_motion_5x5": 2, "compose": 1, "logger_update": 1},
-    "diffeomorphic": {"demons_force": 1, "convolute_motion_5x5": 2, "compose": 3, "logger_update": 1},
-    "fluid": {"fluid_step": 1, "logger_update": 1},
+# algorithmic bytes per pixel per launch of the engine kernels, fp32 (DESIGN.md "Kernels")
+KERNEL_BYTES_PER_PX = {
+    "hs_iter": 28, "conv": 16, "conv_logger": 24, "conv_maxabs": 16, "demons_force": 24, "compose": 24, "square": 16,
+    "sor_tile_elastic": 28, "sor_tile_fluid": 36, "fluid_increment": 24, "fluid_integrate": 24,
+    "curv_rows_fwd": 36, "curv_cols": 32, "curv_rows_inv": 32, "regrid_compose": 24, "final_compose": 24,
 }
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/), 2048^2 fp32
+NCU_TRAFFIC_BYTES = {}
+try:
+    NCU_TRAFFIC_BYTES = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+except (OSError, ValueError):
+    pass
+
+BATCH_METHODS = ["thirion", "fluid"]
+BATCH_PX = 512
+BATCH_NITER = 100
+
+
+def make_batch_inputs(lo: int, hi: int, size: int):
+    from opticalflow2d_b200 import synthetic as S
+    n = hi - lo
+    R = np.empty((n, size, size)); T = np.empty((n, size, size))
+    for k in range(n):
+        R[k], T[k] = S.batch_pair(lo + k, size, size)
+    return R, T
+
+
+def _cpu_batch_one(args):
+    method, k, size, niter = args
+    from oracle import refapi
+    from opticalflow2d_b200 import synthetic as S
+    kind = "ref" if refapi.available("ref", 32) else "oracle"
+    lib = refapi.get(kind, 32)
+    R, T = S.batch_pair(k, size, size)
+    t0 = time.perf_counter()
+    out = lib.register(R, T, REG[method], PARAMS[method], [niter], nscales=0, nrefine=1, verbose=1)
+    return len(out["err"]), time.perf_counter() - t0
+
+
+def cpu_batch_sample(method: str, size: int, niter: int, workers: int):
+    import multiprocessing as mp
+    jobs = [(method, k, size, niter) for k in range(workers)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(workers) as pool:
+        res = pool.map(_cpu_batch_one, jobs)
+    wall = time.perf_counter() - t0
+    return {"pairs_per_s": workers / wall, "cores": workers, "mean_iterations": float(np.mean([r[0] for r in res])),
+            "sample": f"{workers} pairs of {size}^2 ({method}, niter cap {niter}), one process per pair, {wall:.1f} s wall"}
 
 
 def run_ours(args):
@@ -326,6 +310,71 @@ def run_ours(args):
         return 0
     iters_e, ms_e, wall_e, _, _ = timed(True)
 
+    # roofline leg: one extra step with per-kernel CUDA events on the launching stream (not part of the timed steps)
+    kern, dom = {}, None
+    if rank == 0:
+        of.profile_enable(True, 32)
+        step(False)
+        prof = of.profile_read(32)
+        of.profile_enable(False, 32)
+        tot_ms = sum(v[1] for v in prof.values()) or 1e-12
+        for name, (cnt, tms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+            bpp = KERNEL_BYTES_PER_PX.get(name)
+            avg = tms / max(cnt, 1)
+            kern[name] = {"launches": cnt, "avg_ms": avg, "share_of_step": tms / tot_ms, "bytes_per_px": bpp,
+                          "gbs": (bpp * n / (avg * 1e-3) / 1e9) if bpp else None}
+        dom = next((k for k in kern if kern[k]["bytes_per_px"]), None)
+    for s in sessions.values():
+        s.close()
+    sessions.clear()
+    pinned.clear()
+
+    # ---- batched slice registration (BASELINE.json configs[4]): BATCH pairs of 512^2 per GPU, no collective in the solve
+    batch_res = {}
+    if args.batch > 0:
+        B, bp = args.batch, BATCH_PX
+        lo, hi = of.shard_pairs(B * world, world, rank)
+        Rb, Tb = make_batch_inputs(lo, hi, bp)
+        prb = torch.from_numpy(Rb).pin_memory(); ptb = torch.from_numpy(Tb).pin_memory()
+        pob = torch.empty((B, 2, bp, bp), dtype=torch.float64).pin_memory()
+        del Rb, Tb
+        bsteps = max(1, min(args.steps, 2))
+        for m in BATCH_METHODS:
+            bt = of.Batch((bp, bp), B, BATCH_NITER, REG[m], PARAMS[m], nrefine=1, wave=min(B, 256), bits=32)
+            bt.set_images_raw(prb.data_ptr(), ptb.data_ptr())
+            res = {}
+            for leg in ("resident", "e2e"):
+                def bstep():
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    if leg == "e2e":
+                        bt.set_images_raw(prb.data_ptr(), ptb.data_ptr())
+                    bt.estimate()
+                    if leg == "e2e":
+                        bt.motion_raw(pob.data_ptr())
+                    e1.record()
+                    return e0, e1
+                bstep()
+                barrier()
+                evs = [bstep() for _ in range(bsteps)]
+                barrier()
+                sec = sum(a.elapsed_time(b) for a, b in evs) * 1e-3 / bsteps
+                its, rg = bt.iterations()
+                v = torch.tensor([sec], device="cuda", dtype=torch.float64)
+                w = torch.tensor([float(B), float(its.sum())], device="cuda", dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(v, op=dist.ReduceOp.MAX)
+                    dist.all_reduce(w, op=dist.ReduceOp.SUM)
+                res[leg] = {"pairs_per_s": float(w[0]) / float(v[0]), "seconds": float(v[0]),
+                            "mpix_iter_s": float(w[1]) * bp * bp / float(v[0]) / 1e6}
+                res["mean_iterations"] = float(w[1]) / float(w[0])
+            bt.close()
+            batch_res[m] = res
+        batch_res["config"] = {"workload": f"c5_batch_{bp}x{bp}", "pairs_per_gpu": B, "total_pairs": B * world, "niter_cap": BATCH_NITER,
+                               "wave": min(B, 256), "h2d_bytes_per_pair": 2 * bp * bp * 8, "d2h_bytes_per_pair": 2 * bp * bp * 8,
+                               "sharding": "contiguous pair ranges per rank, no collective in the solve"}
+        del prb, ptb, pob
+
     def agg(ms_map, it_map):
         t = sum(ms_map.values()) * 1e-3
         px = sum(it_map[m] for m in METHODS) * n
@@ -350,28 +399,23 @@ def run_ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        kern = kernel_microbench(size)
-        # dominant kernel = largest estimated share of the step
-        share = {}
-        for m in METHODS:
-            for k, c in METHOD_KERNELS[m].items():
-                share[k] = share.get(k, 0.0) + c * iters[m] * kern[k]["ms"]
-        dom = max(share, key=share.get)
         methods = {}
         for m in METHODS:
             mp = n * iters[m] / (ms[m] * 1e-3) / 1e6
             gbs = mp * 1e6 * BYTES_PER_PX_ITER[m] / 1e9
             methods[m] = {"iterations": iters[m], "ms": ms[m], "mpix_iter_s": mp, "gbs_algorithmic": gbs, "frac_of_hbm_peak": gbs / peak,
                           "e2e_ms": ms_e[m]}
-        cpu = None
-        if True:
-            ncpu = os.cpu_count() or 1
-            workers = max(1, min(len(METHODS), ncpu))
-            c = cpu_reference_step(size, 3, workers)
-            cpu = {"value": c["pixel_iters"] / c["wall_s"] / 1e6, "unit": "Mpixel*iter/s", "cores": workers,
-                   "kind": "reference" if c["kind"] == "ref" else "port",
-                   "sample": f"3 iterations of each of the 6 methods at {size}^2, {workers} processes, {c['wall_s']:.1f} s wall",
-                   "per_method_mpix_iter_s": {m: n * v["iterations"] / v["seconds"] / 1e6 for m, v in c["per_method"].items()}}
+        ncpu = os.cpu_count() or 1
+        workers = max(1, min(len(METHODS), ncpu))
+        c = cpu_reference_step(size, 3, workers)
+        cpu = {"value": c["pixel_iters"] / c["wall_s"] / 1e6, "unit": "Mpixel*iter/s", "cores": workers,
+               "kind": "reference" if c["kind"] == "ref" else "port",
+               "sample": f"3 iterations of each of the 6 methods at {size}^2, {workers} processes, {c['wall_s']:.1f} s wall",
+               "per_method_mpix_iter_s": {m: n * v["iterations"] / v["seconds"] / 1e6 for m, v in c["per_method"].items()},
+               "curvature_dct": "stand-in O(N log N) DCT (fftw3 not installed offline)"}
+        if args.batch > 0:
+            bw = max(1, min(ncpu, 16))
+            cpu["batch"] = {m: cpu_batch_sample(m, BATCH_PX, BATCH_NITER, bw) for m in BATCH_METHODS}
         line = {
             "metric": "Mpixel*iter/s (6 registration methods, aggregate)", "value": px / t / 1e6, "unit": "Mpixel*iter/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
@@ -381,17 +425,18 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": kern[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
-                         "share_of_step_estimate": share[dom] / max(sum(share.values()), 1e-12)},
+                         "frac": kern[dom]["gbs"] / peak, "traffic": NCU_TRAFFIC_BYTES.get(dom), "peak_source": peak_src,
+                         "share_of_step": kern[dom]["share_of_step"], "avg_launch_ms": kern[dom]["avg_ms"],
+                         "algorithmic_bytes_per_launch": kern[dom]["bytes_per_px"] * n,
+                         "how": "CUDA events around every engine launch of one extra (untimed) step, on the launching stream"} if dom else None,
             "kernels": kern,
             "methods": methods,
+            "batch": batch_res,
             "cpu_baseline": cpu,
             "wall_s_timed_region": wall,
             "loaded_libraries": [os.path.relpath(p, ROOT) for p in of.loaded_libraries()],
         }
         print(json.dumps(line), flush=True)
-    for s in sessions.values():
-        s.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -405,6 +450,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--batch", type=int, default=512, help="pairs of 512^2 per GPU in the batched leg (0 = skip); 8 GPUs x 512 = BASELINE's 4096")
     ap.add_argument("--quick", action="store_true", help="timed region only (no e2e leg, kernel microbench or CPU baseline): for ncu launch lists")
     ap.add_argument("--methods", default=",".join(list(METHODS)), help="comma-separated subset (profiling only; the default is the benchmark)")
     args = ap.parse_args()

@@ -58,6 +58,10 @@ int of2d_ctx_get_fast_math(of2d_ctx *ctx);
 const char *of2d_last_error(void);
 /* how many of this library's kernels have been launched through ctx since creation */
 uint64_t of2d_ctx_launch_count(of2d_ctx *ctx);
+/* per-kernel timing of the iteration engine with CUDA events on the launching stream: enable (resets), run, read
+   ("name launches total_ms" lines; synchronises).  Used by bench.py for the roofline of the dominant kernel. */
+int of2d_ctx_profile_enable(of2d_ctx *ctx, int on);
+int of2d_ctx_profile_read(of2d_ctx *ctx, char *buf, size_t cap);
 /* reads and clears the sticky per-pair flag words (OF2D_FLAG_*) raised by kernels; synchronises the stream */
 int of2d_poll_status(of2d_ctx *ctx, int batch, unsigned *h_status);
 

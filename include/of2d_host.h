@@ -36,6 +36,9 @@ int of2d_host_use_own_stream(void);
 int of2d_host_sync(void);
 unsigned long long of2d_host_launch_count(void);
 void of2d_host_shutdown(void);
+/* per-kernel CUDA-event timing of the iteration engine (of2d_ctx_profile_* of include/of2d_cuda.h) */
+int of2d_host_profile_enable(int on);
+int of2d_host_profile_read(char *buf, size_t cap);
 
 /* in-process mxArray (real double only), as the interpreter would provide */
 void *of2d_mx_create(int ndim, const size_t *dims);
@@ -60,6 +63,19 @@ int of2d_session_reset(of2d_session *s);
 int of2d_session_get_motion(of2d_session *s, double *planar_out);      /* 2*N doubles: x plane, y plane */
 int of2d_session_get_motion_aos(of2d_session *s, void *out_real);       /* N {x,y} pairs in the field precision */
 int of2d_session_warp(of2d_session *s, const double *img, double *out);
+
+/* extension: `batch` independent pairs of one size registered together on this process's GPU (BASELINE.json
+   configs[4]; one level, cold start per pair = what a fresh ImageRegistration* object with nscales = 0 computes).
+   Iref / Imov: batch images back to back; planar_out: per pair the x plane then the y plane.
+   wave: pairs resident in the engine at a time (0 = default); batch must be a multiple of it. */
+typedef struct of2d_batch of2d_batch;
+int of2d_batch_create(int dimx, int dimy, int batch, int niter, int nrefine, int reg, const double *regparams, int nparams, int wave, of2d_batch **out);
+void of2d_batch_destroy(of2d_batch *b);
+int of2d_batch_set_images(of2d_batch *b, const double *Iref, const double *Imov);
+int of2d_batch_estimate(of2d_batch *b);
+int of2d_batch_get_motion(of2d_batch *b, double *planar_out);
+int of2d_batch_iterations(of2d_batch *b, int *iterations, int *regrids);
+int of2d_batch_wave(of2d_batch *b);
 
 /* trace of the last estimate_motion(); s == NULL addresses the MEX singleton */
 int of2d_trace_num_levels(of2d_session *s);

@@ -30,7 +30,7 @@ from . import _ffi
 DIFFUSION, CURVATURE, ELASTIC, THIRION, DIFFEOMORPHIC, FLUID = range(6)
 METHOD_NAMES = {0: "diffusion", 1: "curvature", 2: "elastic", 3: "thirion", 4: "diffeomorphic", 5: "fluid"}
 
-__all__ = ["OpticalFlow2d", "Session", "cuda", "host", "OF2DError", "DIFFUSION", "CURVATURE", "ELASTIC", "THIRION",
+__all__ = ["OpticalFlow2d", "Session", "Batch", "shard_pairs", "cuda", "host", "OF2DError", "DIFFUSION", "CURVATURE", "ELASTIC", "THIRION",
            "DIFFEOMORPHIC", "FLUID", "METHOD_NAMES"]
 
 
@@ -273,6 +273,68 @@ class Session:
         self.close()
 
 
+class Batch:
+    """`batch` independent pairs registered together (extension, include/of2d_host.h of2d_batch_*).
+    Images: (batch, dimy, dimx) float64; motion: (batch, dimy, dimx, 2)."""
+
+    def __init__(self, dims, batch: int, niter: int, reg: int, regparams, nrefine: int = 1, wave: int = 0, bits: int = 32):
+        self.lib = host(bits)
+        dimx, dimy = dims
+        self.shape = (batch, dimy, dimx)
+        params = _f64(list(regparams) if len(regparams) else [0.0])
+        self.handle = C.c_void_p()
+        _check(self.lib, self.lib.of2d_batch_create(dimx, dimy, batch, niter, nrefine, reg, _ptr(params), len(regparams), wave, C.byref(self.handle)))
+
+    def set_images(self, Iref, Imov):
+        Iref, Imov = _f64(Iref), _f64(Imov)
+        assert Iref.shape == self.shape and Imov.shape == self.shape
+        _check(self.lib, self.lib.of2d_batch_set_images(self.handle, _ptr(Iref), _ptr(Imov)))
+
+    def set_images_raw(self, Iref_ptr: int, Imov_ptr: int):
+        _check(self.lib, self.lib.of2d_batch_set_images(self.handle, C.c_void_p(Iref_ptr), C.c_void_p(Imov_ptr)))
+
+    def estimate(self):
+        _check(self.lib, self.lib.of2d_batch_estimate(self.handle))
+
+    def motion(self) -> np.ndarray:
+        b, dimy, dimx = self.shape
+        planar = np.zeros((b, 2, dimy, dimx))
+        _check(self.lib, self.lib.of2d_batch_get_motion(self.handle, _ptr(planar)))
+        return np.ascontiguousarray(np.moveaxis(planar, 1, -1))
+
+    def motion_raw(self, out_ptr: int):
+        _check(self.lib, self.lib.of2d_batch_get_motion(self.handle, C.c_void_p(out_ptr)))
+
+    def iterations(self):
+        b = self.shape[0]
+        it = np.zeros(b, dtype=np.int32)
+        rg = np.zeros(b, dtype=np.int32)
+        _check(self.lib, self.lib.of2d_batch_iterations(self.handle, _ptr(it), _ptr(rg)))
+        return it, rg
+
+    def wave(self) -> int:
+        return int(self.lib.of2d_batch_wave(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.lib.of2d_batch_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def shard_pairs(total: int, world: int, rank: int):
+    """Contiguous shard [lo, hi) of `total` pairs for `rank` of `world` processes (one per GPU); the
+    solve has no exchange step, so this partition is the whole multi-GPU protocol."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
 def set_strict(strict: bool, bits: int = 32):
     """strict=True: every kernel reproduces the reference's unfused arithmetic bit for bit."""
     lib = host(bits)
@@ -287,6 +349,24 @@ def set_stream(cuda_stream: int, bits: int = 32):
 def synchronize(bits: int = 32):
     lib = host(bits)
     _check(lib, lib.of2d_host_sync())
+
+
+def profile_enable(on: bool, bits: int = 32):
+    """Per-kernel CUDA-event timing of the engine kernels (bench.py's roofline leg)."""
+    lib = host(bits)
+    _check(lib, lib.of2d_host_profile_enable(int(on)))
+
+
+def profile_read(bits: int = 32) -> dict:
+    """{kernel: (launches, total_ms)} since profiling was enabled or last read."""
+    lib = host(bits)
+    buf = C.create_string_buffer(1 << 16)
+    _check(lib, lib.of2d_host_profile_read(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
+    return out
 
 
 def launch_count(bits: int = 32) -> int:

@@ -29,12 +29,22 @@ struct of2d_ctx {
     void *d_mailbox;         // device, 4 KB
     void *d_kernel;          // device copy of convolution weights
     size_t kernel_cap;
+    struct of2d_profiler *prof;   // per-kernel CUDA-event timing (NULL unless enabled)
 };
 
 constexpr int kMaxPartialBlocks = 4096;
 constexpr int kMaxBatchStatus = 8192;
 
 void of2d_set_error(const char *fmt, ...);
+
+// per-kernel timing with CUDA events on the launching stream (ctx.cu); no-ops unless profiling is enabled
+void of2d_prof_begin(of2d_ctx *ctx, const char *name);
+void of2d_prof_end(of2d_ctx *ctx);
+struct ProfScope {
+    of2d_ctx *ctx;
+    ProfScope(of2d_ctx *c, const char *name) : ctx(c) { if (c->prof) of2d_prof_begin(c, name); }
+    ~ProfScope() { if (ctx->prof) of2d_prof_end(ctx); }
+};
 
 #define OF2D_CUDA_TRY(expr)                                                                       \
     do {                                                                                          \

@@ -2,7 +2,28 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
+#include <string>
+#include <vector>
+
 #include "common.cuh"
+
+struct of2d_profiler {
+    struct Rec { std::string name; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t take() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+};
+
+void of2d_prof_begin(of2d_ctx *c, const char *name) {
+    of2d_profiler::Rec r; r.name = name; r.a = c->prof->take(); r.b = c->prof->take();
+    cudaEventRecord(r.a, c->stream);
+    c->prof->recs.push_back(r);
+}
+void of2d_prof_end(of2d_ctx *c) { cudaEventRecord(c->prof->recs.back().b, c->stream); }
 
 static thread_local char g_error[512] = "";
 
@@ -82,6 +103,41 @@ int of2d_ctx_set_fast_math(of2d_ctx *c, int on) {
 }
 int of2d_ctx_get_fast_math(of2d_ctx *c) { return c->fast_math ? 1 : 0; }
 uint64_t of2d_ctx_launch_count(of2d_ctx *c) { return c->launches; }
+
+int of2d_ctx_profile_enable(of2d_ctx *c, int on) {
+    if (on && !c->prof) c->prof = new of2d_profiler();
+    if (c->prof) {
+        cudaStreamSynchronize(c->stream);
+        for (auto &r : c->prof->recs) { c->prof->pool.push_back(r.a); c->prof->pool.push_back(r.b); }
+        c->prof->recs.clear();
+    }
+    if (!on && c->prof) {
+        for (cudaEvent_t e : c->prof->pool) cudaEventDestroy(e);
+        delete c->prof;
+        c->prof = nullptr;
+    }
+    return OF2D_SUCCESS;
+}
+
+// "name count total_ms\n" per kernel since profiling was enabled (or last read); synchronises the stream
+int of2d_ctx_profile_read(of2d_ctx *c, char *buf, size_t cap) {
+    if (!buf || cap == 0) return OF2D_ERR_INVALID;
+    buf[0] = 0;
+    if (!c->prof) return OF2D_SUCCESS;
+    OF2D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    std::map<std::string, std::pair<long, double>> agg;
+    for (auto &r : c->prof->recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { auto &e = agg[r.name]; e.first++; e.second += ms; }
+        c->prof->pool.push_back(r.a); c->prof->pool.push_back(r.b);
+    }
+    c->prof->recs.clear();
+    std::string out;
+    for (auto &kv : agg) { char line[256]; snprintf(line, sizeof(line), "%s %ld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second); out += line; }
+    strncpy(buf, out.c_str(), cap - 1);
+    buf[cap - 1] = 0;
+    return OF2D_SUCCESS;
+}
 
 int of2d_malloc(of2d_ctx *c, size_t bytes, void **p) {
     *p = nullptr;

@@ -414,12 +414,15 @@ int curvature_step_impl(of2d_curvature_plan *P, const R *u, R *unew, const R *gr
             cfg_c = smem_c;
         }
         double2 *specT = (double2 *)P->d_spec;
+        { ProfScope _ps(ctx, "curv_rows_fwd");
         k_cf_rows_fwd<R, LPC><<<dim3(ny / LPC, batch), FFT_THREADS, smem_r, ctx->stream>>>(nx, ny, (const vec2_t<R> *)u, (const vec2_t<R> *)unew, (const vec2_t<R> *)gradI, It,
-                                                                                          (R)P->tau, specT, P->Tx, H);
+                                                                                          (R)P->tau, specT, P->Tx, H); }
         OF2D_LAUNCH_CHECK(ctx);
-        k_cf_cols<<<dim3(nx, batch), FFT_THREADS, smem_c, ctx->stream>>>(nx, ny, specT, P->d_cosx, P->d_cosy, P->tau_alpha, P->Ty, H);
+        { ProfScope _ps(ctx, "curv_cols");
+        k_cf_cols<<<dim3(nx, batch), FFT_THREADS, smem_c, ctx->stream>>>(nx, ny, specT, P->d_cosx, P->d_cosy, P->tau_alpha, P->Ty, H); }
         OF2D_LAUNCH_CHECK(ctx);
-        k_cf_rows_inv<R, LPC><<<dim3(ny / LPC, batch), FFT_THREADS, smem_r, ctx->stream>>>(nx, ny, specT, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN, P->Tx, H);
+        { ProfScope _ps(ctx, "curv_rows_inv");
+        k_cf_rows_inv<R, LPC><<<dim3(ny / LPC, batch), FFT_THREADS, smem_r, ctx->stream>>>(nx, ny, specT, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN, P->Tx, H); }
         OF2D_LAUNCH_CHECK(ctx);
         return OF2D_SUCCESS;
     }

@@ -101,7 +101,7 @@ int launch_conv_kw(of2d_engine *E, const EngK<R> &K, int src, int dst, int which
     const int cx = (W.kw - 1) / 2;
     const size_t smem = sizeof(vec2_t<R>) * (size_t)(TILE + 2 * cx) * (TILE + 2 * cx);
     if (smem > 48 * 1024) OF2D_CUDA_TRY(cudaFuncSetAttribute(k_e_conv<R, EPI, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_e_conv<R, EPI, KW><<<grid_tiles(E), dim3(TX, TY), smem, E->ctx->stream>>>(K, src, dst, W, E->nsq_cap);
+    { ProfScope _ps(E->ctx, EPI == 1 ? "conv_logger" : EPI == 2 ? "conv_maxabs" : "conv"); k_e_conv<R, EPI, KW><<<grid_tiles(E), dim3(TX, TY), smem, E->ctx->stream>>>(K, src, dst, W, E->nsq_cap); }
     OF2D_LAUNCH_CHECK(E->ctx);
     return OF2D_SUCCESS;
 }
@@ -128,7 +128,7 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
     switch (d.method) {
         case 0: {
             const R alpha = (R)d.alpha;
-            k_hs_iter<R><<<g, b, 0, s>>>(K, (const vec2_t<R> *)E->gradI, (const R *)E->It, alpha * alpha);
+            { ProfScope _ps(E->ctx, "hs_iter"); k_hs_iter<R><<<g, b, 0, s>>>(K, (const vec2_t<R> *)E->gradI, (const R *)E->It, alpha * alpha); }
             OF2D_LAUNCH_CHECK(E->ctx);
             break;
         }
@@ -142,20 +142,20 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
         case 3:
         case 4: {
             const R si = (R)d.sigma_i, sx = (R)d.sigma_x;
-            k_e_demons_force<R><<<g, b, 0, s>>>(K, d_Iref, (const R *)E->aux, si * si, sx * sx);
+            { ProfScope _ps(E->ctx, "demons_force"); k_e_demons_force<R><<<g, b, 0, s>>>(K, d_Iref, (const R *)E->aux, si * si, sx * sx); }
             OF2D_LAUNCH_CHECK(E->ctx);
             if (d.method == 3) {
                 TRY((launch_conv<R, 0>(E, K, B_C0, B_C1, 0)));
-                k_e_compose<R><<<g, b, 0, s>>>(K, G_ACTIVE, B_EST_CUR, B_C1, B_C0, d.accumulation == 1);
+                { ProfScope _pc(E->ctx, "compose"); k_e_compose<R><<<g, b, 0, s>>>(K, G_ACTIVE, B_EST_CUR, B_C1, B_C0, d.accumulation == 1); }
                 OF2D_LAUNCH_CHECK(E->ctx);
                 TRY((launch_conv<R, 1>(E, K, B_C0, B_EST_NEXT, 1)));
             } else {
                 TRY((launch_conv<R, 2>(E, K, B_C0, B_C1, 0)));
                 for (int q = 0; q < E->nsq_cap; q++) {
-                    k_e_square<R><<<g, b, 0, s>>>(K, q);
+                    { ProfScope _ps(E->ctx, "square"); k_e_square<R><<<g, b, 0, s>>>(K, q); }
                     OF2D_LAUNCH_CHECK(E->ctx);
                 }
-                k_e_compose<R><<<g, b, 0, s>>>(K, G_ACTIVE, B_EST_CUR, B_CRES, B_CTMP, 0);
+                { ProfScope _pc(E->ctx, "compose"); k_e_compose<R><<<g, b, 0, s>>>(K, G_ACTIVE, B_EST_CUR, B_CRES, B_CTMP, 0); }
                 OF2D_LAUNCH_CHECK(E->ctx);
                 TRY((launch_conv<R, 1>(E, K, B_CTMP, B_EST_NEXT, 1)));
             }
@@ -165,16 +165,16 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
             TRY(sor_tile_launch<R>(E->ctx, E->sor, K.ctl, K.n_active, K.partials, K.pstride, K.tr, 1, (vec2_t<R> *)E->vel[0], (vec2_t<R> *)E->vel[1],
                                    (const vec2_t<R> *)E->est[0], (const vec2_t<R> *)E->est[1], (const vec2_t<R> *)E->gradI, (const R *)E->It));
             const dim3 gt = g;
-            k_fl_increment<R><<<gt, b, 0, s>>>(K, (vec2_t<R> *)E->vel[0], (vec2_t<R> *)E->vel[1], (vec2_t<R> *)E->incr);
+            { ProfScope _ps(E->ctx, "fluid_increment"); k_fl_increment<R><<<gt, b, 0, s>>>(K, (vec2_t<R> *)E->vel[0], (vec2_t<R> *)E->vel[1], (vec2_t<R> *)E->incr); }
             OF2D_LAUNCH_CHECK(E->ctx);
-            k_fl_integrate<R><<<gt, b, 0, s>>>(K, (const vec2_t<R> *)E->incr);
+            { ProfScope _ps(E->ctx, "fluid_integrate"); k_fl_integrate<R><<<gt, b, 0, s>>>(K, (const vec2_t<R> *)E->incr); }
             OF2D_LAUNCH_CHECK(E->ctx);
             // regrid (ImageRegistrationFluid.cpp:108-124): level <- est + level o (id + est); est <- 0; re-warp; derivatives
             k_e_untranspose<R><<<g, b, 0, s>>>(K, G_REGRID, B_EST_CUR, B_ESTN);
             OF2D_LAUNCH_CHECK(E->ctx);
-            k_e_compose<R><<<g, b, 0, s>>>(K, G_REGRID, B_LVL_CUR, B_ESTN, B_LVL_NEXT, 0);
+            { ProfScope _pc(E->ctx, "regrid_compose"); k_e_compose<R><<<g, b, 0, s>>>(K, G_REGRID, B_LVL_CUR, B_ESTN, B_LVL_NEXT, 0); }
             OF2D_LAUNCH_CHECK(E->ctx);
-            k_e_zero<R><<<dim3(E->ctx->sm_count * 2, K.batch), 256, 0, s>>>(K, G_REGRID, B_EST_NEXT, 1);
+            k_e_zero<R><<<dim3(ceil_div(E->ctx->sm_count * 2, K.batch), K.batch), 256, 0, s>>>(K, G_REGRID, B_EST_NEXT, 1);
             OF2D_LAUNCH_CHECK(E->ctx);
             k_e_warp<R><<<g, b, 0, s>>>(K, G_REGRID, (const R *)E->cur_Imov, B_LVL_NEXT, (R *)E->aux);
             OF2D_LAUNCH_CHECK(E->ctx);
@@ -245,9 +245,9 @@ int refine_impl(of2d_engine *E, const R *d_Iref, const R *d_Imov, R *d_motion, i
     if (E->transposed) {
         k_e_untranspose<R><<<g, b, 0, s>>>(K, G_NONE, B_EST_CUR, B_ESTN);
         OF2D_LAUNCH_CHECK(ctx);
-        k_e_compose<R><<<g, b, 0, s>>>(K, G_NONE, B_LVL_CUR, B_ESTN, B_EXT, 0);
+        { ProfScope _pc(E->ctx, "final_compose"); k_e_compose<R><<<g, b, 0, s>>>(K, G_NONE, B_LVL_CUR, B_ESTN, B_EXT, 0); }
     } else {
-        k_e_compose<R><<<g, b, 0, s>>>(K, G_NONE, B_LVL_CUR, B_EST_CUR, B_EXT, 0);
+        { ProfScope _pc(E->ctx, "final_compose"); k_e_compose<R><<<g, b, 0, s>>>(K, G_NONE, B_LVL_CUR, B_EST_CUR, B_EXT, 0); }
     }
     OF2D_LAUNCH_CHECK(ctx);
     OF2D_CUDA_TRY(cudaMemcpyAsync(E->h_ctl.data(), E->d_ctl, sizeof(PairCtl) * K.batch, cudaMemcpyDeviceToHost, s));

@@ -375,13 +375,13 @@ static int sor_tile_launch(of2d_ctx *ctx, const SorPlan &S, PairCtl *ctl, int *n
             OF2D_CUDA_TRY(cudaFuncSetAttribute(k_sor_tile<R, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             configured[pi][1] = true;
         }
-        k_sor_tile<R, 4, true><<<grid, S.NT, smem, ctx->stream>>>(A);
+        { ProfScope _ps(ctx, "sor_tile_fluid"); k_sor_tile<R, 4, true><<<grid, S.NT, smem, ctx->stream>>>(A); }
     } else {
         if (!configured[pi][0]) {
             OF2D_CUDA_TRY(cudaFuncSetAttribute(k_sor_tile<R, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             configured[pi][0] = true;
         }
-        k_sor_tile<R, 4, false><<<grid, S.NT, smem, ctx->stream>>>(A);
+        { ProfScope _ps(ctx, "sor_tile_elastic"); k_sor_tile<R, 4, false><<<grid, S.NT, smem, ctx->stream>>>(A); }
     }
     OF2D_LAUNCH_CHECK(ctx);
     return OF2D_SUCCESS;

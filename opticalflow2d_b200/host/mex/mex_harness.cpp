@@ -13,6 +13,7 @@
 #include <mex.h>
 #include <of2d_host.h>
 
+#include <src/BatchRegistration.h>
 #include <src/DeviceRuntime.h>
 #include <src/Image.h>
 #include <src/ImageRegistrationDemons.h>
@@ -117,6 +118,12 @@ unsigned long long of2d_host_launch_count(void) {
     return n;
 }
 void of2d_host_shutdown(void) { of2d::release_context(); }
+int of2d_host_profile_enable(int on) {
+    return guarded([&] { of2d::check(of2d_ctx_profile_enable(of2d::context(), on)); });
+}
+int of2d_host_profile_read(char* buf, size_t cap) {
+    return guarded([&] { of2d::check(of2d_ctx_profile_read(of2d::context(), buf, cap)); });
+}
 
 void* of2d_mx_create(int ndim, const size_t* dims) { return mxCreateNumericArray((mwSize)ndim, dims, mxDOUBLE_CLASS, mxREAL); }
 double* of2d_mx_data(void* mx) { return static_cast<mxArray*>(mx)->data; }
@@ -191,6 +198,43 @@ int of2d_session_warp(of2d_session* s, const double* img, double* out) {
         m.copy_image_to_input(out);
     });
 }
+
+// ---- batch API (extension): independent pairs registered together ----------------------------------
+struct of2d_batch {
+    std::unique_ptr<BatchRegistration> reg;
+};
+
+int of2d_batch_create(int dimx, int dimy, int batch, int niter, int nrefine, int reg, const double* regparams, int nparams, int wave, of2d_batch** out) {
+    *out = nullptr;
+    return guarded([&] {
+        std::vector<of2d_real> p((size_t)(nparams > 0 ? nparams : 1));
+        for (int k = 0; k < nparams; k++) p[(size_t)k] = (of2d_real)regparams[k];
+        if (reg < 0 || reg > 5) mexErrMsgTxt("Error: invalid regularisation given\n");
+        std::unique_ptr<of2d_batch> b(new of2d_batch());
+        b->reg.reset(new BatchRegistration(dim((unsigned int)dimx, (unsigned int)dimy), batch, niter, nrefine, static_cast<Regularisation>(reg), p.data(),
+                                           (unsigned)nparams, wave));
+        *out = b.release();
+    });
+}
+void of2d_batch_destroy(of2d_batch* b) { delete b; }
+int of2d_batch_set_images(of2d_batch* b, const double* Iref, const double* Imov) {
+    return guarded([&] { b->reg->set_images(Iref, Imov); });
+}
+int of2d_batch_estimate(of2d_batch* b) {
+    return guarded([&] { b->reg->estimate_motion(); });
+}
+int of2d_batch_get_motion(of2d_batch* b, double* planar_out) {
+    return guarded([&] { b->reg->copy_estimated_motion(planar_out); });
+}
+int of2d_batch_iterations(of2d_batch* b, int* iterations, int* regrids) {
+    return guarded([&] {
+        for (int k = 0; k < b->reg->size(); k++) {
+            if (iterations) iterations[k] = b->reg->iterations()[(size_t)k];
+            if (regrids) regrids[k] = b->reg->regrids()[(size_t)k];
+        }
+    });
+}
+int of2d_batch_wave(of2d_batch* b) { return b->reg->wave_size(); }
 
 // ---- trace access: `s` may be NULL to address the MEX singleton -------------------------------------
 static const RegistrationTrace* pick_trace(of2d_session* s) { return trace_of(s ? s->reg.get() : of2d_wrapper_registration()); }
