@@ -136,4 +136,7 @@ template <class R, bool IS_MAX> __device__ __forceinline__ R block_extreme(R v) 
     return v;
 }
 
+// raises (never lowers) a kernel's dynamic shared-memory limit; one record per kernel function per process
+int of2d_ensure_dynamic_smem(const void *kernel, size_t bytes);
+
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }

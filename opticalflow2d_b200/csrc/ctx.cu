@@ -18,6 +18,17 @@ struct of2d_profiler {
     }
 };
 
+int of2d_ensure_dynamic_smem(const void *kernel, size_t bytes) {
+    static std::map<const void *, size_t> configured;
+    if (bytes <= 48 * 1024) return OF2D_SUCCESS;
+    size_t &cur = configured[kernel];
+    if (bytes > cur) {
+        OF2D_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+    return OF2D_SUCCESS;
+}
+
 void of2d_prof_begin(of2d_ctx *c, const char *name) {
     of2d_profiler::Rec r; r.name = name; r.a = c->prof->take(); r.b = c->prof->take();
     cudaEventRecord(r.a, c->stream);
@@ -59,6 +70,12 @@ int of2d_ctx_create(int device, of2d_ctx **out) {
     c->fast_math = true;
     OF2D_CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     OF2D_CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    {   // keep freed blocks in the pool instead of returning them to the driver at every synchronisation
+        cudaMemPool_t pool;
+        OF2D_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        OF2D_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     c->stream = c->own_stream;
     OF2D_CUDA_TRY(cudaMalloc(&c->d_partials, sizeof(double) * kMaxPartialBlocks * 4));
     OF2D_CUDA_TRY(cudaMalloc(&c->d_status, sizeof(unsigned) * kMaxBatchStatus));
@@ -141,14 +158,14 @@ int of2d_ctx_profile_read(of2d_ctx *c, char *buf, size_t cap) {
 
 int of2d_malloc(of2d_ctx *c, size_t bytes, void **p) {
     *p = nullptr;
-    OF2D_CUDA_TRY(cudaSetDevice(c->device));
-    OF2D_CUDA_TRY(cudaMalloc(p, bytes ? bytes : 1));
+    // stream-ordered allocation from the device's default pool (kept cached: see of2d_ctx_create), so the
+    // temporaries the reference API creates per call (Image / Motion copies) cost no cudaMalloc / cudaFree
+    OF2D_CUDA_TRY(cudaMallocAsync(p, bytes ? bytes : 1, c->stream));
     return OF2D_SUCCESS;
 }
 int of2d_free(of2d_ctx *c, void *p) {
     if (!p) return OF2D_SUCCESS;
-    OF2D_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    OF2D_CUDA_TRY(cudaFree(p));
+    OF2D_CUDA_TRY(cudaFreeAsync(p, c->stream));
     return OF2D_SUCCESS;
 }
 int of2d_host_alloc(size_t bytes, void **p) {

@@ -403,16 +403,9 @@ int curvature_step_impl(of2d_curvature_plan *P, const R *u, R *unew, const R *gr
                       sizeof(double2) * (size_t)ny <= kMaxSmem;
     if (fast) {   // dct_fast.cuh: transposed spectrum, radix-8/4 FFT
         const size_t smem_r = sizeof(double2) * (size_t)nx * LPC, smem_c = sizeof(double2) * (size_t)ny;
-        static size_t cfg_r = 0, cfg_c = 0;
-        if (smem_r > cfg_r) {
-            OF2D_CUDA_TRY(cudaFuncSetAttribute(k_cf_rows_fwd<R, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-            OF2D_CUDA_TRY(cudaFuncSetAttribute(k_cf_rows_inv<R, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-            cfg_r = smem_r;
-        }
-        if (smem_c > cfg_c) {
-            OF2D_CUDA_TRY(cudaFuncSetAttribute(k_cf_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-            cfg_c = smem_c;
-        }
+        { int st = of2d_ensure_dynamic_smem((const void *)k_cf_rows_fwd<R, LPC>, smem_r); if (st) return st; }
+        { int st = of2d_ensure_dynamic_smem((const void *)k_cf_rows_inv<R, LPC>, smem_r); if (st) return st; }
+        { int st = of2d_ensure_dynamic_smem((const void *)k_cf_cols, smem_c); if (st) return st; }
         double2 *specT = (double2 *)P->d_spec;
         { ProfScope _ps(ctx, "curv_rows_fwd");
         k_cf_rows_fwd<R, LPC><<<dim3(ny / LPC, batch), FFT_THREADS, smem_r, ctx->stream>>>(nx, ny, (const vec2_t<R> *)u, (const vec2_t<R> *)unew, (const vec2_t<R> *)gradI, It,
@@ -426,16 +419,9 @@ int curvature_step_impl(of2d_curvature_plan *P, const R *u, R *unew, const R *gr
         OF2D_LAUNCH_CHECK(ctx);
         return OF2D_SUCCESS;
     }
-    static size_t configured_rows = 0, configured_cols = 0;   // per template instance: largest dynamic size set so far
-    if (P->smem_rows > configured_rows) {
-        OF2D_CUDA_TRY(cudaFuncSetAttribute(k_curv_rows_fwd<R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_rows));
-        OF2D_CUDA_TRY(cudaFuncSetAttribute(k_curv_rows_inv<R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_rows));
-        configured_rows = P->smem_rows;
-    }
-    if (P->smem_cols > configured_cols) {
-        OF2D_CUDA_TRY(cudaFuncSetAttribute(k_curv_cols<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_cols));
-        configured_cols = P->smem_cols;
-    }
+    { int st = of2d_ensure_dynamic_smem((const void *)k_curv_rows_fwd<R, S>, P->smem_rows); if (st) return st; }
+    { int st = of2d_ensure_dynamic_smem((const void *)k_curv_rows_inv<R, S>, P->smem_rows); if (st) return st; }
+    { int st = of2d_ensure_dynamic_smem((const void *)k_curv_cols<S>, P->smem_cols); if (st) return st; }
     k_curv_rows_fwd<R, S><<<dim3(ny, batch), FFT_THREADS, P->smem_rows, ctx->stream>>>(nx, ny, (const vec2_t<R> *)u, (const vec2_t<R> *)unew, (const vec2_t<R> *)gradI, It,
                                                                                       (R)P->tau, spec, P->Tx, H);
     OF2D_LAUNCH_CHECK(ctx);
@@ -548,7 +534,7 @@ int of2d_dct2d_f64(of2d_ctx *ctx, int n0, int n1, int kind, double *d) {
         const size_t s1 = sizeof(double2) * (size_t)n1 * 2, s0 = sizeof(double2) * (size_t)n0 * 2;
         if (s0 > kMaxSmem || s1 > kMaxSmem) { of2d_set_error("of2d_dct2d_f64: line too long for shared memory"); st = OF2D_ERR_UNSUPPORTED; }
         else {
-            cudaFuncSetAttribute(k_dct_lines<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+            of2d_ensure_dynamic_smem((const void *)k_dct_lines<double>, s1 > s0 ? s1 : s0);
             k_dct_lines<double><<<n0, FFT_THREADS, s1, ctx->stream>>>(n0, n1, (size_t)n1, 1, kind, d, T1);   // dimension 1 (contiguous)
             ctx->launches++;
             k_dct_lines<double><<<n1, FFT_THREADS, s0, ctx->stream>>>(n1, n0, 1, (size_t)n1, kind, d, T0);   // dimension 0 (stride n1)

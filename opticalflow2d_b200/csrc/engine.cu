@@ -60,6 +60,8 @@ struct of2d_engine {
 
 namespace {
 
+#define TRY(x) do { int _s = (x); if (_s) return _s; } while (0)
+
 template <class R>
 EngK<R> make_k(of2d_engine *E) {
     EngK<R> K;
@@ -100,7 +102,7 @@ int launch_conv_kw(of2d_engine *E, const EngK<R> &K, int src, int dst, int which
     const ConvW<R> W = conv_weights<R>(E, which);
     const int cx = (W.kw - 1) / 2;
     const size_t smem = sizeof(vec2_t<R>) * (size_t)(TILE + 2 * cx) * (TILE + 2 * cx);
-    if (smem > 48 * 1024) OF2D_CUDA_TRY(cudaFuncSetAttribute(k_e_conv<R, EPI, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TRY(of2d_ensure_dynamic_smem((const void *)k_e_conv<R, EPI, KW>, smem));
     { ProfScope _ps(E->ctx, EPI == 1 ? "conv_logger" : EPI == 2 ? "conv_maxabs" : "conv"); k_e_conv<R, EPI, KW><<<grid_tiles(E), dim3(TX, TY), smem, E->ctx->stream>>>(K, src, dst, W, E->nsq_cap); }
     OF2D_LAUNCH_CHECK(E->ctx);
     return OF2D_SUCCESS;
@@ -117,7 +119,6 @@ int launch_conv(of2d_engine *E, const EngK<R> &K, int src, int dst, int which) {
     }
 }
 
-#define TRY(x) do { int _s = (x); if (_s) return _s; } while (0)
 
 // one iteration of method `m`, enqueued on the context's stream
 template <class R>

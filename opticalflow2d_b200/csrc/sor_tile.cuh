@@ -368,19 +368,11 @@ static int sor_tile_launch(of2d_ctx *ctx, const SorPlan &S, PairCtl *ctl, int *n
     const size_t stage = (size_t)(A.LR + 4) * sizeof(vec2_t<R>) + (size_t)A.LR * (sizeof(vec2_t<R>) * (fluid ? 2 : 1) + sizeof(R));
     const size_t smem = SOR_NS * stage + 2 * (size_t)S.NT * 2 * sizeof(vec2_t<R>);
     const dim3 grid(S.nbands, S.nstrips, S.batch);
-    static bool configured[2][2] = {};
-    const int pi = sizeof(R) == 8;
     if (fluid) {
-        if (!configured[pi][1]) {
-            OF2D_CUDA_TRY(cudaFuncSetAttribute(k_sor_tile<R, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            configured[pi][1] = true;
-        }
+        { int st = of2d_ensure_dynamic_smem((const void *)k_sor_tile<R, 4, true>, smem); if (st) return st; }
         { ProfScope _ps(ctx, "sor_tile_fluid"); k_sor_tile<R, 4, true><<<grid, S.NT, smem, ctx->stream>>>(A); }
     } else {
-        if (!configured[pi][0]) {
-            OF2D_CUDA_TRY(cudaFuncSetAttribute(k_sor_tile<R, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            configured[pi][0] = true;
-        }
+        { int st = of2d_ensure_dynamic_smem((const void *)k_sor_tile<R, 4, false>, smem); if (st) return st; }
         { ProfScope _ps(ctx, "sor_tile_elastic"); k_sor_tile<R, 4, false><<<grid, S.NT, smem, ctx->stream>>>(A); }
     }
     OF2D_LAUNCH_CHECK(ctx);

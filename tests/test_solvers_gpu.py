@@ -187,7 +187,8 @@ def test_curvature_steps(bits, dimx, dimy):
     dg, dit = to_dev(g), to_dev(it)
     fn = getattr(dev.lib, "of2d_curvature_step_f32" if bits == 32 else "of2d_curvature_step_f64")
     for _ in range(nsteps):
-        assert fn(plan, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(dg.data_ptr()), C.c_void_p(dit.data_ptr())) == 0
+        st = fn(plan, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(dg.data_ptr()), C.c_void_p(dit.data_ptr()))
+        assert st == 0, dev.lib.of2d_last_error()
         a, b = b, a
     got = a.cpu().numpy()
     dev.lib.of2d_curvature_plan_destroy(plan)
