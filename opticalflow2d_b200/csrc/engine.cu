@@ -101,7 +101,8 @@ template <class R, int EPI, int KW>
 int launch_conv_kw(of2d_engine *E, const EngK<R> &K, int src, int dst, int which) {
     const ConvW<R> W = conv_weights<R>(E, which);
     const int cx = (W.kw - 1) / 2;
-    const size_t smem = sizeof(vec2_t<R>) * (size_t)(TILE + 2 * cx) * (TILE + 2 * cx);
+    const int shift = sizeof(vec2_t<R>) == 8 ? (cx & 1) : 0;
+    const size_t smem = 2 * sizeof(vec2_t<R>) * (size_t)(TILE + 2 * cx) * (size_t)((TILE + 2 * cx + shift + 1) & ~1);
     TRY(of2d_ensure_dynamic_smem((const void *)k_e_conv<R, EPI, KW>, smem));
     { ProfScope _ps(E->ctx, EPI == 1 ? "conv_logger" : EPI == 2 ? "conv_maxabs" : "conv"); k_e_conv<R, EPI, KW><<<grid_tiles(E), dim3(TX, TY), smem, E->ctx->stream>>>(K, src, dst, W, E->nsq_cap); }
     OF2D_LAUNCH_CHECK(E->ctx);

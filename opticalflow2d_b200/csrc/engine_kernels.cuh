@@ -11,6 +11,7 @@
 
 #include "device_math.cuh"
 #include "engine_ctl.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -387,22 +388,53 @@ __global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int d
     const int kw = KW > 0 ? KW : W.kw;
     const int cx = (kw - 1) / 2;
     const int SW = TILE + 2 * cx, SH = TILE + 2 * cx;
-    vec2_t<R> *tile_s = reinterpret_cast<vec2_t<R> *>(smem_raw);   // [SH][SW]
+    // Two tile stages.  Interior tiles arrive by TMA: one bulk copy per tile row (a tile row is a contiguous range of
+    // the FLAT array, which is exactly the reference's addressing), issued by warp 0 one tile ahead of the compute.
+    // 16-byte alignment of the copies: for 8-byte elements the window is extended by `shift` elements to the left.
+    const int shift = sizeof(vec2_t<R>) == 8 ? (cx & 1) : 0;
+    const int SWp = (SW + shift + 1) & ~1;
+    const bool rows_aligned = sizeof(vec2_t<R>) == 16 || (nx & 1) == 0;
+    vec2_t<R> *const stages = reinterpret_cast<vec2_t<R> *>(smem_raw);   // [2][SH][SWp]; indexed arithmetically so accesses stay LDS/STS
+    const int stage_elems = SH * SWp;
+    __shared__ uint64_t cbar[2];
     const int tid = threadIdx.x + threadIdx.y * TX;
+    if (tid == 0) { mbar_init(&cbar[0], 1); mbar_init(&cbar[1], 1); mbar_init_fence(); }
+    __syncthreads();
     const TileWalk T(nx, ny);
+    auto tile_start = [&](int tile, int r) -> long {   // flat index of element (r, -shift) of the tile's window
+        const int i0 = (tile % T.tiles_x) * TILE, j0 = (tile / T.tiles_x) * TILE;
+        return (long)(j0 + r - cx) * nx + (i0 - cx - shift);
+    };
+    auto tma_ok = [&](int tile) -> bool { return rows_aligned && tile_start(tile, 0) >= 0 && tile_start(tile, SH - 1) + SWp <= n; };
+    auto issue = [&](int tile, int st) {   // warp 0
+        const int lane = threadIdx.x;
+        if (lane == 0) { proxy_fence_async(); mbar_expect_tx(&cbar[st], (unsigned)(SH * SWp * sizeof(vec2_t<R>))); }
+        __syncwarp();
+        for (int r = lane; r < SH; r += 32) bulk_g2s(stages + st * stage_elems + r * SWp, in + tile_start(tile, r), (unsigned)(SWp * sizeof(vec2_t<R>)), &cbar[st]);
+    };
     double sd = 0.0, sp = 0.0;
     R mx = (R)0;
-    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
+    unsigned uses[2] = {0u, 0u};
+    if ((int)blockIdx.x < T.ntiles && threadIdx.y == 0 && tma_ok(blockIdx.x)) issue(blockIdx.x, 0);
+    int kiter = 0;
+    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x, kiter++) {
         const int i0 = (tile % T.tiles_x) * TILE, j0 = (tile / T.tiles_x) * TILE;
-        __syncthreads();
-        for (int e = tid; e < SH * SW; e += TX * TY) {
-            const int r = e / SW, cc = e - r * SW;
-            const long lin = (long)(j0 + r - cx) * nx + (i0 + cc - cx);
-            vec2_t<R> v = mk2<R>((R)0, (R)0);
-            if (lin >= 0 && lin < n) v = in[lin];
-            tile_s[e] = v;
+        const int st = kiter & 1, next = tile + gridDim.x;
+        if (next < T.ntiles && threadIdx.y == 0 && tma_ok(next)) issue(next, st ^ 1);   // stage st^1 was last read one iteration ago
+        vec2_t<R> *tile_s = stages + st * stage_elems + shift;    // element (r, cc) of the window at tile_s[r * SWp + cc]
+        if (tma_ok(tile)) {
+            mbar_wait(&cbar[st], uses[st] & 1u);
+            uses[st]++;
+        } else {
+            for (int e = tid; e < SH * SW; e += TX * TY) {
+                const int r = e / SW, cc = e - r * SW;
+                const long lin = (long)(j0 + r - cx) * nx + (i0 + cc - cx);
+                vec2_t<R> v = mk2<R>((R)0, (R)0);
+                if (lin >= 0 && lin < n) v = in[lin];
+                tile_s[r * SWp + cc] = v;
+            }
+            __syncthreads();
         }
-        __syncthreads();
         const int i = i0 + threadIdx.x;
         const int jl0 = 4 * threadIdx.y;
         // every tap of every pixel of the tile inside [0, n)?  (first / last flat index of the tile's windows)
@@ -417,7 +449,7 @@ __global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int d
             for (int ii = 0; ii < KW; ii++) {
                 vec2_t<R> col[4 + (KW > 0 ? KW : 1) - 1];
 #pragma unroll
-                for (int r = 0; r < 4 + KW - 1; r++) col[r] = tile_s[(jl0 + r) * SW + threadIdx.x + ii];
+                for (int r = 0; r < 4 + KW - 1; r++) col[r] = tile_s[(jl0 + r) * SWp + threadIdx.x + ii];
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
 #pragma unroll
@@ -430,7 +462,7 @@ __global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int d
             }
             const R wgt = (R)W.full_weight;
 #pragma unroll
-            for (int q = 0; q < 4; q++) o[q] = W.full_weight != 0 ? mk2<R>(ax[q] / wgt, ay[q] / wgt) : tile_s[(jl0 + q + cx) * SW + threadIdx.x + cx];
+            for (int q = 0; q < 4; q++) o[q] = W.full_weight != 0 ? mk2<R>(ax[q] / wgt, ay[q] / wgt) : tile_s[(jl0 + q + cx) * SWp + threadIdx.x + cx];
         } else {
 #pragma unroll 1
             for (int q = 0; q < 4; q++) {
@@ -444,14 +476,14 @@ __global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int d
                         if (lin < 0 || lin >= n) continue;
                         const int ik = (ii + cx) + (jj + cx) * kw;
                         weight += W.taps_d[ik];
-                        const vec2_t<R> f = tile_s[(jl0 + q + jj + cx) * SW + (threadIdx.x + ii + cx)];
+                        const vec2_t<R> f = tile_s[(jl0 + q + jj + cx) * SWp + (threadIdx.x + ii + cx)];
                         const R t = W.w[ik];
                         ax = ax + f.x * t;
                         ay = ay + f.y * t;
                     }
                 }
                 if (weight != 0) { const R wg = (R)weight; o[q] = mk2<R>(ax / wg, ay / wg); }
-                else o[q] = tile_s[(jl0 + q + cx) * SW + threadIdx.x + cx];
+                else o[q] = tile_s[(jl0 + q + cx) * SWp + threadIdx.x + cx];
             }
         }
         if (i < nx) {
@@ -471,6 +503,7 @@ __global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int d
                 }
             }
         }
+        __syncthreads();   // everybody is done with stage st before warp 0 refills it (one iteration from now)
     }
     if (EPI == 0) return;
     if (EPI == 1) {

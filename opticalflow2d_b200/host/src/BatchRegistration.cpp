@@ -37,13 +37,15 @@ BatchRegistration::BatchRegistration(const dim dimin, const int batch_, const in
     d.dimx = (int)grid.x; d.dimy = (int)grid.y; d.batch = wave;
     d.real_is_double = sizeof(of2d_real) == 8;
     d.max_iter = niter;
-    const of2d_real omega_default = 0.66;
+    // the reference's defaults: Elastic `omega = 0.66f` (OpticalFlowElastic.h:9), Fluid `omega = 0.66` (OpticalFlowFluid.h:10):
+    // they differ in the fp64 build
+    const of2d_real omega_elastic = 0.66f, omega_fluid = 0.66;
     Kernel kf(1u), kd(1u);
     switch (reg) {
         case Regularisation::Diffusion: d.alpha = p[0]; break;
         case Regularisation::Curvature: d.alpha = p[0]; d.tau = nparams > 1 ? p[1] : (of2d_real)1; break;
-        case Regularisation::Elastic:
-        case Regularisation::Fluid: d.mu = p[0]; d.lambda = p[1]; d.omega = nparams > 2 ? p[2] : omega_default; break;
+        case Regularisation::Elastic: d.mu = p[0]; d.lambda = p[1]; d.omega = nparams > 2 ? p[2] : omega_elastic; break;
+        case Regularisation::Fluid: d.mu = p[0]; d.lambda = p[1]; d.omega = nparams > 2 ? p[2] : omega_fluid; break;
         case Regularisation::ThirionsDemons:
         case Regularisation::DiffeomorphicDemons: {
             d.sigma_i = p[0]; d.sigma_x = p[1];

@@ -7,7 +7,7 @@
  * Parity status: PINNED against the reference itself.  The reference has no
  * tests or golden vectors, so the pin is
  * oracle/_ref/libof2d_ref{32,64}.so -- the reference's own sources compiled
- * unchanged in the authoring container -- and tests/test_oracle_vs_ref.py
+ * unchanged in the authoring container -- and tests/test_oracle_cpu.py
  * requires this restatement to reproduce its outputs bit for bit, plus the
  * fixtures in tests/golden/ generated from it (tests/golden/make_golden.py).
  *

@@ -1,0 +1,10 @@
+#!/bin/bash
+# round profile: launch list of one bench step + full captures of the main kernels (2048^2 fp32)
+python bench.py --steps 1 --warmup 1 --quick > gpurun_out/quick_plain.log 2>&1 || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 1 --warmup 1 --quick > gpurun_out/quick_ncu.log 2>&1
+for spec in curvature:k_cf_cols:curv_cols curvature:k_cf_rows_fwd:curv_rows_fwd curvature:k_cf_rows_inv:curv_rows_inv thirion:k_e_demons_force:demons_force thirion:k_e_compose:compose fluid:k_fl_integrate:fluid_integrate fluid:k_fl_increment:fluid_increment fluid:k_sor_tile:sor_tile_fluid elastic:k_sor_tile:sor_tile_elastic diffusion:k_hs_iter:hs_iter; do
+  IFS=: read m k t <<< "$spec"
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 10 -c 1 -f -o gpurun_out/r1_$t python bench.py --steps 1 --warmup 0 --quick --methods $m > gpurun_out/ncu_$t.log 2>&1 || echo "ncu $t failed"
+done
+ncu --set full --clock-control none --import-source on -k regex:k_e_conv -s 11 -c 1 -f -o gpurun_out/r1_conv_logger python bench.py --steps 1 --warmup 0 --quick --methods thirion > gpurun_out/ncu_conv.log 2>&1
+ls gpurun_out/r1_*.ncu-rep | wc -l
