@@ -412,7 +412,9 @@ int curvature_step_impl(of2d_curvature_plan *P, const R *u, R *unew, const R *gr
                                                                                           (R)P->tau, specT, P->Tx, H); }
         OF2D_LAUNCH_CHECK(ctx);
         { ProfScope _ps(ctx, "curv_cols");
-        k_cf_cols<<<dim3(nx, batch), FFT_THREADS, smem_c, ctx->stream>>>(nx, ny, specT, P->d_cosx, P->d_cosy, P->tau_alpha, P->Ty, H); }
+        static int cols_threads = 0;
+        if (!cols_threads) { const char *e = getenv("OF2D_FFT_COLS_THREADS"); cols_threads = e && atoi(e) >= 32 ? atoi(e) : FFT_THREADS; }
+        k_cf_cols<<<dim3(nx, batch), cols_threads, smem_c, ctx->stream>>>(nx, ny, specT, P->d_cosx, P->d_cosy, P->tau_alpha, P->Ty, H); }
         OF2D_LAUNCH_CHECK(ctx);
         { ProfScope _ps(ctx, "curv_rows_inv");
         k_cf_rows_inv<R, LPC><<<dim3(ny / LPC, batch), FFT_THREADS, smem_r, ctx->stream>>>(nx, ny, specT, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN, P->Tx, H); }

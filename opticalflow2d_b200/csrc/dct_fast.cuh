@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(FFT_THREADS) k_cf_rows_fwd(int nx, int ny, con
 }
 
 // ---- P2: one spectrum column (contiguous in spec_T) per CTA: DCT-II along y, eigenvalues, DCT-III along y ----
-__global__ void __launch_bounds__(FFT_THREADS) k_cf_cols(int nx, int ny, double2 *__restrict__ specT, const double *__restrict__ cosx, const double *__restrict__ cosy,
+#ifndef OF2D_COLS_MINB
+#define OF2D_COLS_MINB 1
+#endif
+__global__ void __launch_bounds__(FFT_THREADS, OF2D_COLS_MINB) k_cf_cols(int nx, int ny, double2 *__restrict__ specT, const double *__restrict__ cosx, const double *__restrict__ cosy,
                                                          double tau_alpha, LineTables T, CurvHook H) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2 *x = reinterpret_cast<double2 *>(smem_raw);   // [ny]

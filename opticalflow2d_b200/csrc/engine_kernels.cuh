@@ -83,8 +83,22 @@ __device__ __forceinline__ bool gate_open(const CtlHot &h, int gate) {
 
 // Motion::norm addend (Motion.cpp:45).  The reference takes the square root in double of float data;
 // the fp32 build of the engine takes it in float (1 ulp of a term that is then averaged over all pixels).
-__device__ __forceinline__ double norm_term(float2 v) { return (double)sqrtf(v.x * v.x + v.y * v.y); }
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float norm_term_f(float2 v) { return sqrt_approx(v.x * v.x + v.y * v.y); }
+__device__ __forceinline__ double norm_term(float2 v) { return (double)norm_term_f(v); }
 __device__ __forceinline__ double norm_term(double2 v) { return sqrt(v.x * v.x + v.y * v.y); }
+
+// per-thread accumulation of the Logger terms: in the field precision within a tile, flushed into double per tile
+template <class R> struct NormAcc {
+    R sd = 0, sp = 0;
+    double dsd = 0.0, dsp = 0.0;
+    __device__ __forceinline__ void add(vec2_t<R> nv, vec2_t<R> old) {
+        const vec2_t<R> df = mk2<R>(nv.x - old.x, nv.y - old.y);
+        if (sizeof(R) == 4) { sd += (R)norm_term_f(make_float2((float)df.x, (float)df.y)); sp += (R)norm_term_f(make_float2((float)old.x, (float)old.y)); }
+        else { sd += (R)norm_term(df); sp += (R)norm_term(old); }
+    }
+    __device__ __forceinline__ void flush() { dsd += (double)sd; dsp += (double)sp; sd = 0; sp = 0; }
+};
 
 struct TileWalk {
     int tiles_x, ntiles;
@@ -160,7 +174,7 @@ __global__ void __launch_bounds__(TX *TY) k_hs_iter(EngK<R> K, const vec2_t<R> *
     const vec2_t<R> *__restrict__ gradI = gradI_all + (size_t)pair * K.n;
     const R *__restrict__ It = It_all + (size_t)pair * K.n;
     const TileWalk T(nx, ny);
-    double sd = 0.0, sp = 0.0;
+    NormAcc<R> acc;
     bool divzero = false;
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
         const int i = (tile % T.tiles_x) * TILE + threadIdx.x;
@@ -195,13 +209,13 @@ __global__ void __launch_bounds__(TX *TY) k_hs_iter(EngK<R> K, const vec2_t<R> *
             else o = mk2<R>(q.x - f.x / den, q.y - f.y / den);
             if (i < nx && j < ny) {
                 un[i + j * nx] = o;
-                sd += norm_term(mk2<R>(o.x - old[p].x, o.y - old[p].y));
-                sp += norm_term(old[p]);
+                acc.add(o, old[p]);
             }
         }
+        acc.flush();
     }
     if (divzero) atomicOr(&c->flags, OF2D_FLAG_DIVZERO);
-    logger_epilogue<R>(K, c, pair, sd, sp);
+    logger_epilogue<R>(K, c, pair, acc.dsd, acc.dsp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -412,7 +426,7 @@ __global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int d
         __syncwarp();
         for (int r = lane; r < SH; r += 32) bulk_g2s(stages + st * stage_elems + r * SWp, in + tile_start(tile, r), (unsigned)(SWp * sizeof(vec2_t<R>)), &cbar[st]);
     };
-    double sd = 0.0, sp = 0.0;
+    NormAcc<R> acc;
     R mx = (R)0;
     unsigned uses[2] = {0u, 0u};
     if ((int)blockIdx.x < T.ntiles && threadIdx.y == 0 && tma_ok(blockIdx.x)) issue(blockIdx.x, 0);
@@ -494,20 +508,19 @@ __global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int d
                 const long idx = i + (long)j * nx;
                 out[idx] = o[q];
                 if (EPI == 1) {
-                    const vec2_t<R> old = est_cur[idx];
-                    sd += norm_term(mk2<R>(o[q].x - old.x, o[q].y - old.y));
-                    sp += norm_term(old);
+                    acc.add(o[q], est_cur[idx]);
                 } else if (EPI == 2) {
                     const R s = maxabs_term<R>(o[q]);
                     mx = mx < s ? s : mx;
                 }
             }
         }
+        if (EPI == 1) acc.flush();
         __syncthreads();   // everybody is done with stage st before warp 0 refills it (one iteration from now)
     }
     if (EPI == 0) return;
     if (EPI == 1) {
-        logger_epilogue<R>(K, c, pair, sd, sp);
+        logger_epilogue<R>(K, c, pair, acc.dsd, acc.dsp);
     } else {
         mx = block_extreme<R, true>(mx);
         const double vals[1] = {(double)mx};
@@ -713,7 +726,7 @@ __global__ void __launch_bounds__(TX *TY) k_fl_integrate(EngK<R> K, const vec2_t
         return v;
     };
     const TileWalk T(ny, nx);
-    double sd = 0.0, sp = 0.0;
+    NormAcc<R> acc;
     R mj = (R)INFINITY;
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
         const int j = (tile % T.tiles_x) * TILE + threadIdx.x;
@@ -726,8 +739,7 @@ __global__ void __launch_bounds__(TX *TY) k_fl_integrate(EngK<R> K, const vec2_t
             const size_t o = (size_t)i * P + j;
             const vec2_t<R> nv = unew_at(o);
             const vec2_t<R> prev = prev_other ? un[o] : u[o];   // after a regrid Logger's prev is the pre-reset estimate
-            sd += norm_term(mk2<R>(nv.x - prev.x, nv.y - prev.y));
-            sp += norm_term(prev);
+            acc.add(nv, prev);
             // Jacobian of the new field (one-sided at the edges, gradients.h:9-32)
             vec2_t<R> dx, dy;
             if (i == 0) { const vec2_t<R> a = unew_at(o + P); dx = mk2<R>(a.x - nv.x, a.y - nv.y); }
@@ -740,7 +752,9 @@ __global__ void __launch_bounds__(TX *TY) k_fl_integrate(EngK<R> K, const vec2_t
             mj = J < mj ? J : mj;
             un[o] = nv;
         }
+        acc.flush();
     }
+    double sd = acc.dsd, sp = acc.dsp;
     block_sum2(sd, sp);
     mj = block_extreme<R, false>(mj);
     const double vals[3] = {sd, sp, (double)mj};
