@@ -329,6 +329,25 @@ def run_ours(args):
     sessions.clear()
     pinned.clear()
 
+    # ---- fp64 mode (BASELINE.json configs[3] asks for fp64 and fp32): every method once, same inputs and caps
+    f64 = {}
+    if args.fp64 and rank == 0:
+        of.set_stream(torch.cuda.current_stream().cuda_stream, 64)
+        for m in METHODS:
+            R, T = make_inputs(m, size)
+            with of.Session((size, size), [NITER[m]], 0, REG[m], PARAMS[m], nrefine=1, verbose=0, bits=64) as s:
+                s.set_images(R, T)
+                ts = []
+                for rep in range(2):     # first pass warms up (engine creation, caches); second is timed
+                    s.reset()
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(); s.estimate(); e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                it = s.trace()["total_iterations"]
+            mp = n * it / (ts[-1] * 1e-3) / 1e6
+            f64[m] = {"iterations": it, "ms": ts[-1], "mpix_iter_s": mp, "gbs_algorithmic": mp * 1e6 * 2 * BYTES_PER_PX_ITER[m] / 1e9}
+
     # ---- batched slice registration (BASELINE.json configs[4]): BATCH pairs of 512^2 per GPU, no collective in the solve
     batch_res = {}
     if args.batch > 0:
@@ -431,6 +450,7 @@ def run_ours(args):
                          "how": "CUDA events around every engine launch of one extra (untimed) step, on the launching stream"} if dom else None,
             "kernels": kern,
             "methods": methods,
+            "methods_f64": {m: dict(v, frac_of_hbm_peak=v["gbs_algorithmic"] / peak) for m, v in f64.items()},
             "batch": batch_res,
             "cpu_baseline": cpu,
             "wall_s_timed_region": wall,
@@ -451,6 +471,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--batch", type=int, default=512, help="pairs of 512^2 per GPU in the batched leg (0 = skip); 8 GPUs x 512 = BASELINE's 4096")
+    ap.add_argument("--no-fp64", dest="fp64", action="store_false", help="skip the fp64-mode leg")
     ap.add_argument("--quick", action="store_true", help="timed region only (no e2e leg, kernel microbench or CPU baseline): for ncu launch lists")
     ap.add_argument("--methods", default=",".join(list(METHODS)), help="comma-separated subset (profiling only; the default is the benchmark)")
     args = ap.parse_args()

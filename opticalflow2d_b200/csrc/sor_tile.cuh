@@ -66,8 +66,8 @@ struct SorTileArgs {
     TraceDev tr;
 };
 
-template <class R, int RPT, bool FLUID>
-__global__ void __launch_bounds__(128) k_sor_tile(SorTileArgs<R> A) {
+template <class R, int RPT, bool FLUID, bool WARP>
+__global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) {
     using V = vec2_t<R>;
     static_assert(RPT == 4, "row blocks of 4: 32-byte aligned vector loads from the ring");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -209,25 +209,45 @@ __global__ void __launch_bounds__(128) k_sor_tile(SorTileArgs<R> A) {
             const R ar = comp[r] ? a : (R)0;
             xt[r] = mk2<R>(ar * xt[r - 1].x + d[r].x, ar * xt[r - 1].y + d[r].y);
         }
-        Pub *pb = pub + (k & 1) * NT;
-        {
-            Pub me;
-            me.top = xt[RPT - 1];
-            me.d0 = d[0];
-            pb[t] = me;
-        }
-        __syncthreads();
-        if (t == 0) {   // stage sC (and stage 0 after the first step) is free: stream the next column(s) in
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (k == 1 && SOR_NS < ncols) issue(SOR_NS);
-            if (k + SOR_NS < ncols) issue(k + SOR_NS);
-        }
-        // the new value of the row below the thread's block
-        V carry = mk2<R>((R)0, (R)0);
+        V carry = mk2<R>((R)0, (R)0);   // the new value of the row below the thread's block
+        V d0_above = mk2<R>((R)0, (R)0);
+        if (WARP) {   // one warp per tile: exchange through shuffles, no shared memory round trip and no block barrier
+            __syncwarp();
+            if (t == 0) {   // every lane has read stage sC: stream the next column(s) in
+                proxy_fence_async();
+                if (k == 1 && SOR_NS < ncols) issue(SOR_NS);
+                if (k + SOR_NS < ncols) issue(k + SOR_NS);
+            }
+            const V top = xt[RPT - 1];
 #pragma unroll
-        for (int q = 0; q < MQ; q++) {
-            const V tv = pb[tqi[q]].top;
-            carry.x += cq[q] * tv.x; carry.y += cq[q] * tv.y;
+            for (int q = 0; q < MQ; q++) {
+                if (q < A.M) {
+                    const R tx_ = __shfl_up_sync(0xffffffffu, top.x, q + 1), ty_ = __shfl_up_sync(0xffffffffu, top.y, q + 1);
+                    carry.x += cq[q] * tx_; carry.y += cq[q] * ty_;
+                }
+            }
+            d0_above.x = __shfl_down_sync(0xffffffffu, d[0].x, 1);
+            d0_above.y = __shfl_down_sync(0xffffffffu, d[0].y, 1);
+        } else {
+            Pub *pb = pub + (k & 1) * NT;
+            {
+                Pub me;
+                me.top = xt[RPT - 1];
+                me.d0 = d[0];
+                pb[t] = me;
+            }
+            __syncthreads();
+            if (t == 0) {   // stage sC (and stage 0 after the first step) is free: stream the next column(s) in
+                proxy_fence_async();
+                if (k == 1 && SOR_NS < ncols) issue(SOR_NS);
+                if (k + SOR_NS < ncols) issue(k + SOR_NS);
+            }
+#pragma unroll
+            for (int q = 0; q < MQ; q++) {
+                const V tv = pb[tqi[q]].top;
+                carry.x += cq[q] * tv.x; carry.y += cq[q] * tv.y;
+            }
+            if (t + 1 < NT) d0_above = pb[t + 1].d0;
         }
         // the reference's expression, literally, with S = the (estimated) new value of the cell below
         V xn[RPT];
@@ -242,12 +262,8 @@ __global__ void __launch_bounds__(128) k_sor_tile(SorTileArgs<R> A) {
             }
         }
         V ntop;
-        if (t + 1 < NT) {
-            const V d0 = pb[t + 1].d0;
-            ntop = above_comp ? mk2<R>(a * xn[RPT - 1].x + d0.x, a * xn[RPT - 1].y + d0.y) : d0;
-        } else {
-            ntop = oldC[RPT + 1];
-        }
+        if (t + 1 < NT) ntop = above_comp ? mk2<R>(a * xn[RPT - 1].x + d0_above.x, a * xn[RPT - 1].y + d0_above.y) : d0_above;
+        else ntop = oldC[RPT + 1];
         if (i >= is) {
 #pragma unroll
             for (int r = 0; r < RPT; r++) {
@@ -347,13 +363,17 @@ static int sor_tile_launch(of2d_ctx *ctx, const SorPlan &S, PairCtl *ctl, int *n
     const size_t stage = (size_t)(A.LR + 4) * sizeof(vec2_t<R>) + (size_t)A.LR * (sizeof(vec2_t<R>) * (fluid ? 2 : 1) + sizeof(R));
     const size_t smem = SOR_NS * stage + 2 * (size_t)S.NT * 2 * sizeof(vec2_t<R>);
     const dim3 grid(S.nbands, S.nstrips, S.batch);
-    if (fluid) {
-        { int st = of2d_ensure_dynamic_smem((const void *)k_sor_tile<R, 4, true>, smem); if (st) return st; }
-        { ProfScope _ps(ctx, "sor_tile_fluid"); k_sor_tile<R, 4, true><<<grid, S.NT, smem, ctx->stream>>>(A); }
-    } else {
-        { int st = of2d_ensure_dynamic_smem((const void *)k_sor_tile<R, 4, false>, smem); if (st) return st; }
-        { ProfScope _ps(ctx, "sor_tile_elastic"); k_sor_tile<R, 4, false><<<grid, S.NT, smem, ctx->stream>>>(A); }
-    }
+    auto go = [&](auto kernel, const char *name) -> int {
+        int st = of2d_ensure_dynamic_smem((const void *)kernel, smem);
+        if (st) return st;
+        ProfScope _ps(ctx, name);
+        kernel<<<grid, S.NT, smem, ctx->stream>>>(A);
+        return OF2D_SUCCESS;
+    };
+    int st;
+    if (fluid) st = S.NT == 32 ? go(k_sor_tile<R, 4, true, true>, "sor_tile_fluid") : go(k_sor_tile<R, 4, true, false>, "sor_tile_fluid");
+    else st = S.NT == 32 ? go(k_sor_tile<R, 4, false, true>, "sor_tile_elastic") : go(k_sor_tile<R, 4, false, false>, "sor_tile_elastic");
+    if (st) return st;
     OF2D_LAUNCH_CHECK(ctx);
     return OF2D_SUCCESS;
 }

@@ -1,0 +1,56 @@
+"""Parity at BASELINE.json's full size (-m gpu): the engine at 2048 x 2048, fp32, against golden vectors sampled from
+the COMPILED REFERENCE at the same size (tests/golden/full2048_*.npz, made by tests/golden/make_golden_full.py), plus
+size-independent properties: identical control flow, fast mode == strict mode where the arithmetic is exact, and the
+registration actually reduces the SSD."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import bench
+import opticalflow2d_b200 as of
+from gpu_common import maxdiff
+
+pytestmark = pytest.mark.gpu
+FULL = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "full2048_*.npz")))
+
+
+def run(method, size, niter, strict=False):
+    R, T = bench.make_inputs(method, size)
+    of.set_strict(strict, 32)
+    with of.Session((size, size), [niter], 0, bench.REG[method], bench.PARAMS[method], nrefine=1, verbose=0, bits=32) as s:
+        s.set_images(R, T)
+        s.estimate()
+        return R, T, s.motion(), s.trace()["levels"][0], s.warp(T)
+
+
+@pytest.mark.parametrize("path", FULL, ids=[os.path.basename(p)[9:-4] for p in FULL])
+def test_full_size_matches_compiled_reference(path):
+    g = np.load(path)
+    method, size, niter = str(g["method"]), int(g["size"]), int(g["niter"])
+    R, T, mo, tr, warped = run(method, size, niter)
+    assert tr["iterations"] == len(g["err"])
+    assert np.array_equal(np.asarray(tr["regrid_iter"], dtype=int), g["regrid_iter"].astype(int))
+    # the reference sums 4 M norm terms into one float accumulator (src/Motion.cpp:42-49): its own error series
+    # carries ~1e-3 relative rounding noise at this size
+    rel = np.abs(np.asarray(tr["err"]) - g["err"]) / np.maximum(np.abs(g["err"]), 1e-12)
+    assert rel.max() <= 2e-2, (rel.max(), int(rel.argmax()))
+    st, off = int(g["stride"]), int(g["offset"])
+    assert maxdiff(mo[off::st, off::st], g["sample"]) <= 1e-3            # north-star fp32 bar, px
+    assert np.allclose(mo.mean(axis=(0, 1)), g["mean"], rtol=0, atol=1e-5)
+    assert np.allclose((mo.astype(np.float64) ** 2).mean(axis=(0, 1)), g["meansq"], rtol=1e-4, atol=1e-9)
+    ssd0, ssd1 = float(((T - R) ** 2).sum()), float(((warped - R) ** 2).sum())
+    assert ssd1 < ssd0                                                    # it registers
+
+
+@pytest.mark.parametrize("method", ["diffusion", "thirion", "diffeomorphic"])
+def test_full_size_engine_is_bit_identical_to_strict(method):
+    """Exact-arithmetic methods: interior of the field must agree bit for bit; on the outermost rows / columns the
+    reference's out-of-bounds test (src/Motion.cpp:141-144) is a discontinuity that both modes evaluate on inputs
+    that are themselves identical, so they agree there too."""
+    size, niter = 1024, 12
+    _, _, mf, tf, _ = run(method, size, niter, strict=False)
+    _, _, ms, ts, _ = run(method, size, niter, strict=True)
+    assert tf["iterations"] == ts["iterations"]
+    assert maxdiff(mf, ms) == 0.0
