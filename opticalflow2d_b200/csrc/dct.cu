@@ -54,6 +54,8 @@ struct LineTables {
     const void *tw;    // e^{-2 pi i k / n}, k < n/2       (cplx<S>)
     const void *q;     // e^{-i pi k / (2n)}, k < n        (cplx<S>)
     const double *costab;  // cos(pi m / (2n)), m < 4n (direct path only)
+    const void *tw16a;     // [4][n/16]:  e^{-2 pi i k 2^i / n}       (register path, dct_reg.cuh; 512 <= n <= 4096)
+    const void *tw16b;     // [4][n/256]: e^{-2 pi i k 2^i / (n/16)}
     int n, log2n, pow2;
 };
 
@@ -334,6 +336,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_dct_lines(int nlines, int n, si
 }  // namespace
 
 #include "dct_fast.cuh"
+#include "dct_reg.cuh"
 
 namespace {
 
@@ -350,16 +353,22 @@ int build_tables(int n, LineTables *T, void **d_blob) {
         int l = 0;
         while ((1 << l) < n) l++;
         T->log2n = l;
-        const size_t ntw = n / 2, nq = n;
-        cplx_t<S> *h = (cplx_t<S> *)malloc(sizeof(cplx_t<S>) * (ntw + nq));
+        const bool reg = l >= 9 && l <= 12;
+        const size_t ntw = n / 2, nq = n, s1 = reg ? n / 16 : 0, s2 = reg ? n / 256 : 0, tot = ntw + nq + 4 * s1 + 4 * s2;
+        cplx_t<S> *h = (cplx_t<S> *)malloc(sizeof(cplx_t<S>) * tot);
         for (size_t k = 0; k < ntw; k++) { h[k].x = (S)cos(-2.0 * kPi * k / n); h[k].y = (S)sin(-2.0 * kPi * k / n); }
         for (size_t k = 0; k < nq; k++) { h[ntw + k].x = (S)cos(-kPi * k / (2.0 * n)); h[ntw + k].y = (S)sin(-kPi * k / (2.0 * n)); }
-        cudaError_t e = cudaMalloc(d_blob, sizeof(cplx_t<S>) * (ntw + nq));
-        if (e == cudaSuccess) e = cudaMemcpy(*d_blob, h, sizeof(cplx_t<S>) * (ntw + nq), cudaMemcpyHostToDevice);
+        for (int i = 0; i < 4; i++) {
+            for (size_t k = 0; k < s1; k++) { const double a = -2.0 * kPi * (double)(k << i) / n; h[ntw + nq + i * s1 + k].x = (S)cos(a); h[ntw + nq + i * s1 + k].y = (S)sin(a); }
+            for (size_t k = 0; k < s2; k++) { const double a = -2.0 * kPi * (double)(k << i) / (n / 16); h[ntw + nq + 4 * s1 + i * s2 + k].x = (S)cos(a); h[ntw + nq + 4 * s1 + i * s2 + k].y = (S)sin(a); }
+        }
+        cudaError_t e = cudaMalloc(d_blob, sizeof(cplx_t<S>) * tot);
+        if (e == cudaSuccess) e = cudaMemcpy(*d_blob, h, sizeof(cplx_t<S>) * tot, cudaMemcpyHostToDevice);
         free(h);
         if (e != cudaSuccess) { of2d_set_error("dct tables: %s", cudaGetErrorString(e)); return OF2D_ERR_CUDA; }
         T->tw = *d_blob;
         T->q = (const cplx_t<S> *)*d_blob + ntw;
+        if (reg) { T->tw16a = (const cplx_t<S> *)*d_blob + ntw + nq; T->tw16b = (const cplx_t<S> *)*d_blob + ntw + nq + 4 * s1; }
     } else {
         double *h = (double *)malloc(sizeof(double) * 4 * (size_t)n);
         for (int m = 0; m < 4 * n; m++) h[m] = cos(kPi * m / (2.0 * n));
@@ -391,6 +400,64 @@ struct of2d_curvature_plan {
 
 namespace {
 
+// dct_reg.cuh: register-blocked radix-16 path (both line lengths in 512 .. 4096)
+template <class R, int LX>
+int launch_reg_rows(of2d_curvature_plan *P, bool fwd, const R *u, R *unew, const R *gradI, const R *It, const CurvHook &H, int batch) {
+    of2d_ctx *ctx = P->ctx;
+    constexpr int LPC = 2, NT = LPC * rg::Geo<LX>::TPL;
+    const size_t smem = sizeof(double2) * (size_t)P->nx * LPC;
+    const rg::Tw16 T{(const double2 *)P->Tx.tw16a, (const double2 *)P->Tx.tw16b};
+    const R fourN = (R)4.0f * (R)(unsigned)(P->nx * P->ny);
+    if (fwd) {
+        { int st = of2d_ensure_dynamic_smem((const void *)rg::k_rg_rows_fwd<R, LX, LPC>, smem); if (st) return st; }
+        ProfScope _ps(ctx, "curv_rows_fwd");
+        rg::k_rg_rows_fwd<R, LX, LPC><<<dim3(P->ny / LPC, batch), NT, smem, ctx->stream>>>(P->ny, (const vec2_t<R> *)u, (const vec2_t<R> *)unew, (const vec2_t<R> *)gradI, It,
+                                                                                       (R)P->tau, (double2 *)P->d_spec, (const double2 *)P->Tx.q, T, H);
+    } else {
+        { int st = of2d_ensure_dynamic_smem((const void *)rg::k_rg_rows_inv<R, LX, LPC>, smem); if (st) return st; }
+        ProfScope _ps(ctx, "curv_rows_inv");
+        rg::k_rg_rows_inv<R, LX, LPC><<<dim3(P->ny / LPC, batch), NT, smem, ctx->stream>>>(P->ny, (const double2 *)P->d_spec, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN,
+                                                                                       (const double2 *)P->Tx.q, T, H);
+    }
+    OF2D_LAUNCH_CHECK(ctx);
+    return OF2D_SUCCESS;
+}
+template <int LY>
+int launch_reg_cols(of2d_curvature_plan *P, const CurvHook &H, int batch) {
+    of2d_ctx *ctx = P->ctx;
+    constexpr int TPL = rg::Geo<LY>::TPL, LPC = TPL >= 128 ? 1 : 128 / TPL, NT = LPC * TPL;
+    const size_t smem = sizeof(double2) * (size_t)P->ny * LPC;
+    const rg::Tw16 T{(const double2 *)P->Ty.tw16a, (const double2 *)P->Ty.tw16b};
+    { int st = of2d_ensure_dynamic_smem((const void *)rg::k_rg_cols<LY, LPC>, smem); if (st) return st; }
+    ProfScope _ps(ctx, "curv_cols");
+    rg::k_rg_cols<LY, LPC><<<dim3(P->nx / LPC, batch), NT, smem, ctx->stream>>>(P->nx, (double2 *)P->d_spec, P->d_cosx, P->d_cosy, P->tau_alpha, (const double2 *)P->Ty.q, T, H);
+    OF2D_LAUNCH_CHECK(ctx);
+    return OF2D_SUCCESS;
+}
+template <class R>
+int curvature_step_reg(of2d_curvature_plan *P, const R *u, R *unew, const R *gradI, const R *It, const CurvHook &H) {
+    const int batch = H.enabled ? P->batch : 1;
+    int st = OF2D_SUCCESS;
+    for (int phase = 0; phase < 3 && st == OF2D_SUCCESS; phase++) {
+        if (phase == 1) {
+            switch (P->Ty.log2n) {
+                case 9: st = launch_reg_cols<9>(P, H, batch); break;
+                case 10: st = launch_reg_cols<10>(P, H, batch); break;
+                case 11: st = launch_reg_cols<11>(P, H, batch); break;
+                default: st = launch_reg_cols<12>(P, H, batch); break;
+            }
+        } else {
+            switch (P->Tx.log2n) {
+                case 9: st = launch_reg_rows<R, 9>(P, phase == 0, u, unew, gradI, It, H, batch); break;
+                case 10: st = launch_reg_rows<R, 10>(P, phase == 0, u, unew, gradI, It, H, batch); break;
+                case 11: st = launch_reg_rows<R, 11>(P, phase == 0, u, unew, gradI, It, H, batch); break;
+                default: st = launch_reg_rows<R, 12>(P, phase == 0, u, unew, gradI, It, H, batch); break;
+            }
+        }
+    }
+    return st;
+}
+
 template <class R, class S>
 int curvature_step_impl(of2d_curvature_plan *P, const R *u, R *unew, const R *gradI, const R *It, const CurvHook &H) {
     of2d_ctx *ctx = P->ctx;
@@ -398,6 +465,7 @@ int curvature_step_impl(of2d_curvature_plan *P, const R *u, R *unew, const R *gr
     const int nx = P->nx, ny = P->ny;
     cplx_t<S> *spec = (cplx_t<S> *)P->d_spec;
     const R fourN = (R)4.0f * (R)(unsigned)(nx * ny);
+    if (P->Tx.tw16a && P->Ty.tw16a && !getenv("OF2D_NO_REG_FFT")) return curvature_step_reg<R>(P, u, unew, gradI, It, H);
     constexpr int LPC = 2;
     const bool fast = P->Tx.pow2 && P->Ty.pow2 && P->Tx.log2n >= 6 && P->Ty.log2n >= 6 && sizeof(double2) * (size_t)nx * LPC <= kMaxSmem &&
                       sizeof(double2) * (size_t)ny <= kMaxSmem;

@@ -1,0 +1,380 @@
+// dct_reg.cuh -- register-blocked DCT path of the curvature solver for line lengths 512 .. 4096 (included by dct.cu).
+//
+// Same transform definitions as dct.cu (Makhoul's N-point DCT-II / DCT-III through ONE N-point complex FFT whose real /
+// imaginary parts carry the x / y components of the motion), restructured so that shared memory is touched as little as
+// the dependency structure allows:
+//   * every thread keeps 16 points in registers and a line is transformed in THREE super-passes of radix 16, 16 and
+//     N/256 (2 shared-memory exchanges per FFT instead of 5 passes); threads per line = N/16;
+//   * forward = decimation in frequency (natural in, digit-reversed out), inverse = decimation in time (digit-reversed
+//     in, natural out), so no permutation pass exists: the pair stages (DCT-II post-twiddle, eigenvalues, DCT-III
+//     pre-twiddle), which have to visit (k, N-k) anyway, address the digit-reversed slot of k directly;
+//   * twiddles of a super-pass: four coalesced table loads (w^k, w^2k, w^4k, w^8k), the other eleven composed in registers
+//     (the radix-4 passes of dct_fast.cuh spent more L1 wavefronts on scattered twiddle loads than on the data);
+//   * in the first / last super-pass a warp owns the offsets k in [16w, 16w+16) and their mirror images S1-1-k, so that
+//     v[m] and v[N-1-m] -- the two halves of a pixel pair (2m, 2m+1) in Makhoul's ordering -- live in lanes l and l^16:
+//     one shuffle turns register contents into complete pixel pairs and global loads / stores are full 16-byte accesses;
+//   * FMA is allowed inside the FFT (the reference's fftw has no defined operation order to reproduce); the
+//     reference's own expressions (force, rhs, 1/(4N), eigenvalue) keep their order and stay unfused.
+// Shared-memory indices go through the XOR swizzle of dct_fast.cuh (conflict-free for every power-of-two stride).
+#pragma once
+
+namespace {
+namespace rg {
+
+__device__ __forceinline__ double2 cmulf(double2 a, double2 b) { return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x)); }
+__device__ __forceinline__ double2 cmulcf(double2 a, double2 b) { return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -(a.x * b.y))); }   // a conj(b)
+__device__ __forceinline__ double2 add2(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 sub2(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+template <int SIGN> __device__ __forceinline__ double2 mul_i(double2 a) { return SIGN > 0 ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x); }   // a (SIGN i)
+
+// a e^{SIGN 2 pi i n / 16}
+template <int SIGN, int n> __device__ __forceinline__ double2 mul_w16(double2 a) {
+    constexpr int m = n & 15;
+    if constexpr (m == 0) return a;
+    else if constexpr (m == 4) return mul_i<SIGN>(a);
+    else if constexpr (m == 8) return make_double2(-a.x, -a.y);
+    else if constexpr (m == 12) return mul_i<-SIGN>(a);
+    else {
+        constexpr double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, r = 0.70710678118654752440;
+        constexpr double C[16] = {1, c1, r, s1, 0, -s1, -r, -c1, -1, -c1, -r, -s1, 0, s1, r, c1};
+        constexpr double S[16] = {0, s1, r, c1, 1, c1, r, s1, 0, -s1, -r, -c1, -1, -c1, -r, -s1};
+        constexpr double c = C[m], s = SIGN * S[m];
+        return make_double2(fma(a.x, c, -(a.y * s)), fma(a.x, s, a.y * c));
+    }
+}
+
+template <int SIGN> __device__ __forceinline__ void radix4(double2 &a0, double2 &a1, double2 &a2, double2 &a3) {
+    const double2 p02 = add2(a0, a2), m02 = sub2(a0, a2), p13 = add2(a1, a3), d = mul_i<SIGN>(sub2(a1, a3));
+    a0 = add2(p02, p13); a1 = add2(m02, d); a2 = sub2(p02, p13); a3 = sub2(m02, d);
+}
+
+// slot of a[] that holds output index q after dft<R>() (and its inverse map; both are involutions for R = 16)
+__host__ __device__ constexpr int slot_q(int R, int s) { return R == 16 ? (s >> 2) + 4 * (s & 3) : R == 8 ? (s >> 1) + 4 * (s & 1) : s; }
+
+// unnormalised R-point DFT with kernel e^{SIGN 2 pi i j q / R} of a[OFF .. OFF+R): output q is left in slot OFF + s, q = slot_q(R, s)
+template <int R, int SIGN, int OFF> __device__ __forceinline__ void dft(double2 (&a)[16]) {
+    if constexpr (R == 2) {
+        const double2 p = add2(a[OFF], a[OFF + 1]), m = sub2(a[OFF], a[OFF + 1]);
+        a[OFF] = p; a[OFF + 1] = m;
+    } else if constexpr (R == 4) {
+        radix4<SIGN>(a[OFF], a[OFF + 1], a[OFF + 2], a[OFF + 3]);
+    } else if constexpr (R == 8) {   // j = j0 + 2 j1, q = q1 + 4 q0
+        radix4<SIGN>(a[OFF + 0], a[OFF + 2], a[OFF + 4], a[OFF + 6]);
+        radix4<SIGN>(a[OFF + 1], a[OFF + 3], a[OFF + 5], a[OFF + 7]);
+        a[OFF + 3] = mul_w16<SIGN, 2>(a[OFF + 3]); a[OFF + 5] = mul_w16<SIGN, 4>(a[OFF + 5]); a[OFF + 7] = mul_w16<SIGN, 6>(a[OFF + 7]);
+#pragma unroll
+        for (int q1 = 0; q1 < 4; q1++) { const double2 p = add2(a[OFF + 2 * q1], a[OFF + 2 * q1 + 1]), m = sub2(a[OFF + 2 * q1], a[OFF + 2 * q1 + 1]); a[OFF + 2 * q1] = p; a[OFF + 2 * q1 + 1] = m; }
+    } else {                         // j = j0 + 4 j1, q = q1 + 4 q0
+        radix4<SIGN>(a[0], a[4], a[8], a[12]);
+        radix4<SIGN>(a[1], a[5], a[9], a[13]);
+        radix4<SIGN>(a[2], a[6], a[10], a[14]);
+        radix4<SIGN>(a[3], a[7], a[11], a[15]);
+        a[5] = mul_w16<SIGN, 1>(a[5]); a[9] = mul_w16<SIGN, 2>(a[9]); a[13] = mul_w16<SIGN, 3>(a[13]);
+        a[6] = mul_w16<SIGN, 2>(a[6]); a[10] = mul_w16<SIGN, 4>(a[10]); a[14] = mul_w16<SIGN, 6>(a[14]);
+        a[7] = mul_w16<SIGN, 3>(a[7]); a[11] = mul_w16<SIGN, 6>(a[11]); a[15] = mul_w16<SIGN, 9>(a[15]);
+        radix4<SIGN>(a[0], a[1], a[2], a[3]);
+        radix4<SIGN>(a[4], a[5], a[6], a[7]);
+        radix4<SIGN>(a[8], a[9], a[10], a[11]);
+        radix4<SIGN>(a[12], a[13], a[14], a[15]);
+    }
+}
+
+// a[idx(q)] *= w^q (CONJ: conj(w)^q), q = 1..15, from w, w^2, w^4, w^8; SLOT: a[] is in dft<16> output order
+template <bool SLOT, bool CONJ> __device__ __forceinline__ void twiddle16(double2 (&a)[16], double2 w1, double2 w2, double2 w4, double2 w8) {
+#define RG_AT(q) a[SLOT ? slot_q(16, (q)) : (q)]
+#define RG_MUL(q, w) RG_AT(q) = CONJ ? cmulcf(RG_AT(q), w) : cmulf(RG_AT(q), w)
+    RG_MUL(1, w1); RG_MUL(2, w2); RG_MUL(4, w4); RG_MUL(8, w8);
+    const double2 w3 = cmulf(w1, w2), w5 = cmulf(w1, w4), w6 = cmulf(w2, w4), w12 = cmulf(w4, w8);
+    RG_MUL(3, w3); RG_MUL(5, w5); RG_MUL(6, w6); RG_MUL(12, w12);
+    const double2 w7 = cmulf(w3, w4);
+    RG_MUL(7, w7);
+    { const double2 w9 = cmulf(w1, w8); RG_MUL(9, w9); }
+    { const double2 w10 = cmulf(w2, w8); RG_MUL(10, w10); }
+    { const double2 w11 = cmulf(w3, w8); RG_MUL(11, w11); }
+    { const double2 w13 = cmulf(w5, w8); RG_MUL(13, w13); }
+    { const double2 w14 = cmulf(w6, w8); RG_MUL(14, w14); }
+    { const double2 w15 = cmulf(w7, w8); RG_MUL(15, w15); }
+#undef RG_MUL
+#undef RG_AT
+}
+
+template <int L> struct Geo {
+    static constexpr int N = 1 << L, S1 = N >> 4, S2 = N >> 8, M3 = N >> 8, TPL = N >> 4;
+    static_assert(L >= 9 && L <= 12, "register path: 512 <= N <= 4096");
+    // digit-reversed slot of frequency k
+    __device__ static __forceinline__ int pos(int k) { return (k & 15) * S1 + ((k >> 4) & 15) * S2 + (k >> 8); }
+    // offset handled by thread u of a line in the first / last super-pass: lanes l and l^16 hold k and S1-1-k
+    __device__ static __forceinline__ int k1(int u) {
+        const int lane = u & 31, w = u >> 5;
+        return lane < 16 ? 16 * w + lane : S1 - 1 - 16 * w - (lane - 16);
+    }
+};
+
+struct Tw16 { const double2 *a, *b; };   // [4][S1] for super-pass 1 (w_N), [4][S2] for super-pass 2 (w_{N/16}); forward sign
+
+// ---- forward (DIF): registers -> ... -> shared memory, digit-reversed --------------------------------------------
+// in: a[j] = v[k + S1 j] (natural order), k = Geo::k1(u).  out: X_k at xl[swz(pos(k))], after the trailing barrier.
+template <int L> __device__ __forceinline__ void fft_fwd(double2 (&a)[16], double2 *xl, int u, Tw16 T) {
+    using G = Geo<L>;
+    {
+        const int k = G::k1(u);
+        dft<16, -1, 0>(a);
+        twiddle16<true, false>(a, T.a[k], T.a[G::S1 + k], T.a[2 * G::S1 + k], T.a[3 * G::S1 + k]);
+#pragma unroll
+        for (int s = 0; s < 16; s++) xl[swz(k + G::S1 * slot_q(16, s))] = a[s];
+    }
+    __syncthreads();
+    {
+        const int b = u / G::S2, k = u % G::S2, base = b * G::S1 + k;
+#pragma unroll
+        for (int j = 0; j < 16; j++) a[j] = xl[swz(base + G::S2 * j)];
+        dft<16, -1, 0>(a);
+        twiddle16<true, false>(a, T.b[k], T.b[G::S2 + k], T.b[2 * G::S2 + k], T.b[3 * G::S2 + k]);
+#pragma unroll
+        for (int s = 0; s < 16; s++) xl[swz(base + G::S2 * slot_q(16, s))] = a[s];
+    }
+    __syncthreads();
+    {
+#pragma unroll
+        for (int j = 0; j < 16; j++) a[j] = xl[swz(16 * u + j)];
+        if constexpr (G::M3 == 16) dft<16, -1, 0>(a);
+        if constexpr (G::M3 == 8) { dft<8, -1, 0>(a); dft<8, -1, 8>(a); }
+        if constexpr (G::M3 == 4) { dft<4, -1, 0>(a); dft<4, -1, 4>(a); dft<4, -1, 8>(a); dft<4, -1, 12>(a); }
+        if constexpr (G::M3 == 2) { dft<2, -1, 0>(a); dft<2, -1, 2>(a); dft<2, -1, 4>(a); dft<2, -1, 6>(a); dft<2, -1, 8>(a); dft<2, -1, 10>(a); dft<2, -1, 12>(a); dft<2, -1, 14>(a); }
+#pragma unroll
+        for (int s = 0; s < 16; s++) xl[swz(16 * u + (s & ~(G::M3 - 1)) + slot_q(G::M3, s & (G::M3 - 1)))] = a[s];
+    }
+    __syncthreads();
+}
+
+// ---- inverse (DIT, unnormalised): shared memory, digit-reversed -> ... -> registers -------------------------------
+// in: h_k at xl[swz(pos(k))] (caller has synchronised).  out: a[s] = t[k + S1 q], q = slot_q(16, s), k = Geo::k1(u).
+template <int L> __device__ __forceinline__ void fft_inv(double2 (&a)[16], double2 *xl, int u, Tw16 T) {
+    using G = Geo<L>;
+    {
+#pragma unroll
+        for (int j = 0; j < 16; j++) a[j] = xl[swz(16 * u + j)];
+        if constexpr (G::M3 == 16) dft<16, +1, 0>(a);
+        if constexpr (G::M3 == 8) { dft<8, +1, 0>(a); dft<8, +1, 8>(a); }
+        if constexpr (G::M3 == 4) { dft<4, +1, 0>(a); dft<4, +1, 4>(a); dft<4, +1, 8>(a); dft<4, +1, 12>(a); }
+        if constexpr (G::M3 == 2) { dft<2, +1, 0>(a); dft<2, +1, 2>(a); dft<2, +1, 4>(a); dft<2, +1, 6>(a); dft<2, +1, 8>(a); dft<2, +1, 10>(a); dft<2, +1, 12>(a); dft<2, +1, 14>(a); }
+#pragma unroll
+        for (int s = 0; s < 16; s++) xl[swz(16 * u + (s & ~(G::M3 - 1)) + slot_q(G::M3, s & (G::M3 - 1)))] = a[s];
+    }
+    __syncthreads();
+    {
+        const int b = u / G::S2, k = u % G::S2, base = b * G::S1 + k;
+#pragma unroll
+        for (int j = 0; j < 16; j++) a[j] = xl[swz(base + G::S2 * j)];
+        twiddle16<false, true>(a, T.b[k], T.b[G::S2 + k], T.b[2 * G::S2 + k], T.b[3 * G::S2 + k]);
+        dft<16, +1, 0>(a);
+#pragma unroll
+        for (int s = 0; s < 16; s++) xl[swz(base + G::S2 * slot_q(16, s))] = a[s];
+    }
+    __syncthreads();
+    {
+        const int k = G::k1(u);
+#pragma unroll
+        for (int j = 0; j < 16; j++) a[j] = xl[swz(k + G::S1 * j)];
+        twiddle16<false, true>(a, T.a[k], T.a[G::S1 + k], T.a[2 * G::S1 + k], T.a[3 * G::S1 + k]);
+        dft<16, +1, 0>(a);
+    }
+}
+
+template <class R> __device__ __forceinline__ void load_px_pair(const vec2_t<R> *p, vec2_t<R> &a, vec2_t<R> &b) { a = p[0]; b = p[1]; }
+template <> __device__ __forceinline__ void load_px_pair<float>(const float2 *p, float2 &a, float2 &b) {
+    const float4 v = *reinterpret_cast<const float4 *>(p);
+    a = make_float2(v.x, v.y); b = make_float2(v.z, v.w);
+}
+template <class R> __device__ __forceinline__ void store_px_pair(vec2_t<R> *p, vec2_t<R> a, vec2_t<R> b) { p[0] = a; p[1] = b; }
+template <> __device__ __forceinline__ void store_px_pair<float>(float2 *p, float2 a, float2 b) { *reinterpret_cast<float4 *>(p) = make_float4(a.x, a.y, b.x, b.y); }
+template <class R> __device__ __forceinline__ void load_s_pair(const R *p, R &a, R &b) { a = p[0]; b = p[1]; }
+template <> __device__ __forceinline__ void load_s_pair<float>(const float *p, float &a, float &b) { const float2 v = *reinterpret_cast<const float2 *>(p); a = v.x; b = v.y; }
+
+// ---- P1: LPC rows per CTA.  rhs = u - tau f, DCT-II along x, spectrum written transposed -----------------------------
+template <class R, int L, int LPC>
+__global__ void __launch_bounds__(LPC * Geo<L>::TPL) k_rg_rows_fwd(int ny, const vec2_t<R> *est0, const vec2_t<R> *est1, const vec2_t<R> *__restrict__ gradI,
+                                                                   const R *__restrict__ It, R tau, double2 *__restrict__ specT, const double2 *__restrict__ q, Tw16 T,
+                                                                   CurvHook H) {
+    using G = Geo<L>;
+    constexpr int N = G::N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *x = reinterpret_cast<double2 *>(smem_raw);   // [LPC][N]
+    const size_t pair_off = (size_t)blockIdx.y * N * ny;
+    const vec2_t<R> *__restrict__ uin = est0;
+    if (H.enabled) {
+        const PairCtl *c = H.ctl + blockIdx.y;
+        if (!__ldcg(&c->active)) return;
+        uin = __ldcg(&c->sel) ? est1 : est0;
+    }
+    uin += pair_off; gradI += pair_off; It += pair_off; specT += pair_off;
+    const int tid = threadIdx.x, l = tid / G::TPL, u = tid % G::TPL, j0 = blockIdx.x * LPC;
+    double2 *xl = x + l * N;
+    double2 a[16];
+    {   // pixel pairs (2m, 2m+1), m = k + S1 j (j < 8): the even pixel is v[m] (mine), the odd one v[N-1-m] (lane ^ 16, element 15-j)
+        const int k = G::k1(u);
+        const size_t row = (size_t)(j0 + l) * N;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const size_t g = row + 2 * (k + G::S1 * j);
+            vec2_t<R> u0, u1, g0, g1; R t0, t1;
+            load_px_pair<R>(uin + g, u0, u1); load_px_pair<R>(gradI + g, g0, g1); load_s_pair<R>(It + g, t0, t1);
+            const vec2_t<R> f0 = lssd_force<R>(g0, t0, u0), f1 = lssd_force<R>(g1, t1, u1);                  // OpticalFlow.cpp:33
+            const R ex = u0.x - tau * f0.x, ey = u0.y - tau * f0.y, ox = u1.x - tau * f1.x, oy = u1.y - tau * f1.y;   // OpticalFlowCurvature.cpp:90-91
+            a[j] = make_double2((double)ex, (double)ey);
+            a[15 - j] = make_double2((double)__shfl_xor_sync(0xffffffffu, ox, 16), (double)__shfl_xor_sync(0xffffffffu, oy, 16));
+        }
+    }
+    fft_fwd<L>(a, xl, u, T);
+    constexpr int hp = (N >> 1) + 1;
+    for (int e = tid; e < LPC * hp; e += LPC * G::TPL) {
+        const int ll = e % LPC, k = e / LPC, nk = (N - k) & (N - 1);
+        const double2 *base = x + ll * N;
+        double2 ok, on;
+        dct2_post_pair(base[swz(G::pos(k))], base[swz(G::pos(nk))], q[k], q[nk], nk == k, ok, on);
+        specT[(size_t)k * ny + j0 + ll] = ok;
+        if (nk != k) specT[(size_t)nk * ny + j0 + ll] = on;
+    }
+}
+
+// ---- P2: LPC spectrum columns (contiguous in spec_T) per CTA: DCT-II along y, eigenvalues, DCT-III along y ------------
+template <int L, int LPC>
+__global__ void __launch_bounds__(LPC * Geo<L>::TPL) k_rg_cols(int nx, double2 *__restrict__ specT, const double *__restrict__ cosx, const double *__restrict__ cosy,
+                                                               double tau_alpha, const double2 *__restrict__ q, Tw16 T, CurvHook H) {
+    using G = Geo<L>;
+    constexpr int N = G::N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *x = reinterpret_cast<double2 *>(smem_raw);   // [LPC][N]
+    if (H.enabled && !__ldcg(&H.ctl[blockIdx.y].active)) return;
+    const int tid = threadIdx.x, l = tid / G::TPL, u = tid % G::TPL, p = blockIdx.x * LPC + l;
+    double2 *xl = x + l * N;
+    double2 *__restrict__ line = specT + (size_t)blockIdx.y * nx * N + (size_t)p * N;
+    const int k1 = G::k1(u);
+    double2 a[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int m = k1 + G::S1 * j;
+        a[j] = line[j < 8 ? 2 * m : 2 * (N - 1 - m) + 1];
+    }
+    fft_fwd<L>(a, xl, u, T);
+    const double cxp = cosx[p];
+#pragma unroll 2
+    for (int c = 0; c <= 8; c++) {
+        const int k = c < 8 ? u + G::TPL * c : N >> 1;
+        if (c == 8 && u != 0) break;
+        const int nk = (N - k) & (N - 1);
+        const bool self = nk == k;
+        const int sk = swz(G::pos(k)), sn = swz(G::pos(nk));
+        double2 ak, an;
+        dct2_post_pair(xl[sk], xl[sn], q[k], q[nk], self, ak, an);
+        {   // OpticalFlowCurvature.cpp:24, :135-136
+            const double lap = -4 + cxp + cosy[k];
+            const double eig = 1.0f / (1.0f + tau_alpha * (lap * lap));
+            ak.x *= eig; ak.y *= eig;
+        }
+        if (!self) {
+            const double lap = -4 + cxp + cosy[nk];
+            const double eig = 1.0f / (1.0f + tau_alpha * (lap * lap));
+            an.x *= eig; an.y *= eig;
+        }
+        if (k == 0) {
+            xl[sk] = ak;                          // h_0 = X_0
+        } else if (self) {
+            double2 oj, dummy;
+            dct3_pre_pair(ak, ak, q[k], q[k], true, oj, dummy);
+            xl[sk] = oj;
+        } else {
+            double2 oj, on;
+            dct3_pre_pair(ak, an, q[k], q[nk], false, oj, on);
+            xl[sk] = oj;
+            xl[sn] = on;
+        }
+    }
+    __syncthreads();
+    fft_inv<L>(a, xl, u, T);
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        const int qq = slot_q(16, s), m = k1 + G::S1 * qq;
+        line[qq < 8 ? 2 * m : 2 * (N - 1 - m) + 1] = a[s];
+    }
+}
+
+// ---- P3: LPC rows per CTA.  DCT-III along x, u' = rhs / (4 N), Logger epilogue ------------------------------------------
+template <class R, int L, int LPC>
+__global__ void __launch_bounds__(LPC * Geo<L>::TPL) k_rg_rows_inv(int ny, const double2 *__restrict__ specT, vec2_t<R> *est0, vec2_t<R> *est1, R fourN,
+                                                                   const double2 *__restrict__ q, Tw16 T, CurvHook H) {
+    using G = Geo<L>;
+    constexpr int N = G::N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *x = reinterpret_cast<double2 *>(smem_raw);   // [LPC][N]
+    const int pair = blockIdx.y;
+    const size_t pair_off = (size_t)pair * N * ny;
+    vec2_t<R> *__restrict__ unew = est1;
+    const vec2_t<R> *__restrict__ uold = est0;
+    PairCtl *c = nullptr;
+    if (H.enabled) {
+        c = H.ctl + pair;
+        if (!__ldcg(&c->active)) return;
+        if (__ldcg(&c->sel)) { unew = est0; uold = est1; }
+    }
+    unew += pair_off; uold += pair_off; specT += pair_off;
+    const int tid = threadIdx.x, l = tid / G::TPL, u = tid % G::TPL, j0 = blockIdx.x * LPC;
+    constexpr int hp = (N >> 1) + 1;   // j = 0 .. N/2
+    for (int e = tid; e < LPC * hp; e += LPC * G::TPL) {
+        const int ll = e % LPC, j = e / LPC, nj = N - j;
+        double2 *base = x + ll * N;
+        const double2 Xj = specT[(size_t)j * ny + j0 + ll];
+        if (j == 0) { base[0] = Xj; continue; }                     // h_0 = X_0; pos(0) = 0 = swz(0)
+        const bool self = nj == j;
+        const double2 Xn = self ? Xj : specT[(size_t)nj * ny + j0 + ll];
+        double2 oj, on;
+        dct3_pre_pair(Xj, Xn, q[j], q[nj], self, oj, on);
+        base[swz(G::pos(j))] = oj;
+        if (!self) base[swz(G::pos(nj))] = on;
+    }
+    __syncthreads();
+    double2 a[16];
+    fft_inv<L>(a, x + l * N, u, T);
+    double sd = 0.0, sp = 0.0;
+    {
+        const int k = G::k1(u);
+        const size_t row = (size_t)(j0 + l) * N;
+#pragma unroll
+        for (int qq = 0; qq < 8; qq++) {
+            // t[m] (mine, m = k + S1 qq) is pixel 2m; pixel 2m+1 is t[N-1-m] = element 15-qq of lane ^ 16
+            const double2 ve = a[slot_q(16, qq)], vs = a[slot_q(16, 15 - qq)];
+            const vec2_t<R> o0 = mk2<R>((R)ve.x / fourN, (R)ve.y / fourN);                      // OpticalFlowCurvature.cpp:116-117
+            const vec2_t<R> os = mk2<R>((R)vs.x / fourN, (R)vs.y / fourN);
+            const vec2_t<R> o1 = mk2<R>(__shfl_xor_sync(0xffffffffu, os.x, 16), __shfl_xor_sync(0xffffffffu, os.y, 16));
+            const size_t g = row + 2 * (k + G::S1 * qq);
+            store_px_pair<R>(unew + g, o0, o1);
+            if (H.enabled) {   // Logger.cpp:32-51: prev is the estimate this iteration started from
+                vec2_t<R> p0, p1;
+                load_px_pair<R>(uold + g, p0, p1);
+                const vec2_t<R> d0 = mk2<R>(o0.x - p0.x, o0.y - p0.y), d1 = mk2<R>(o1.x - p1.x, o1.y - p1.y);
+                if (sizeof(R) == 4) {
+                    sd += (double)sqrtf((float)(d0.x * d0.x + d0.y * d0.y)) + (double)sqrtf((float)(d1.x * d1.x + d1.y * d1.y));
+                    sp += (double)sqrtf((float)(p0.x * p0.x + p0.y * p0.y)) + (double)sqrtf((float)(p1.x * p1.x + p1.y * p1.y));
+                } else {
+                    sd += sqrt((double)(d0.x * d0.x + d0.y * d0.y)) + sqrt((double)(d1.x * d1.x + d1.y * d1.y));
+                    sp += sqrt((double)(p0.x * p0.x + p0.y * p0.y)) + sqrt((double)(p1.x * p1.x + p1.y * p1.y));
+                }
+            }
+        }
+    }
+    if (!H.enabled) return;
+    block_sum2(sd, sp);
+    const double vals[2] = {sd, sp};
+    double *part = H.partials + (size_t)pair * H.pstride;
+    if (publish_partials<2>(vals, part, &c->ticket[0], gridDim.x, blockIdx.x)) {
+        double out[2];
+        reduce_partials<2>(part, gridDim.x, out, 0u, 0u);
+        if (threadIdx.x == 0) {
+            c->sel ^= 1;
+            finalize_logger<R>(c, H.tr, pair, out[0], out[1], (unsigned)(N * ny), H.n_active);
+        }
+    }
+}
+
+}  // namespace rg
+}  // namespace

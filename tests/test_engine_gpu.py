@@ -53,7 +53,7 @@ def test_engine_is_bit_identical_to_strict(bits, reg, params, niter, dimx, dimy)
 
 
 @pytest.mark.parametrize("bits", [32, 64])
-@pytest.mark.parametrize("dimx,dimy", [(128, 128), (256, 64)])
+@pytest.mark.parametrize("dimx,dimy", [(128, 128), (256, 64), (512, 512), (1024, 512)])
 def test_engine_curvature_fast_dct(bits, dimx, dimy):
     R, T = S.make_pair(dimx, dimy, "lattice", shift=(1.5, -0.75))
     mf, tf = run(bits, False, (dimx, dimy), R, T, of.CURVATURE, [0.25, 1.0], [12])

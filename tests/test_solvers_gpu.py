@@ -174,7 +174,8 @@ def test_dct2d_matches_fftw_definition(n0, n1, kind):
 
 
 @pytest.mark.parametrize("bits", BITS)
-@pytest.mark.parametrize("dimx,dimy", [(64, 32), (128, 128), (48, 40), (64, 64), (256, 128), (64, 512), (1024, 64), (2048, 256), (128, 4096)])
+@pytest.mark.parametrize("dimx,dimy", [(64, 32), (128, 128), (48, 40), (64, 64), (256, 128), (64, 512), (1024, 64), (2048, 256), (128, 4096),
+                                       (512, 512), (1024, 512), (512, 2048), (4096, 512), (2048, 1024)])   # >= 512 both ways: register path (dct_reg.cuh)
 def test_curvature_steps(bits, dimx, dimy):
     dev = device()
     orc, R, T, g, it, _ = _setup(bits, dimx, dimy)
