@@ -181,6 +181,21 @@ template <int L> __device__ __forceinline__ void fft_inv(double2 (&a)[16], doubl
     }
 }
 
+// DCT-II post-twiddle of the pair (k, N-k) of the packed FFT output (same algebra as dct2_post_pair with the factors
+// 1/2 and 2 cancelled and q_{N-k} = -i conj(q_k)): ok = (A_k, B_k), on = (A_{N-k}, B_{N-k}).  zn = zk for k = 0, N/2.
+__device__ __forceinline__ void post_pair(double2 zk, double2 zn, double2 q, double2 &ok, double2 &on) {
+    const double sx = zk.x + zn.x, sy = zk.y - zn.y, dx = zk.x - zn.x, dy = zk.y + zn.y;
+    ok = make_double2(fma(sx, q.x, -(sy * q.y)), fma(dy, q.x, dx * q.y));
+    on = make_double2(-fma(sx, q.y, sy * q.x), fma(dx, q.x, -(dy * q.y)));
+}
+// DCT-III pre-twiddle of the pair (j, N-j), j >= 1: h_j = (X_j - i X_{N-j}) conj(q_j) for both packed sequences
+__device__ __forceinline__ void pre_pair(double2 Xj, double2 Xn, double2 q, double2 &oj, double2 &on) {
+    const double har = fma(Xj.x, q.x, -(Xn.x * q.y)), hai = -fma(Xj.x, q.y, Xn.x * q.x);
+    const double hbr = fma(Xj.y, q.x, -(Xn.y * q.y)), hbi = -fma(Xj.y, q.y, Xn.y * q.x);
+    oj = make_double2(har - hbi, hai + hbr);
+    on = make_double2(har + hbi, hbr - hai);
+}
+
 template <class R> __device__ __forceinline__ void load_px_pair(const vec2_t<R> *p, vec2_t<R> &a, vec2_t<R> &b) { a = p[0]; b = p[1]; }
 template <> __device__ __forceinline__ void load_px_pair<float>(const float2 *p, float2 &a, float2 &b) {
     const float4 v = *reinterpret_cast<const float4 *>(p);
@@ -231,7 +246,7 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL) k_rg_rows_fwd(int ny, const
         const int ll = e % LPC, k = e / LPC, nk = (N - k) & (N - 1);
         const double2 *base = x + ll * N;
         double2 ok, on;
-        dct2_post_pair(base[swz(G::pos(k))], base[swz(G::pos(nk))], q[k], q[nk], nk == k, ok, on);
+        post_pair(base[swz(G::pos(k))], base[swz(G::pos(nk))], q[k], ok, on);
         specT[(size_t)k * ny + j0 + ll] = ok;
         if (nk != k) specT[(size_t)nk * ny + j0 + ll] = on;
     }
@@ -239,7 +254,7 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL) k_rg_rows_fwd(int ny, const
 
 // ---- P2: LPC spectrum columns (contiguous in spec_T) per CTA: DCT-II along y, eigenvalues, DCT-III along y ------------
 template <int L, int LPC>
-__global__ void __launch_bounds__(LPC * Geo<L>::TPL) k_rg_cols(int nx, double2 *__restrict__ specT, const double *__restrict__ cosx, const double *__restrict__ cosy,
+__global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 128 ? 4 : 2) k_rg_cols(int nx, double2 *__restrict__ specT, const double *__restrict__ cosx, const double *__restrict__ cosy,
                                                                double tau_alpha, const double2 *__restrict__ q, Tw16 T, CurvHook H) {
     using G = Geo<L>;
     constexpr int N = G::N;
@@ -258,37 +273,39 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL) k_rg_cols(int nx, double2 *
     }
     fft_fwd<L>(a, xl, u, T);
     const double cxp = cosx[p];
-#pragma unroll 2
-    for (int c = 0; c <= 8; c++) {
-        const int k = c < 8 ? u + G::TPL * c : N >> 1;
-        if (c == 8 && u != 0) break;
-        const int nk = (N - k) & (N - 1);
-        const bool self = nk == k;
+#pragma unroll 4
+    for (int c = 0; c < 8; c++) {   // pairs (k, N-k), k = 1 .. N/2-1 (k = 0 of thread 0, c = 0, is handled below)
+        const int k = u + G::TPL * c, nk = (N - k) & (N - 1);
         const int sk = swz(G::pos(k)), sn = swz(G::pos(nk));
+        const double2 qk = q[k];
         double2 ak, an;
-        dct2_post_pair(xl[sk], xl[sn], q[k], q[nk], self, ak, an);
-        {   // OpticalFlowCurvature.cpp:24, :135-136
-            const double lap = -4 + cxp + cosy[k];
-            const double eig = 1.0f / (1.0f + tau_alpha * (lap * lap));
-            ak.x *= eig; ak.y *= eig;
-        }
-        if (!self) {
-            const double lap = -4 + cxp + cosy[nk];
-            const double eig = 1.0f / (1.0f + tau_alpha * (lap * lap));
-            an.x *= eig; an.y *= eig;
-        }
-        if (k == 0) {
-            xl[sk] = ak;                          // h_0 = X_0
-        } else if (self) {
-            double2 oj, dummy;
-            dct3_pre_pair(ak, ak, q[k], q[k], true, oj, dummy);
-            xl[sk] = oj;
+        post_pair(xl[sk], xl[sn], qk, ak, an);
+        // OpticalFlowCurvature.cpp:24, :135-136: 1 / (1 + tau alpha lap^2) for k and N-k, with one division for the two
+        const double lk = -4 + cxp + cosy[k], ln = -4 + cxp + cosy[nk];
+        const double dk = 1.0f + tau_alpha * (lk * lk), dn = 1.0f + tau_alpha * (ln * ln);
+        const double r = 1.0 / (dk * dn), ek = r * dn, en = r * dk;
+        ak.x *= ek; ak.y *= ek; an.x *= en; an.y *= en;
+        double2 oj, on;
+        pre_pair(ak, an, qk, oj, on);
+        if (k == 0) {                             // self pair: h_0 = X_0
+            xl[sk] = ak;
         } else {
-            double2 oj, on;
-            dct3_pre_pair(ak, an, q[k], q[nk], false, oj, on);
             xl[sk] = oj;
             xl[sn] = on;
         }
+    }
+    if (u == 0) {                                 // self pair k = N/2
+        constexpr int k = N >> 1;
+        const int sk = swz(G::pos(k));
+        const double2 qk = q[k], z = xl[sk];
+        double2 ak, an;
+        post_pair(z, z, qk, ak, an);
+        const double lk = -4 + cxp + cosy[k];
+        const double ek = 1.0f / (1.0f + tau_alpha * (lk * lk));
+        ak.x *= ek; ak.y *= ek;
+        double2 oj, on;
+        pre_pair(ak, ak, qk, oj, on);
+        xl[sk] = oj;
     }
     __syncthreads();
     fft_inv<L>(a, xl, u, T);
@@ -319,21 +336,36 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL) k_rg_rows_inv(int ny, const
     }
     unew += pair_off; uold += pair_off; specT += pair_off;
     const int tid = threadIdx.x, l = tid / G::TPL, u = tid % G::TPL, j0 = blockIdx.x * LPC;
-    constexpr int hp = (N >> 1) + 1;   // j = 0 .. N/2
-    for (int e = tid; e < LPC * hp; e += LPC * G::TPL) {
-        const int ll = e % LPC, j = e / LPC, nj = N - j;
-        double2 *base = x + ll * N;
-        const double2 Xj = specT[(size_t)j * ny + j0 + ll];
-        if (j == 0) { base[0] = Xj; continue; }                     // h_0 = X_0; pos(0) = 0 = swz(0)
-        const bool self = nj == j;
-        const double2 Xn = self ? Xj : specT[(size_t)nj * ny + j0 + ll];
-        double2 oj, on;
-        dct3_pre_pair(Xj, Xn, q[j], q[nj], self, oj, on);
-        base[swz(G::pos(j))] = oj;
-        if (!self) base[swz(G::pos(nj))] = on;
+    double2 a[16];
+    {   // pairs (j, N-j), j = 1 .. N/2-1: LPC (N/2-1) work items, 8 per thread; all 16 loads are issued before the first use
+        constexpr int NT = LPC * G::TPL, items = LPC * ((N >> 1) - 1);
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int e = tid + NT * c, ll = e % LPC, j = 1 + e / LPC;
+            if (e < items) {
+                a[2 * c] = specT[(size_t)j * ny + j0 + ll];
+                a[2 * c + 1] = specT[(size_t)(N - j) * ny + j0 + ll];
+            }
+        }
+        if (tid < 2 * LPC) {                                          // j = 0 (h_0 = X_0; pos(0) = 0 = swz(0)) and the self pair j = N/2
+            const int ll = tid % LPC, j = (tid / LPC) * (N >> 1);
+            const double2 Xj = specT[(size_t)j * ny + j0 + ll];
+            double2 oj = Xj, on;
+            if (j) pre_pair(Xj, Xj, q[j], oj, on);
+            x[ll * N + swz(G::pos(j))] = oj;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int e = tid + NT * c, ll = e % LPC, j = 1 + e / LPC;
+            if (e < items) {
+                double2 oj, on;
+                pre_pair(a[2 * c], a[2 * c + 1], q[j], oj, on);
+                x[ll * N + swz(G::pos(j))] = oj;
+                x[ll * N + swz(G::pos(N - j))] = on;
+            }
+        }
     }
     __syncthreads();
-    double2 a[16];
     fft_inv<L>(a, x + l * N, u, T);
     double sd = 0.0, sp = 0.0;
     {
