@@ -392,7 +392,8 @@ struct of2d_curvature_plan {
     LineTables Tx, Ty;
     void *blob_x, *blob_y;
     double *d_cosx, *d_cosy;
-    void *d_spec;
+    void *d_spec;    // spectrum between the row and the column pass (transposed on the fast paths)
+    void *d_spec2;   // register path: column pass output in the natural layout
     int cols_per_cta;
     size_t smem_rows, smem_cols;
     int batch;
@@ -416,7 +417,7 @@ int launch_reg_rows(of2d_curvature_plan *P, bool fwd, const R *u, R *unew, const
     } else {
         { int st = of2d_ensure_dynamic_smem((const void *)rg::k_rg_rows_inv<R, LX, LPC>, smem); if (st) return st; }
         ProfScope _ps(ctx, "curv_rows_inv");
-        rg::k_rg_rows_inv<R, LX, LPC><<<dim3(P->ny / LPC, batch), NT, smem, ctx->stream>>>(P->ny, (const double2 *)P->d_spec, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN,
+        rg::k_rg_rows_inv<R, LX, LPC><<<dim3(P->ny / LPC, batch), NT, smem, ctx->stream>>>(P->ny, (const double2 *)P->d_spec2, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN,
                                                                                        (const double2 *)P->Tx.q, T, H);
     }
     OF2D_LAUNCH_CHECK(ctx);
@@ -425,12 +426,13 @@ int launch_reg_rows(of2d_curvature_plan *P, bool fwd, const R *u, R *unew, const
 template <int LY>
 int launch_reg_cols(of2d_curvature_plan *P, const CurvHook &H, int batch) {
     of2d_ctx *ctx = P->ctx;
-    constexpr int TPL = rg::Geo<LY>::TPL, LPC = TPL >= 128 ? 1 : 128 / TPL, NT = LPC * TPL;
-    const size_t smem = sizeof(double2) * (size_t)P->ny * LPC;
+    constexpr int NT = 2 * rg::Geo<LY>::TPL;
+    const size_t smem = sizeof(double2) * (size_t)P->ny * 2;
     const rg::Tw16 T{(const double2 *)P->Ty.tw16a, (const double2 *)P->Ty.tw16b};
-    { int st = of2d_ensure_dynamic_smem((const void *)rg::k_rg_cols<LY, LPC>, smem); if (st) return st; }
+    { int st = of2d_ensure_dynamic_smem((const void *)rg::k_rg_cols<LY>, smem); if (st) return st; }
     ProfScope _ps(ctx, "curv_cols");
-    rg::k_rg_cols<LY, LPC><<<dim3(P->nx / LPC, batch), NT, smem, ctx->stream>>>(P->nx, (double2 *)P->d_spec, P->d_cosx, P->d_cosy, P->tau_alpha, (const double2 *)P->Ty.q, T, H);
+    rg::k_rg_cols<LY><<<dim3(P->nx / 2, batch), NT, smem, ctx->stream>>>(P->nx, (const double2 *)P->d_spec, (double2 *)P->d_spec2, P->d_cosx, P->d_cosy, P->tau_alpha,
+                                                                      (const double2 *)P->Ty.q, T, H);
     OF2D_LAUNCH_CHECK(ctx);
     return OF2D_SUCCESS;
 }
@@ -529,6 +531,7 @@ int of2d_curvature_plan_create(of2d_ctx *ctx, int nx, int ny, double alpha, doub
     if (e == cudaSuccess) e = cudaMemcpy(P->d_cosx, hx, sizeof(double) * nx, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(P->d_cosy, hy, sizeof(double) * ny, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&P->d_spec, sizeof(double2) * (size_t)nx * ny);
+    if (e == cudaSuccess && P->Tx.tw16a && P->Ty.tw16a) e = cudaMalloc(&P->d_spec2, sizeof(double2) * (size_t)nx * ny);
     free(hx); free(hy);
     if (e != cudaSuccess) {
         of2d_set_error("curvature plan: %s", cudaGetErrorString(e));
@@ -554,7 +557,7 @@ int of2d_curvature_plan_create(of2d_ctx *ctx, int nx, int ny, double alpha, doub
 void of2d_curvature_plan_destroy(of2d_curvature_plan *P) {
     if (!P) return;
     cudaStreamSynchronize(P->ctx->stream);
-    cudaFree(P->blob_x); cudaFree(P->blob_y); cudaFree(P->d_cosx); cudaFree(P->d_cosy); cudaFree(P->d_spec);
+    cudaFree(P->blob_x); cudaFree(P->blob_y); cudaFree(P->d_cosx); cudaFree(P->d_cosy); cudaFree(P->d_spec); cudaFree(P->d_spec2);
     delete P;
 }
 
@@ -580,6 +583,11 @@ int of2d_curvature_plan_set_batch(of2d_curvature_plan *P, int batch) {
     OF2D_CUDA_TRY(cudaFree(P->d_spec));
     P->d_spec = nullptr;
     OF2D_CUDA_TRY(cudaMalloc(&P->d_spec, sizeof(double2) * (size_t)P->nx * P->ny * batch));
+    if (P->d_spec2) {
+        OF2D_CUDA_TRY(cudaFree(P->d_spec2));
+        P->d_spec2 = nullptr;
+        OF2D_CUDA_TRY(cudaMalloc(&P->d_spec2, sizeof(double2) * (size_t)P->nx * P->ny * batch));
+    }
     P->batch = batch;
     return OF2D_SUCCESS;
 }

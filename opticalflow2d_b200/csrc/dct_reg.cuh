@@ -113,11 +113,12 @@ template <int L> struct Geo {
 struct Tw16 { const double2 *a, *b; };   // [4][S1] for super-pass 1 (w_N), [4][S2] for super-pass 2 (w_{N/16}); forward sign
 
 // ---- forward (DIF): registers -> ... -> shared memory, digit-reversed --------------------------------------------
-// in: a[j] = v[k + S1 j] (natural order), k = Geo::k1(u).  out: X_k at xl[swz(pos(k))], after the trailing barrier.
-template <int L> __device__ __forceinline__ void fft_fwd(double2 (&a)[16], double2 *xl, int u, Tw16 T) {
+// in: a[j] = v[k + S1 j] (natural order); the threads of a line hold k1 = a permutation of 0 .. S1-1 and u = 0 .. S1-1.
+// out: X_k at xl[swz(pos(k))], after the trailing barrier.
+template <int L> __device__ __forceinline__ void fft_fwd(double2 (&a)[16], double2 *xl, int u, int k1, Tw16 T) {
     using G = Geo<L>;
     {
-        const int k = G::k1(u);
+        const int k = k1;
         dft<16, -1, 0>(a);
         twiddle16<true, false>(a, T.a[k], T.a[G::S1 + k], T.a[2 * G::S1 + k], T.a[3 * G::S1 + k]);
 #pragma unroll
@@ -148,8 +149,10 @@ template <int L> __device__ __forceinline__ void fft_fwd(double2 (&a)[16], doubl
 }
 
 // ---- inverse (DIT, unnormalised): shared memory, digit-reversed -> ... -> registers -------------------------------
-// in: h_k at xl[swz(pos(k))] (caller has synchronised).  out: a[s] = t[k + S1 q], q = slot_q(16, s), k = Geo::k1(u).
-template <int L> __device__ __forceinline__ void fft_inv(double2 (&a)[16], double2 *xl, int u, Tw16 T) {
+// in: h_k at xl[swz(pos(k))] (caller has synchronised).  out: a[s] = t[k1 + S1 q], q = slot_q(16, s).
+// `before_last_barrier` runs while a[] is dead (prefetches of the epilogue go there).
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+template <int L, class Hook = NoHook> __device__ __forceinline__ void fft_inv(double2 (&a)[16], double2 *xl, int u, int k1, Tw16 T, Hook before_last_barrier = Hook()) {
     using G = Geo<L>;
     {
 #pragma unroll
@@ -171,9 +174,10 @@ template <int L> __device__ __forceinline__ void fft_inv(double2 (&a)[16], doubl
 #pragma unroll
         for (int s = 0; s < 16; s++) xl[swz(base + G::S2 * slot_q(16, s))] = a[s];
     }
+    before_last_barrier();
     __syncthreads();
     {
-        const int k = G::k1(u);
+        const int k = k1;
 #pragma unroll
         for (int j = 0; j < 16; j++) a[j] = xl[swz(k + G::S1 * j)];
         twiddle16<false, true>(a, T.a[k], T.a[G::S1 + k], T.a[2 * G::S1 + k], T.a[3 * G::S1 + k]);
@@ -208,7 +212,7 @@ template <> __device__ __forceinline__ void load_s_pair<float>(const float *p, f
 
 // ---- P1: LPC rows per CTA.  rhs = u - tau f, DCT-II along x, spectrum written transposed -----------------------------
 template <class R, int L, int LPC>
-__global__ void __launch_bounds__(LPC * Geo<L>::TPL) k_rg_rows_fwd(int ny, const vec2_t<R> *est0, const vec2_t<R> *est1, const vec2_t<R> *__restrict__ gradI,
+__global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 2 : 1) k_rg_rows_fwd(int ny, const vec2_t<R> *est0, const vec2_t<R> *est1, const vec2_t<R> *__restrict__ gradI,
                                                                    const R *__restrict__ It, R tau, double2 *__restrict__ specT, const double2 *__restrict__ q, Tw16 T,
                                                                    CurvHook H) {
     using G = Geo<L>;
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL) k_rg_rows_fwd(int ny, const
             a[15 - j] = make_double2((double)__shfl_xor_sync(0xffffffffu, ox, 16), (double)__shfl_xor_sync(0xffffffffu, oy, 16));
         }
     }
-    fft_fwd<L>(a, xl, u, T);
+    fft_fwd<L>(a, xl, u, G::k1(u), T);
     constexpr int hp = (N >> 1) + 1;
     for (int e = tid; e < LPC * hp; e += LPC * G::TPL) {
         const int ll = e % LPC, k = e / LPC, nk = (N - k) & (N - 1);
@@ -252,29 +256,33 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL) k_rg_rows_fwd(int ny, const
     }
 }
 
-// ---- P2: LPC spectrum columns (contiguous in spec_T) per CTA: DCT-II along y, eigenvalues, DCT-III along y ------------
-template <int L, int LPC>
-__global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 128 ? 4 : 2) k_rg_cols(int nx, double2 *__restrict__ specT, const double *__restrict__ cosx, const double *__restrict__ cosy,
-                                                               double tau_alpha, const double2 *__restrict__ q, Tw16 T, CurvHook H) {
+// ---- P2: two spectrum columns (contiguous lines of spec_T) per CTA: DCT-II along y, eigenvalues, DCT-III along y ------
+// Lanes 0-15 of every warp work on the first line, lanes 16-31 on the second (quarter-warps never mix lines, so the
+// shared-memory phases stay conflict-free), and the result goes out in the NATURAL layout spec_N[y][p]: lane pairs
+// (l, l+16) fill whole 32-byte sectors, so P3 reads contiguous rows and all scattered traffic of the iteration is writes.
+template <int L>
+__global__ void __launch_bounds__(2 * Geo<L>::TPL, 2 * Geo<L>::TPL <= 256 ? 2 : 1) k_rg_cols(int nx, const double2 *__restrict__ specT, double2 *__restrict__ specN,
+                                                                                        const double *__restrict__ cosx, const double *__restrict__ cosy, double tau_alpha,
+                                                                                        const double2 *__restrict__ q, Tw16 T, CurvHook H) {
     using G = Geo<L>;
     constexpr int N = G::N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *x = reinterpret_cast<double2 *>(smem_raw);   // [LPC][N]
+    double2 *x = reinterpret_cast<double2 *>(smem_raw);   // [2][N]
     if (H.enabled && !__ldcg(&H.ctl[blockIdx.y].active)) return;
-    const int tid = threadIdx.x, l = tid / G::TPL, u = tid % G::TPL, p = blockIdx.x * LPC + l;
+    const int tid = threadIdx.x, lane = tid & 31, l = lane >> 4, u = (tid >> 5) * 16 + (lane & 15), p = blockIdx.x * 2 + l;
     double2 *xl = x + l * N;
-    double2 *__restrict__ line = specT + (size_t)blockIdx.y * nx * N + (size_t)p * N;
-    const int k1 = G::k1(u);
+    const double2 *__restrict__ line = specT + (size_t)blockIdx.y * nx * N + (size_t)p * N;
+    specN += (size_t)blockIdx.y * nx * N;
     double2 a[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-        const int m = k1 + G::S1 * j;
+        const int m = u + G::S1 * j;
         a[j] = line[j < 8 ? 2 * m : 2 * (N - 1 - m) + 1];
     }
-    fft_fwd<L>(a, xl, u, T);
+    fft_fwd<L>(a, xl, u, u, T);
     const double cxp = cosx[p];
 #pragma unroll 4
-    for (int c = 0; c < 8; c++) {   // pairs (k, N-k), k = 1 .. N/2-1 (k = 0 of thread 0, c = 0, is handled below)
+    for (int c = 0; c < 8; c++) {   // pairs (k, N-k), k = 1 .. N/2-1 (and the self pair k = 0: thread 0, c = 0)
         const int k = u + G::TPL * c, nk = (N - k) & (N - 1);
         const int sk = swz(G::pos(k)), sn = swz(G::pos(nk));
         const double2 qk = q[k];
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 128 ? 
         ak.x *= ek; ak.y *= ek; an.x *= en; an.y *= en;
         double2 oj, on;
         pre_pair(ak, an, qk, oj, on);
-        if (k == 0) {                             // self pair: h_0 = X_0
+        if (k == 0) {                             // h_0 = X_0
             xl[sk] = ak;
         } else {
             xl[sk] = oj;
@@ -308,17 +316,17 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 128 ? 
         xl[sk] = oj;
     }
     __syncthreads();
-    fft_inv<L>(a, xl, u, T);
+    fft_inv<L>(a, xl, u, u, T);
 #pragma unroll
     for (int s = 0; s < 16; s++) {
-        const int qq = slot_q(16, s), m = k1 + G::S1 * qq;
-        line[qq < 8 ? 2 * m : 2 * (N - 1 - m) + 1] = a[s];
+        const int qq = slot_q(16, s), m = u + G::S1 * qq, y = qq < 8 ? 2 * m : 2 * (N - 1 - m) + 1;
+        specN[(size_t)y * nx + p] = a[s];
     }
 }
 
 // ---- P3: LPC rows per CTA.  DCT-III along x, u' = rhs / (4 N), Logger epilogue ------------------------------------------
 template <class R, int L, int LPC>
-__global__ void __launch_bounds__(LPC * Geo<L>::TPL) k_rg_rows_inv(int ny, const double2 *__restrict__ specT, vec2_t<R> *est0, vec2_t<R> *est1, R fourN,
+__global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 2 : 1) k_rg_rows_inv(int ny, const double2 *__restrict__ specN, vec2_t<R> *est0, vec2_t<R> *est1, R fourN,
                                                                    const double2 *__restrict__ q, Tw16 T, CurvHook H) {
     using G = Geo<L>;
     constexpr int N = G::N;
@@ -334,29 +342,30 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL) k_rg_rows_inv(int ny, const
         if (!__ldcg(&c->active)) return;
         if (__ldcg(&c->sel)) { unew = est0; uold = est1; }
     }
-    unew += pair_off; uold += pair_off; specT += pair_off;
+    unew += pair_off; uold += pair_off; specN += pair_off;
     const int tid = threadIdx.x, l = tid / G::TPL, u = tid % G::TPL, j0 = blockIdx.x * LPC;
     double2 a[16];
-    {   // pairs (j, N-j), j = 1 .. N/2-1: LPC (N/2-1) work items, 8 per thread; all 16 loads are issued before the first use
-        constexpr int NT = LPC * G::TPL, items = LPC * ((N >> 1) - 1);
+    {   // pairs (j, N-j), j = 1 .. N/2-1 of each line (contiguous in spec_N): 8 per thread, all 16 loads issued before the first use
+        constexpr int NT = LPC * G::TPL, per_line = (N >> 1) - 1, items = LPC * per_line;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            const int e = tid + NT * c, ll = e % LPC, j = 1 + e / LPC;
+            const int e = tid + NT * c, ll = e / per_line, j = 1 + e % per_line;
             if (e < items) {
-                a[2 * c] = specT[(size_t)j * ny + j0 + ll];
-                a[2 * c + 1] = specT[(size_t)(N - j) * ny + j0 + ll];
+                const double2 *ln = specN + (size_t)(j0 + ll) * N;
+                a[2 * c] = ln[j];
+                a[2 * c + 1] = ln[N - j];
             }
         }
         if (tid < 2 * LPC) {                                          // j = 0 (h_0 = X_0; pos(0) = 0 = swz(0)) and the self pair j = N/2
             const int ll = tid % LPC, j = (tid / LPC) * (N >> 1);
-            const double2 Xj = specT[(size_t)j * ny + j0 + ll];
+            const double2 Xj = specN[(size_t)(j0 + ll) * N + j];
             double2 oj = Xj, on;
             if (j) pre_pair(Xj, Xj, q[j], oj, on);
             x[ll * N + swz(G::pos(j))] = oj;
         }
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            const int e = tid + NT * c, ll = e % LPC, j = 1 + e / LPC;
+            const int e = tid + NT * c, ll = e / per_line, j = 1 + e % per_line;
             if (e < items) {
                 double2 oj, on;
                 pre_pair(a[2 * c], a[2 * c + 1], q[j], oj, on);
@@ -366,11 +375,21 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL) k_rg_rows_inv(int ny, const
         }
     }
     __syncthreads();
-    fft_inv<L>(a, x + l * N, u, T);
+    const int k = G::k1(u);
+    const size_t row = (size_t)(j0 + l) * N;
+    // Logger.cpp:32-51: prev is the estimate this iteration started from; fp32 fields: fetched while a[] is dead
+    vec2_t<R> pv[16];
+    constexpr bool PREFETCH = sizeof(R) == 4;
+    auto fetch_prev = [&]() {
+        if (H.enabled) {
+#pragma unroll
+            for (int qq = 0; qq < 8; qq++) load_px_pair<R>(uold + row + 2 * (k + G::S1 * qq), pv[2 * qq], pv[2 * qq + 1]);
+        }
+    };
+    if constexpr (PREFETCH) fft_inv<L>(a, x + l * N, u, k, T, fetch_prev);
+    else { fft_inv<L>(a, x + l * N, u, k, T); fetch_prev(); }
     double sd = 0.0, sp = 0.0;
     {
-        const int k = G::k1(u);
-        const size_t row = (size_t)(j0 + l) * N;
 #pragma unroll
         for (int qq = 0; qq < 8; qq++) {
             // t[m] (mine, m = k + S1 qq) is pixel 2m; pixel 2m+1 is t[N-1-m] = element 15-qq of lane ^ 16
@@ -378,11 +397,9 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL) k_rg_rows_inv(int ny, const
             const vec2_t<R> o0 = mk2<R>((R)ve.x / fourN, (R)ve.y / fourN);                      // OpticalFlowCurvature.cpp:116-117
             const vec2_t<R> os = mk2<R>((R)vs.x / fourN, (R)vs.y / fourN);
             const vec2_t<R> o1 = mk2<R>(__shfl_xor_sync(0xffffffffu, os.x, 16), __shfl_xor_sync(0xffffffffu, os.y, 16));
-            const size_t g = row + 2 * (k + G::S1 * qq);
-            store_px_pair<R>(unew + g, o0, o1);
-            if (H.enabled) {   // Logger.cpp:32-51: prev is the estimate this iteration started from
-                vec2_t<R> p0, p1;
-                load_px_pair<R>(uold + g, p0, p1);
+            store_px_pair<R>(unew + row + 2 * (k + G::S1 * qq), o0, o1);
+            if (H.enabled) {
+                const vec2_t<R> p0 = pv[2 * qq], p1 = pv[2 * qq + 1];
                 const vec2_t<R> d0 = mk2<R>(o0.x - p0.x, o0.y - p0.y), d1 = mk2<R>(o1.x - p1.x, o1.y - p1.y);
                 if (sizeof(R) == 4) {
                     sd += (double)sqrtf((float)(d0.x * d0.x + d0.y * d0.y)) + (double)sqrtf((float)(d1.x * d1.x + d1.y * d1.y));
