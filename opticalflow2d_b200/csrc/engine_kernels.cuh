@@ -102,10 +102,14 @@ template <class R> struct NormAcc {
 
 struct TileWalk {
     int tiles_x, ntiles;
+    unsigned magic;   // ceil(2^32 / tiles_x): tile / tiles_x == umulhi(tile, magic) while tile * tiles_x < 2^32
     __device__ __forceinline__ TileWalk(int fast_extent, int slow_extent) {
         tiles_x = (fast_extent + TILE - 1) / TILE;
         ntiles = tiles_x * ((slow_extent + TILE - 1) / TILE);
+        magic = tiles_x > 1 ? 0xFFFFFFFFu / (unsigned)tiles_x + 1u : 0u;
     }
+    __device__ __forceinline__ int ty(int tile) const { return tiles_x > 1 ? (int)__umulhi((unsigned)tile, magic) : tile; }
+    __device__ __forceinline__ int tx(int tile) const { return tile - ty(tile) * tiles_x; }
 };
 
 // Logger epilogue shared by the kernels that produce the next estimate
@@ -177,8 +181,8 @@ __global__ void __launch_bounds__(TX *TY) k_hs_iter(EngK<R> K, const vec2_t<R> *
     NormAcc<R> acc;
     bool divzero = false;
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
-        const int i = (tile % T.tiles_x) * TILE + threadIdx.x;
-        const int jb = (tile / T.tiles_x) * TILE + threadIdx.y;
+        const int i = T.tx(tile) * TILE + threadIdx.x;
+        const int jb = T.ty(tile) * TILE + threadIdx.y;
         // all loads of the thread's 4 pixels are issued before any arithmetic: indices are clamped into the
         // field so that they are unconditional (the clamped values are never used)
         const int ic = min(i, nx - 1);
@@ -232,8 +236,8 @@ __global__ void __launch_bounds__(TX *TY) k_e_warp(EngK<R> K, int gate, const R 
     const vec2_t<R> *__restrict__ u = pick(K, u_buf, h, pair);
     const TileWalk T(nx, ny);
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
-        const int i = (tile % T.tiles_x) * TILE + threadIdx.x;
-        const int jb = (tile / T.tiles_x) * TILE + threadIdx.y;
+        const int i = T.tx(tile) * TILE + threadIdx.x;
+        const int jb = T.ty(tile) * TILE + threadIdx.y;
         if (i >= nx) continue;
 #pragma unroll
         for (int p = 0; p < PY; p++) {
@@ -258,8 +262,8 @@ __global__ void __launch_bounds__(TX *TY) k_e_compose(EngK<R> K, int gate, int u
     vec2_t<R> *__restrict__ out = pick(K, out_buf, h, pair);
     const TileWalk T(nx, ny);
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
-        const int i = (tile % T.tiles_x) * TILE + threadIdx.x;
-        const int jb = (tile / T.tiles_x) * TILE + threadIdx.y;
+        const int i = T.tx(tile) * TILE + threadIdx.x;
+        const int jb = T.ty(tile) * TILE + threadIdx.y;
         if (i >= nx) continue;
 #pragma unroll
         for (int p = 0; p < PY; p++) {
@@ -288,8 +292,8 @@ __global__ void __launch_bounds__(TX *TY) k_e_square(EngK<R> K, int s) {
     const R sc = s == 0 ? (R)__ldcg(&c->scale) : (R)1;
     const TileWalk T(nx, ny);
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
-        const int i = (tile % T.tiles_x) * TILE + threadIdx.x;
-        const int jb = (tile / T.tiles_x) * TILE + threadIdx.y;
+        const int i = T.tx(tile) * TILE + threadIdx.x;
+        const int jb = T.ty(tile) * TILE + threadIdx.y;
         if (i >= nx) continue;
 #pragma unroll
         for (int p = 0; p < PY; p++) {
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(TX *TY) k_e_demons_force(EngK<R> K, const R *_
     const TileWalk T(nx, ny);
     bool divzero = false;
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
-        const int i0 = (tile % T.tiles_x) * TILE, j0 = (tile / T.tiles_x) * TILE;
+        const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
         __syncthreads();
         for (int e = tid; e < (TILE + 2) * (TILE + 2); e += TX * TY) {
             const int r = e / (TILE + 2), cc = e - r * (TILE + 2);
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int d
     __syncthreads();
     const TileWalk T(nx, ny);
     auto tile_start = [&](int tile, int r) -> long {   // flat index of element (r, -shift) of the tile's window
-        const int i0 = (tile % T.tiles_x) * TILE, j0 = (tile / T.tiles_x) * TILE;
+        const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
         return (long)(j0 + r - cx) * nx + (i0 - cx - shift);
     };
     auto tma_ok = [&](int tile) -> bool { return rows_aligned && tile_start(tile, 0) >= 0 && tile_start(tile, SH - 1) + SWp <= n; };
@@ -432,7 +436,7 @@ __global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int d
     if ((int)blockIdx.x < T.ntiles && threadIdx.y == 0 && tma_ok(blockIdx.x)) issue(blockIdx.x, 0);
     int kiter = 0;
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x, kiter++) {
-        const int i0 = (tile % T.tiles_x) * TILE, j0 = (tile / T.tiles_x) * TILE;
+        const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
         const int st = kiter & 1, next = tile + gridDim.x;
         if (next < T.ntiles && threadIdx.y == 0 && tma_ok(next)) issue(next, st ^ 1);   // stage st^1 was last read one iteration ago
         vec2_t<R> *tile_s = stages + st * stage_elems + shift;    // element (r, cc) of the window at tile_s[r * SWp + cc]
@@ -454,8 +458,21 @@ __global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int d
         // every tap of every pixel of the tile inside [0, n)?  (first / last flat index of the tile's windows)
         const long lo = (long)(j0 - cx) * nx + (i0 - cx), hi = (long)(min(j0 + TILE, ny) - 1 + cx) * nx + (min(i0 + TILE, nx) - 1 + cx);
         const bool tile_interior = lo >= 0 && hi < n;
-        vec2_t<R> o[4];
-        if (KW > 0 && tile_interior) {
+        auto epilogue = [&](vec2_t<R> o, vec2_t<R> prev) {
+            if (EPI == 1) {
+                acc.add(o, prev);
+            } else if (EPI == 2) {
+                const R s = maxabs_term<R>(o);
+                mx = mx < s ? s : mx;
+            }
+        };
+        if (KW > 0 && tile_interior && i0 + TILE <= nx && j0 + TILE <= ny) {
+            const long idx0 = i + (long)(j0 + jl0) * nx;
+            vec2_t<R> prev[4];
+            if (EPI == 1) {   // Logger's prev: in flight while the taps are accumulated
+#pragma unroll
+                for (int q = 0; q < 4; q++) prev[q] = est_cur[idx0 + (long)q * nx];
+            }
             R ax[4], ay[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) { ax[q] = (R)0; ay[q] = (R)0; }
@@ -475,8 +492,19 @@ __global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int d
                 }
             }
             const R wgt = (R)W.full_weight;
+            if (W.full_weight == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) o[q] = W.full_weight != 0 ? mk2<R>(ax[q] / wgt, ay[q] / wgt) : tile_s[(jl0 + q + cx) * SWp + threadIdx.x + cx];
+                for (int q = 0; q < 4; q++) { const vec2_t<R> ce = tile_s[(jl0 + q + cx) * SWp + threadIdx.x + cx]; ax[q] = ce.x; ay[q] = ce.y; }
+            } else if (wgt != (R)1) {   // x / 1 == x: a normalised kernel (Kernel.cpp:66-68) needs no division
+#pragma unroll
+                for (int q = 0; q < 4; q++) { ax[q] = ax[q] / wgt; ay[q] = ay[q] / wgt; }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const vec2_t<R> o = mk2<R>(ax[q], ay[q]);
+                out[idx0 + (long)q * nx] = o;
+                epilogue(o, prev[q]);
+            }
         } else {
 #pragma unroll 1
             for (int q = 0; q < 4; q++) {
@@ -496,22 +524,12 @@ __global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int d
                         ay = ay + f.y * t;
                     }
                 }
-                if (weight != 0) { const R wg = (R)weight; o[q] = mk2<R>(ax / wg, ay / wg); }
-                else o[q] = tile_s[(jl0 + q + cx) * SWp + threadIdx.x + cx];
-            }
-        }
-        if (i < nx) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int j = j0 + jl0 + q;
-                if (j >= ny) continue;
-                const long idx = i + (long)j * nx;
-                out[idx] = o[q];
-                if (EPI == 1) {
-                    acc.add(o[q], est_cur[idx]);
-                } else if (EPI == 2) {
-                    const R s = maxabs_term<R>(o[q]);
-                    mx = mx < s ? s : mx;
+                vec2_t<R> o;
+                if (weight != 0) { const R wg = (R)weight; o = mk2<R>(ax / wg, ay / wg); }
+                else o = tile_s[(jl0 + q + cx) * SWp + threadIdx.x + cx];
+                if (i < nx && j < ny) {
+                    out[idx] = o;
+                    epilogue(o, EPI == 1 ? est_cur[idx] : o);
                 }
             }
         }
@@ -562,7 +580,7 @@ __global__ void __launch_bounds__(TX *TY) k_e_derivatives(EngK<R> K, int gate, c
     const R *__restrict__ Imov = Imov_all + (size_t)pair * K.n;
     const TileWalk T(nx, ny);
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
-        const int i0 = (tile % T.tiles_x) * TILE, j0 = (tile / T.tiles_x) * TILE;
+        const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
         const int i = i0 + threadIdx.x;
         if (transposed) __syncthreads();
 #pragma unroll
@@ -608,7 +626,7 @@ __global__ void __launch_bounds__(TX *TY) k_e_untranspose(EngK<R> K, int gate, i
     vec2_t<R> *__restrict__ dst = pick(K, dst_buf, h, pair, false);
     const TileWalk T(nx, ny);
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
-        const int i0 = (tile % T.tiles_x) * TILE, j0 = (tile / T.tiles_x) * TILE;
+        const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
         __syncthreads();
         const int jt = j0 + threadIdx.x;
 #pragma unroll
@@ -668,8 +686,8 @@ __global__ void __launch_bounds__(TX *TY) k_fl_increment(EngK<R> K, vec2_t<R> *c
     const TileWalk T(ny, nx);
     R m = (R)0;
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
-        const int j = (tile % T.tiles_x) * TILE + threadIdx.x;
-        const int ib = (tile / T.tiles_x) * TILE + threadIdx.y;
+        const int j = T.tx(tile) * TILE + threadIdx.x;
+        const int ib = T.ty(tile) * TILE + threadIdx.y;
         if (j >= ny) continue;
 #pragma unroll
         for (int p = 0; p < PY; p++) {
@@ -729,8 +747,8 @@ __global__ void __launch_bounds__(TX *TY) k_fl_integrate(EngK<R> K, const vec2_t
     NormAcc<R> acc;
     R mj = (R)INFINITY;
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
-        const int j = (tile % T.tiles_x) * TILE + threadIdx.x;
-        const int ib = (tile / T.tiles_x) * TILE + threadIdx.y;
+        const int j = T.tx(tile) * TILE + threadIdx.x;
+        const int ib = T.ty(tile) * TILE + threadIdx.y;
         if (j >= ny) continue;
 #pragma unroll
         for (int p = 0; p < PY; p++) {
