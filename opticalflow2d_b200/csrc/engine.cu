@@ -74,12 +74,25 @@ EngK<R> make_k(of2d_engine *E) {
     return K;
 }
 
-// grid = (CTAs per pair, batch): enough CTAs to fill the GPU about four deep, never more than there are tiles
-inline dim3 grid_tiles(const of2d_engine *E) {
+// grid = (CTAs per pair, batch): exactly ONE wave of the kernel -- as many CTAs as are resident at once
+// (occupancy of this kernel x number of SMs), never more than there are tiles.  With a single wave every CTA
+// walks ntiles / grid tiles (+-1), so no SM waits for a partially filled last wave, and the per-CTA fixed costs
+// (control-block load, reduction partial) are paid once per resident slot.
+inline int ctas_per_sm(const void *kernel, size_t smem) {
+    static int forced = -1;
+    if (forced < 0) { const char *e = getenv("OF2D_CTAS_PER_SM"); forced = e && atoi(e) > 0 ? atoi(e) : 0; }
+    if (forced) return forced;
+    static std::vector<std::pair<std::pair<const void *, size_t>, int>> cache;
+    for (const auto &c : cache) if (c.first.first == kernel && c.first.second == smem) return c.second;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TX * TY, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 4; }
+    cache.push_back({{kernel, smem}, occ});
+    return occ;
+}
+template <class KernelT>
+inline dim3 grid_tiles(const of2d_engine *E, KernelT kernel, size_t smem = 0) {
     const int ntiles = ceil_div(E->d.dimx, TILE) * ceil_div(E->d.dimy, TILE);
-    static int per_sm = 0;
-    if (per_sm == 0) { const char *e = getenv("OF2D_CTAS_PER_SM"); per_sm = e && atoi(e) > 0 ? atoi(e) : 8; }
-    int per_pair = ceil_div((long)E->ctx->sm_count * per_sm, E->d.batch);
+    int per_pair = ceil_div((long)E->ctx->sm_count * ctas_per_sm((const void *)kernel, smem), E->d.batch);
     if (per_pair > ntiles) per_pair = ntiles;
     if (per_pair < 1) per_pair = 1;
     return dim3(per_pair, E->d.batch);
@@ -94,6 +107,7 @@ ConvW<R> conv_weights(of2d_engine *E, int which) {
     W.taps_d = (const double *)E->d_taps[which];
     for (int t = 0; t < kw * kw; t++) W.w[t] = (R)E->h_taps[which][(size_t)t];
     W.full_weight = E->full_weight[which];
+    W.neg_zero = -0.0f;
     return W;
 }
 
@@ -104,7 +118,7 @@ int launch_conv_kw(of2d_engine *E, const EngK<R> &K, int src, int dst, int which
     const int shift = sizeof(vec2_t<R>) == 8 ? (cx & 1) : 0;
     const size_t smem = 2 * sizeof(vec2_t<R>) * (size_t)(TILE + 2 * cx) * (size_t)((TILE + 2 * cx + shift + 1) & ~1);
     TRY(of2d_ensure_dynamic_smem((const void *)k_e_conv<R, EPI, KW>, smem));
-    { ProfScope _ps(E->ctx, EPI == 1 ? "conv_logger" : EPI == 2 ? "conv_maxabs" : "conv"); k_e_conv<R, EPI, KW><<<grid_tiles(E), dim3(TX, TY), smem, E->ctx->stream>>>(K, src, dst, W, E->nsq_cap); }
+    { ProfScope _ps(E->ctx, EPI == 1 ? "conv_logger" : EPI == 2 ? "conv_maxabs" : "conv"); k_e_conv<R, EPI, KW><<<grid_tiles(E, k_e_conv<R, EPI, KW>, smem), dim3(TX, TY), smem, E->ctx->stream>>>(K, src, dst, W, E->nsq_cap); }
     OF2D_LAUNCH_CHECK(E->ctx);
     return OF2D_SUCCESS;
 }
@@ -125,12 +139,12 @@ int launch_conv(of2d_engine *E, const EngK<R> &K, int src, int dst, int which) {
 template <class R>
 int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
     cudaStream_t s = E->ctx->stream;
-    const dim3 g = grid_tiles(E), b(TX, TY);
+    const dim3 b(TX, TY);
     const of2d_engine_desc &d = E->d;
     switch (d.method) {
         case 0: {
             const R alpha = (R)d.alpha;
-            { ProfScope _ps(E->ctx, "hs_iter"); k_hs_iter<R><<<g, b, 0, s>>>(K, (const vec2_t<R> *)E->gradI, (const R *)E->It, alpha * alpha); }
+            { ProfScope _ps(E->ctx, "hs_iter"); k_hs_iter<R><<<grid_tiles(E, k_hs_iter<R>), b, 0, s>>>(K, (const vec2_t<R> *)E->gradI, (const R *)E->It, alpha * alpha); }
             OF2D_LAUNCH_CHECK(E->ctx);
             break;
         }
@@ -144,20 +158,20 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
         case 3:
         case 4: {
             const R si = (R)d.sigma_i, sx = (R)d.sigma_x;
-            { ProfScope _ps(E->ctx, "demons_force"); k_e_demons_force<R><<<g, b, 0, s>>>(K, d_Iref, (const R *)E->aux, si * si, sx * sx); }
+            { ProfScope _ps(E->ctx, "demons_force"); k_e_demons_force<R><<<grid_tiles(E, k_e_demons_force<R>), b, 0, s>>>(K, d_Iref, (const R *)E->aux, si * si, sx * sx); }
             OF2D_LAUNCH_CHECK(E->ctx);
             if (d.method == 3) {
                 TRY((launch_conv<R, 0>(E, K, B_C0, B_C1, 0)));
-                { ProfScope _pc(E->ctx, "compose"); k_e_compose<R><<<g, b, 0, s>>>(K, G_ACTIVE, B_EST_CUR, B_C1, B_C0, d.accumulation == 1); }
+                { ProfScope _pc(E->ctx, "compose"); k_e_compose<R><<<grid_tiles(E, k_e_compose<R>), b, 0, s>>>(K, G_ACTIVE, B_EST_CUR, B_C1, B_C0, d.accumulation == 1); }
                 OF2D_LAUNCH_CHECK(E->ctx);
                 TRY((launch_conv<R, 1>(E, K, B_C0, B_EST_NEXT, 1)));
             } else {
                 TRY((launch_conv<R, 2>(E, K, B_C0, B_C1, 0)));
                 for (int q = 0; q < E->nsq_cap; q++) {
-                    { ProfScope _ps(E->ctx, "square"); k_e_square<R><<<g, b, 0, s>>>(K, q); }
+                    { ProfScope _ps(E->ctx, "square"); k_e_square<R><<<grid_tiles(E, k_e_square<R>), b, 0, s>>>(K, q); }
                     OF2D_LAUNCH_CHECK(E->ctx);
                 }
-                { ProfScope _pc(E->ctx, "compose"); k_e_compose<R><<<g, b, 0, s>>>(K, G_ACTIVE, B_EST_CUR, B_CRES, B_CTMP, 0); }
+                { ProfScope _pc(E->ctx, "compose"); k_e_compose<R><<<grid_tiles(E, k_e_compose<R>), b, 0, s>>>(K, G_ACTIVE, B_EST_CUR, B_CRES, B_CTMP, 0); }
                 OF2D_LAUNCH_CHECK(E->ctx);
                 TRY((launch_conv<R, 1>(E, K, B_CTMP, B_EST_NEXT, 1)));
             }
@@ -166,21 +180,20 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
         case 5: {
             TRY(sor_tile_launch<R>(E->ctx, E->sor, K.ctl, K.n_active, K.partials, K.pstride, K.tr, 1, (vec2_t<R> *)E->vel[0], (vec2_t<R> *)E->vel[1],
                                    (const vec2_t<R> *)E->est[0], (const vec2_t<R> *)E->est[1], (const vec2_t<R> *)E->gradI, (const R *)E->It));
-            const dim3 gt = g;
-            { ProfScope _ps(E->ctx, "fluid_increment"); k_fl_increment<R><<<gt, b, 0, s>>>(K, (vec2_t<R> *)E->vel[0], (vec2_t<R> *)E->vel[1], (vec2_t<R> *)E->incr); }
+            { ProfScope _ps(E->ctx, "fluid_increment"); k_fl_increment<R><<<grid_tiles(E, k_fl_increment<R>), b, 0, s>>>(K, (vec2_t<R> *)E->vel[0], (vec2_t<R> *)E->vel[1], (vec2_t<R> *)E->incr); }
             OF2D_LAUNCH_CHECK(E->ctx);
-            { ProfScope _ps(E->ctx, "fluid_integrate"); k_fl_integrate<R><<<gt, b, 0, s>>>(K, (const vec2_t<R> *)E->incr); }
+            { ProfScope _ps(E->ctx, "fluid_integrate"); k_fl_integrate<R><<<grid_tiles(E, k_fl_integrate<R>), b, 0, s>>>(K, (const vec2_t<R> *)E->incr); }
             OF2D_LAUNCH_CHECK(E->ctx);
             // regrid (ImageRegistrationFluid.cpp:108-124): level <- est + level o (id + est); est <- 0; re-warp; derivatives
-            k_e_untranspose<R><<<g, b, 0, s>>>(K, G_REGRID, B_EST_CUR, B_ESTN);
+            k_e_untranspose<R><<<grid_tiles(E, k_e_untranspose<R>), b, 0, s>>>(K, G_REGRID, B_EST_CUR, B_ESTN);
             OF2D_LAUNCH_CHECK(E->ctx);
-            { ProfScope _pc(E->ctx, "regrid_compose"); k_e_compose<R><<<g, b, 0, s>>>(K, G_REGRID, B_LVL_CUR, B_ESTN, B_LVL_NEXT, 0); }
+            { ProfScope _pc(E->ctx, "regrid_compose"); k_e_compose<R><<<grid_tiles(E, k_e_compose<R>), b, 0, s>>>(K, G_REGRID, B_LVL_CUR, B_ESTN, B_LVL_NEXT, 0); }
             OF2D_LAUNCH_CHECK(E->ctx);
             k_e_zero<R><<<dim3(ceil_div(E->ctx->sm_count * 2, K.batch), K.batch), 256, 0, s>>>(K, G_REGRID, B_EST_NEXT, 1);
             OF2D_LAUNCH_CHECK(E->ctx);
-            k_e_warp<R><<<g, b, 0, s>>>(K, G_REGRID, (const R *)E->cur_Imov, B_LVL_NEXT, (R *)E->aux);
+            k_e_warp<R><<<grid_tiles(E, k_e_warp<R>), b, 0, s>>>(K, G_REGRID, (const R *)E->cur_Imov, B_LVL_NEXT, (R *)E->aux);
             OF2D_LAUNCH_CHECK(E->ctx);
-            k_e_derivatives<R><<<g, b, 0, s>>>(K, G_REGRID, d_Iref, (const R *)E->aux, (vec2_t<R> *)E->gradI, (R *)E->It, 1);
+            k_e_derivatives<R><<<grid_tiles(E, k_e_derivatives<R>), b, 0, s>>>(K, G_REGRID, d_Iref, (const R *)E->aux, (vec2_t<R> *)E->gradI, (R *)E->It, 1);
             OF2D_LAUNCH_CHECK(E->ctx);
             k_regrid_commit<<<ceil_div(K.batch, 128), 128, 0, s>>>(K.ctl, K.batch);
             OF2D_LAUNCH_CHECK(E->ctx);
@@ -201,7 +214,7 @@ int refine_impl(of2d_engine *E, const R *d_Iref, const R *d_Imov, R *d_motion, i
     EngK<R> K = make_k<R>(E);
     K.ext = (vec2_t<R> *)d_motion;
     const of2d_engine_desc &d = E->d;
-    const dim3 g = grid_tiles(E), b(TX, TY);
+    const dim3 b(TX, TY);
     const size_t vbytes = sizeof(vec2_t<R>) * E->n * K.batch, vbytesT = sizeof(vec2_t<R>) * E->nT * K.batch;
     if (niter > E->tr.cap) { of2d_set_error("engine: niter %d above the trace capacity %d", niter, E->tr.cap); return OF2D_ERR_INVALID; }
     E->cur_Imov = d_Imov;
@@ -211,10 +224,10 @@ int refine_impl(of2d_engine *E, const R *d_Iref, const R *d_Imov, R *d_motion, i
     OF2D_CUDA_TRY(cudaMemcpyAsync(E->lvl[0], d_motion, vbytes, cudaMemcpyDeviceToDevice, s));
     k_ctl_begin<<<ceil_div(K.batch, 128), 128, 0, s>>>(K.ctl, K.batch, niter, K.n_active);
     OF2D_LAUNCH_CHECK(ctx);
-    k_e_warp<R><<<g, b, 0, s>>>(K, G_NONE, d_Imov, B_LVL_CUR, (R *)E->aux);
+    k_e_warp<R><<<grid_tiles(E, k_e_warp<R>), b, 0, s>>>(K, G_NONE, d_Imov, B_LVL_CUR, (R *)E->aux);
     OF2D_LAUNCH_CHECK(ctx);
     if (d.method != 3 && d.method != 4) {
-        k_e_derivatives<R><<<g, b, 0, s>>>(K, G_NONE, d_Iref, (const R *)E->aux, (vec2_t<R> *)E->gradI, (R *)E->It, E->transposed ? 1 : 0);
+        k_e_derivatives<R><<<grid_tiles(E, k_e_derivatives<R>), b, 0, s>>>(K, G_NONE, d_Iref, (const R *)E->aux, (vec2_t<R> *)E->gradI, (R *)E->It, E->transposed ? 1 : 0);
         OF2D_LAUNCH_CHECK(ctx);
     }
     const size_t eb = E->transposed ? vbytesT : vbytes;
@@ -245,11 +258,11 @@ int refine_impl(of2d_engine *E, const R *d_Iref, const R *d_Imov, R *d_motion, i
 
     // ---- tear-down: motion <- estimate + motion o (id + estimate); the estimate is dropped (:136-137)
     if (E->transposed) {
-        k_e_untranspose<R><<<g, b, 0, s>>>(K, G_NONE, B_EST_CUR, B_ESTN);
+        k_e_untranspose<R><<<grid_tiles(E, k_e_untranspose<R>), b, 0, s>>>(K, G_NONE, B_EST_CUR, B_ESTN);
         OF2D_LAUNCH_CHECK(ctx);
-        { ProfScope _pc(E->ctx, "final_compose"); k_e_compose<R><<<g, b, 0, s>>>(K, G_NONE, B_LVL_CUR, B_ESTN, B_EXT, 0); }
+        { ProfScope _pc(E->ctx, "final_compose"); k_e_compose<R><<<grid_tiles(E, k_e_compose<R>), b, 0, s>>>(K, G_NONE, B_LVL_CUR, B_ESTN, B_EXT, 0); }
     } else {
-        { ProfScope _pc(E->ctx, "final_compose"); k_e_compose<R><<<g, b, 0, s>>>(K, G_NONE, B_LVL_CUR, B_EST_CUR, B_EXT, 0); }
+        { ProfScope _pc(E->ctx, "final_compose"); k_e_compose<R><<<grid_tiles(E, k_e_compose<R>), b, 0, s>>>(K, G_NONE, B_LVL_CUR, B_EST_CUR, B_EXT, 0); }
     }
     OF2D_LAUNCH_CHECK(ctx);
     OF2D_CUDA_TRY(cudaMemcpyAsync(E->h_ctl.data(), E->d_ctl, sizeof(PairCtl) * K.batch, cudaMemcpyDeviceToHost, s));

@@ -88,6 +88,12 @@ __device__ __forceinline__ float norm_term_f(float2 v) { return sqrt_approx(v.x 
 __device__ __forceinline__ double norm_term(float2 v) { return (double)norm_term_f(v); }
 __device__ __forceinline__ double norm_term(double2 v) { return sqrt(v.x * v.x + v.y * v.y); }
 
+// packed fp32 pairs (sm_100a FFMA2 / FADD2): two lanes per issue slot, each lane IEEE round-to-nearest
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float2 unpack_f32x2(unsigned long long v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 // per-thread accumulation of the Logger terms: in the field precision within a tile, flushed into double per tile
 template <class R> struct NormAcc {
     R sd = 0, sp = 0;
@@ -181,8 +187,39 @@ __global__ void __launch_bounds__(TX *TY) k_hs_iter(EngK<R> K, const vec2_t<R> *
     NormAcc<R> acc;
     bool divzero = false;
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
-        const int i = T.tx(tile) * TILE + threadIdx.x;
-        const int jb = T.ty(tile) * TILE + threadIdx.y;
+        const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
+        if (i0 >= 1 && i0 + TILE < nx && j0 >= 1 && j0 + TILE < ny) {
+            // interior tile: no edge cases.  A thread owns 4 consecutive rows of one column, so the column of u it
+            // needs (rows j-1 .. j+4) is loaded once and every address is a row pointer plus an immediate offset.
+            const size_t idx0 = (size_t)(i0 + threadIdx.x) + (size_t)(j0 + 4 * threadIdx.y) * nx;
+            const vec2_t<R> *__restrict__ up = u + idx0;
+            vec2_t<R> ce[6], le[4], ri[4], dI[4];
+            R it[4];
+#pragma unroll
+            for (int r = 0; r < 6; r++) ce[r] = up[(ptrdiff_t)(r - 1) * nx];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                le[q] = up[(ptrdiff_t)q * nx - 1];
+                ri[q] = up[(ptrdiff_t)q * nx + 1];
+                dI[q] = gradI[idx0 + (size_t)q * nx];
+                it[q] = It[idx0 + (size_t)q * nx];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const vec2_t<R> qm = mk2<R>((((le[q].x + ri[q].x) + ce[q].x) + ce[q + 2].x) / (R)4.0f, (((le[q].y + ri[q].y) + ce[q].y) + ce[q + 2].y) / (R)4.0f);   // gradients.h:78
+                const vec2_t<R> f = lssd_force<R>(dI[q], it[q], qm);
+                const R den = alphasq + dI[q].x * dI[q].x + dI[q].y * dI[q].y;
+                vec2_t<R> o;
+                if (den == 0) { divzero = true; o = qm; }
+                else o = mk2<R>(qm.x - f.x / den, qm.y - f.y / den);
+                un[idx0 + (size_t)q * nx] = o;
+                acc.add(o, ce[q + 1]);
+            }
+            acc.flush();
+            continue;
+        }
+        const int i = i0 + threadIdx.x;
+        const int jb = j0 + threadIdx.y;
         // all loads of the thread's 4 pixels are issued before any arithmetic: indices are clamped into the
         // field so that they are unconditional (the clamped values are never used)
         const int ic = min(i, nx - 1);
@@ -389,6 +426,7 @@ struct ConvW {
     const double *taps_d;         // the same weights in double (renormalisation of truncated windows)
     double full_weight;           // sum over the visiting order
     int kw;
+    float neg_zero;               // -0.0f, opaque to the compiler (see the packed fast path of k_e_conv)
 };
 
 template <class R, int EPI, int KW>
@@ -474,20 +512,47 @@ __global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int d
                 for (int q = 0; q < 4; q++) prev[q] = est_cur[idx0 + (long)q * nx];
             }
             R ax[4], ay[4];
+            if constexpr (sizeof(R) == 4) {
+                // both components of a tap in one packed instruction: FFMA2 with the -0 addend rounds exactly like the
+                // reference's multiply (x*t + -0 == x*t, signed zeros included) and FADD2 is its add, so the result is
+                // still bit-identical while the issue slots per tap halve.  The addend comes from a kernel parameter:
+                // with a literal, ptxas folds the pair into one contracted FFMA2 even under -fmad=false.
+                const unsigned long long nz2 = pack_f32x2(W.neg_zero, W.neg_zero);
+                unsigned long long a2[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) { ax[q] = (R)0; ay[q] = (R)0; }
+                for (int q = 0; q < 4; q++) a2[q] = pack_f32x2(0.0f, 0.0f);
 #pragma unroll
-            for (int ii = 0; ii < KW; ii++) {
-                vec2_t<R> col[4 + (KW > 0 ? KW : 1) - 1];
+                for (int ii = 0; ii < KW; ii++) {
+                    unsigned long long col[4 + (KW > 0 ? KW : 1) - 1];
 #pragma unroll
-                for (int r = 0; r < 4 + KW - 1; r++) col[r] = tile_s[(jl0 + r) * SWp + threadIdx.x + ii];
+                    for (int r = 0; r < 4 + KW - 1; r++) { const float2 e = tile_s[(jl0 + r) * SWp + threadIdx.x + ii]; col[r] = pack_f32x2(e.x, e.y); }
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
+                    for (int q = 0; q < 4; q++) {
 #pragma unroll
-                    for (int jj = 0; jj < KW; jj++) {
-                        const R t = W.w[ii + jj * KW];
-                        ax[q] = ax[q] + col[q + jj].x * t;
-                        ay[q] = ay[q] + col[q + jj].y * t;
+                        for (int jj = 0; jj < KW; jj++) {
+                            const float t = W.w[ii + jj * KW];
+                            a2[q] = add_f32x2(a2[q], fma_f32x2(col[q + jj], pack_f32x2(t, t), nz2));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) { const float2 e = unpack_f32x2(a2[q]); ax[q] = e.x; ay[q] = e.y; }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++) { ax[q] = (R)0; ay[q] = (R)0; }
+#pragma unroll
+                for (int ii = 0; ii < KW; ii++) {
+                    vec2_t<R> col[4 + (KW > 0 ? KW : 1) - 1];
+#pragma unroll
+                    for (int r = 0; r < 4 + KW - 1; r++) col[r] = tile_s[(jl0 + r) * SWp + threadIdx.x + ii];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+#pragma unroll
+                        for (int jj = 0; jj < KW; jj++) {
+                            const R t = W.w[ii + jj * KW];
+                            ax[q] = ax[q] + col[q + jj].x * t;
+                            ay[q] = ay[q] + col[q + jj].y * t;
+                        }
                     }
                 }
             }
@@ -747,8 +812,45 @@ __global__ void __launch_bounds__(TX *TY) k_fl_integrate(EngK<R> K, const vec2_t
     NormAcc<R> acc;
     R mj = (R)INFINITY;
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
-        const int j = T.tx(tile) * TILE + threadIdx.x;
-        const int ib = T.ty(tile) * TILE + threadIdx.y;
+        const int j0 = T.tx(tile) * TILE, i0 = T.ty(tile) * TILE;
+        if (!skip && j0 >= 1 && j0 + TILE < ny && i0 >= 1 && i0 + TILE < nx) {
+            // interior tile: a thread owns 4 consecutive i of one j, so the new field along its line (i-1 .. i+4) is
+            // evaluated once; all differences are central.  Same expressions as the general path below.
+            const size_t o0 = (size_t)(i0 + 4 * threadIdx.y) * P + (size_t)(j0 + threadIdx.x);
+            const vec2_t<R> *__restrict__ up = u + o0;
+            const vec2_t<R> *__restrict__ rp = incr + o0;
+            vec2_t<R> ce[6], rc[6], le[4], rl[4], ri[4], rr[4], pv[4];
+#pragma unroll
+            for (int r = 0; r < 6; r++) { ce[r] = up[(ptrdiff_t)(r - 1) * P]; rc[r] = rp[(ptrdiff_t)(r - 1) * P]; }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                le[q] = up[(ptrdiff_t)q * P - 1]; rl[q] = rp[(ptrdiff_t)q * P - 1];
+                ri[q] = up[(ptrdiff_t)q * P + 1]; rr[q] = rp[(ptrdiff_t)q * P + 1];
+                pv[q] = ce[q + 1];
+            }
+            if (prev_other) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) pv[q] = un[o0 + (size_t)q * P];
+            }
+#pragma unroll
+            for (int r = 0; r < 6; r++) { ce[r].x += rc[r].x * dt; ce[r].y += rc[r].y * dt; }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                le[q].x += rl[q].x * dt; le[q].y += rl[q].y * dt;
+                ri[q].x += rr[q].x * dt; ri[q].y += rr[q].y * dt;
+                const vec2_t<R> nv = ce[q + 1];
+                acc.add(nv, pv[q]);
+                const vec2_t<R> dx = mk2<R>((ce[q + 2].x - ce[q].x) / (R)2.0f, (ce[q + 2].y - ce[q].y) / (R)2.0f);
+                const vec2_t<R> dy = mk2<R>((ri[q].x - le[q].x) / (R)2.0f, (ri[q].y - le[q].y) / (R)2.0f);
+                const R J = ((R)1.0f + dx.x) * ((R)1.0f + dy.y) - dx.y * dy.x;
+                mj = J < mj ? J : mj;
+                un[o0 + (size_t)q * P] = nv;
+            }
+            acc.flush();
+            continue;
+        }
+        const int j = j0 + threadIdx.x;
+        const int ib = i0 + threadIdx.y;
         if (j >= ny) continue;
 #pragma unroll
         for (int p = 0; p < PY; p++) {
