@@ -92,6 +92,45 @@ __device__ __forceinline__ vec2_t<R> compose_pixel(const vec2_t<R> *__restrict__
     return v;
 }
 
+// The same two operations with the four taps already in registers: the batched fast paths of the engine issue
+// every gather of a thread's pixels before any arithmetic (taps the reference does not read are loaded from a
+// clamped address and ignored), then evaluate the reference's expressions unchanged.
+template <class R>
+struct BilinTaps {
+    int o, ox, oy;   // clamped gather addresses: o, o + ox, o + oy, o + ox + oy
+};
+template <class R>
+__device__ __forceinline__ BilinTaps<R> bilin_taps(const Bilin<R> &b, int idx_self, int nx) {
+    BilinTaps<R> t;
+    t.o = b.inside ? b.idxO : idx_self;
+    t.ox = (b.inside && b.hx) ? 1 : 0;
+    t.oy = (b.inside && b.hy) ? nx : 0;
+    return t;
+}
+template <class R>
+__device__ __forceinline__ vec2_t<R> compose_taps(const Bilin<R> &b, vec2_t<R> s00, vec2_t<R> s10, vec2_t<R> s01, vec2_t<R> s11, vec2_t<R> v, vec2_t<R> keep) {
+    if (!b.inside) return keep;
+    const R one = (R)1;
+    R vx = s00.x * (one - b.fx) * (one - b.fy), vy = s00.y * (one - b.fx) * (one - b.fy);
+    R weight = (one - b.fx) * (one - b.fy);
+    if (b.hx) { vx += s10.x * b.fx * (one - b.fy); vy += s10.y * b.fx * (one - b.fy); weight += b.fx * (one - b.fy); }
+    if (b.hy) { vx += s01.x * (one - b.fx) * b.fy; vy += s01.y * (one - b.fx) * b.fy; weight += (one - b.fx) * b.fy; }
+    if (b.hx && b.hy) { vx += s11.x * b.fx * b.fy; vy += s11.y * b.fx * b.fy; weight += b.fx * b.fy; }
+    if (weight != 0) return mk2<R>(v.x + vx / weight, v.y + vy / weight);
+    return v;
+}
+template <class R>
+__device__ __forceinline__ R warp_taps(const Bilin<R> &b, R s00, R s10, R s01, R s11, R keep) {
+    if (!b.inside) return keep;
+    const R one = (R)1;
+    R val = s00 * (one - b.fx) * (one - b.fy);
+    R weight = (one - b.fx) * (one - b.fy);
+    if (b.hx) { val += s10 * b.fx * (one - b.fy); weight += b.fx * (one - b.fy); }
+    if (b.hy) { val += s01 * (one - b.fx) * b.fy; weight += (one - b.fx) * b.fy; }
+    if (b.hx && b.hy) { val += s11 * b.fx * b.fy; weight += b.fx * b.fy; }
+    return weight != 0 ? val / weight : keep;
+}
+
 // ---- reductions' per-pixel terms --------------------------------------------------------------------
 // Motion::norm addend, Motion.cpp:45: sqrt(pow(x,2)+pow(y,2)) evaluated in double
 template <class R>

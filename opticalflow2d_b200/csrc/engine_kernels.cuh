@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(TX *TY) k_e_warp(EngK<R> K, int gate, const R 
 
 // out = v + u o (id + v)   (Motion::accumulate, Motion.cpp:113-178); add_only: out = u + v (Field::operator+=)
 template <class R>
-__global__ void __launch_bounds__(TX *TY) k_e_compose(EngK<R> K, int gate, int u_buf, int v_buf, int out_buf, int add_only) {
+__global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 4 : 2) k_e_compose(EngK<R> K, int gate, int u_buf, int v_buf, int out_buf, int add_only) {
     const int pair = blockIdx.y;
     const CtlHot h = load_ctl(K.ctl + pair);
     if (!gate_open(h, gate)) return;
@@ -299,8 +299,33 @@ __global__ void __launch_bounds__(TX *TY) k_e_compose(EngK<R> K, int gate, int u
     vec2_t<R> *__restrict__ out = pick(K, out_buf, h, pair);
     const TileWalk T(nx, ny);
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
-        const int i = T.tx(tile) * TILE + threadIdx.x;
-        const int jb = T.ty(tile) * TILE + threadIdx.y;
+        const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
+        const int i = i0 + threadIdx.x;
+        const int jb = j0 + threadIdx.y;
+        if (i0 + TILE <= nx && j0 + TILE <= ny) {
+            // full tile: the loads of the thread's 4 pixels are batched (4 x {v, u}, then the 16 gathers), so a warp
+            // has up to 16 loads in flight instead of 2; same expressions as compose_pixel
+            vec2_t<R> vv[PY], uu[PY];
+#pragma unroll
+            for (int p = 0; p < PY; p++) { const int idx = i + (jb + p * TY) * nx; vv[p] = v[idx]; uu[p] = u[idx]; }
+            if (add_only) {
+#pragma unroll
+                for (int p = 0; p < PY; p++) out[i + (jb + p * TY) * nx] = mk2<R>(uu[p].x + vv[p].x, uu[p].y + vv[p].y);
+                continue;
+            }
+            Bilin<R> bl[PY];
+            vec2_t<R> s00[PY], s10[PY], s01[PY], s11[PY];
+#pragma unroll
+            for (int p = 0; p < PY; p++) {
+                const int j = jb + p * TY;
+                bl[p] = bilin_setup<R>(i, j, vv[p].x, vv[p].y, nx, ny);
+                const BilinTaps<R> t = bilin_taps<R>(bl[p], i + j * nx, nx);
+                s00[p] = u[t.o]; s10[p] = u[t.o + t.ox]; s01[p] = u[t.o + t.oy]; s11[p] = u[t.o + t.ox + t.oy];
+            }
+#pragma unroll
+            for (int p = 0; p < PY; p++) out[i + (jb + p * TY) * nx] = compose_taps<R>(bl[p], s00[p], s10[p], s01[p], s11[p], vv[p], uu[p]);
+            continue;
+        }
         if (i >= nx) continue;
 #pragma unroll
         for (int p = 0; p < PY; p++) {

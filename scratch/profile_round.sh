@@ -1,10 +1,17 @@
 #!/bin/bash
-# round profile: launch list of one bench step + full captures of the main kernels (2048^2 fp32)
+# round profile (2048^2 fp32): launch list of one bench step + one `ncu --set full` capture of each main kernel.
+# Reports are summarised ON the box (scratch/ncu_box.py) because gpurun returns at most 64 MiB.
+TAG=${1:-r1b}
 python bench.py --steps 1 --warmup 1 --quick > gpurun_out/quick_plain.log 2>&1 || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 1 --warmup 1 --quick > gpurun_out/quick_ncu.log 2>&1
-for spec in curvature:k_cf_cols:curv_cols curvature:k_cf_rows_fwd:curv_rows_fwd curvature:k_cf_rows_inv:curv_rows_inv thirion:k_e_demons_force:demons_force thirion:k_e_compose:compose fluid:k_fl_integrate:fluid_integrate fluid:k_fl_increment:fluid_increment fluid:k_sor_tile:sor_tile_fluid elastic:k_sor_tile:sor_tile_elastic diffusion:k_hs_iter:hs_iter; do
-  IFS=: read m k t <<< "$spec"
-  ncu --set full --clock-control none --import-source on -k regex:$k -s 10 -c 1 -f -o gpurun_out/r1_$t python bench.py --steps 1 --warmup 0 --quick --methods $m > gpurun_out/ncu_$t.log 2>&1 || echo "ncu $t failed"
-done
-ncu --set full --clock-control none --import-source on -k regex:k_e_conv -s 11 -c 1 -f -o gpurun_out/r1_conv_logger python bench.py --steps 1 --warmup 0 --quick --methods thirion > gpurun_out/ncu_conv.log 2>&1
-ls gpurun_out/r1_*.ncu-rep | wc -l
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 1 --quick > gpurun_out/quick_ncu.log 2>&1
+cap() {  # method(s) kernel-regex skip count name
+  ncu --set full --clock-control none -k "regex:$2" -s $3 -c $4 -f -o gpurun_out/$5 python bench.py --steps 1 --warmup 0 --quick --methods $1 > gpurun_out/ncu_$5.log 2>&1 || echo "ncu $5 failed"
+}
+cap thirion 'k_e_(demons_force|conv|compose)' 40 4 thirion
+cap diffeomorphic 'k_e_(conv|square)' 61 3 diffeo          # conv_maxabs + the first squarings of an iteration
+cap fluid 'k_fl_|k_sor_tile' 30 3 fluid
+cap curvature 'k_rg_' 30 3 curvature
+cap diffusion 'k_hs_iter' 10 1 diffusion
+cap elastic 'k_sor_tile' 10 1 elastic
+python scratch/ncu_box.py $TAG 30
+ls -la gpurun_out/summ | head -40
