@@ -144,6 +144,13 @@ __device__ __forceinline__ R maxabs_term(vec2_t<R> v) {
     const double y = (double)v.y;
     return (R)(y * y + y * y);
 }
+// float data: y*y is exact in double (48 bits) and so is its doubling, so the one rounding to float is RN(2 y^2) = 2 RN(y^2):
+// the same bits from two float instructions (no double pipe)
+template <>
+__device__ __forceinline__ float maxabs_term<float>(float2 v) {
+    const float t = v.y * v.y;
+    return t + t;
+}
 
 // ---- OpticalFlow::get_force, OpticalFlow.cpp:33 -------------------------------------------------------
 template <class R>

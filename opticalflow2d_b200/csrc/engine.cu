@@ -179,9 +179,8 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
         }
         case 5: {
             TRY(sor_tile_launch<R>(E->ctx, E->sor, K.ctl, K.n_active, K.partials, K.pstride, K.tr, 1, (vec2_t<R> *)E->vel[0], (vec2_t<R> *)E->vel[1],
-                                   (const vec2_t<R> *)E->est[0], (const vec2_t<R> *)E->est[1], (const vec2_t<R> *)E->gradI, (const R *)E->It));
-            { ProfScope _ps(E->ctx, "fluid_increment"); k_fl_increment<R><<<grid_tiles(E, k_fl_increment<R>), b, 0, s>>>(K, (vec2_t<R> *)E->vel[0], (vec2_t<R> *)E->vel[1], (vec2_t<R> *)E->incr); }
-            OF2D_LAUNCH_CHECK(E->ctx);
+                                   (const vec2_t<R> *)E->est[0], (const vec2_t<R> *)E->est[1], (const vec2_t<R> *)E->gradI, (const R *)E->It, (vec2_t<R> *)E->incr));
+            // (the increment of the new velocity and the time step are produced by the sweep kernel itself)
             { ProfScope _ps(E->ctx, "fluid_integrate"); k_fl_integrate<R><<<grid_tiles(E, k_fl_integrate<R>), b, 0, s>>>(K, (const vec2_t<R> *)E->incr); }
             OF2D_LAUNCH_CHECK(E->ctx);
             // regrid (ImageRegistrationFluid.cpp:108-124): level <- est + level o (id + est); est <- 0; re-warp; derivatives

@@ -747,71 +747,7 @@ __global__ void k_e_zero(EngK<R> K, int gate, int buf, int transposed) {
 // ---------------------------------------------------------------------------------------------
 // Fluid in the transposed layout (element (i,j) at i*P + j; threadIdx.x runs along j)
 // ---------------------------------------------------------------------------------------------
-template <class R>
-__device__ __forceinline__ vec2_t<R> tdx(const vec2_t<R> *__restrict__ f, size_t o, int i, int nx, int P) {   // d/dx, gradients.h:9-19
-    if (i == 0) { const vec2_t<R> a = f[o + P], b = f[o]; return mk2<R>(a.x - b.x, a.y - b.y); }
-    if (i == nx - 1) { const vec2_t<R> a = f[o], b = f[o - P]; return mk2<R>(a.x - b.x, a.y - b.y); }
-    const vec2_t<R> a = f[o + P], b = f[o - P];
-    return mk2<R>((a.x - b.x) / (R)2.0f, (a.y - b.y) / (R)2.0f);
-}
-template <class R>
-__device__ __forceinline__ vec2_t<R> tdy(const vec2_t<R> *__restrict__ f, size_t o, int j, int ny) {          // d/dy, gradients.h:22-32
-    if (j == 0) { const vec2_t<R> a = f[o + 1], b = f[o]; return mk2<R>(a.x - b.x, a.y - b.y); }
-    if (j == ny - 1) { const vec2_t<R> a = f[o], b = f[o - 1]; return mk2<R>(a.x - b.x, a.y - b.y); }
-    const vec2_t<R> a = f[o + 1], b = f[o - 1];
-    return mk2<R>((a.x - b.x) / (R)2.0f, (a.y - b.y) / (R)2.0f);
-}
-
-// increment R = v - du/dx v.x - du/dy v.y (OpticalFlowFluid.cpp:60-90) + time step (:92-95, :135-137)
-template <class R>
-__global__ void __launch_bounds__(TX *TY) k_fl_increment(EngK<R> K, vec2_t<R> *const vel0, vec2_t<R> *const vel1, vec2_t<R> *__restrict__ incr_all) {
-    const int pair = blockIdx.y;
-    PairCtl *c = K.ctl + pair;
-    const CtlHot h = load_ctl(c);
-    if (!h.active) return;
-    const int nx = K.nx, ny = K.ny, P = K.P;
-    const vec2_t<R> *__restrict__ u = pick(K, B_EST_CUR, h, pair, true);
-    const vec2_t<R> *__restrict__ vel = (h.vsel ? vel0 : vel1) + (size_t)pair * K.nT;   // the buffer the sweep just wrote
-    vec2_t<R> *__restrict__ incr = incr_all + (size_t)pair * K.nT;
-    const TileWalk T(ny, nx);
-    R m = (R)0;
-    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
-        const int j = T.tx(tile) * TILE + threadIdx.x;
-        const int ib = T.ty(tile) * TILE + threadIdx.y;
-        if (j >= ny) continue;
-#pragma unroll
-        for (int p = 0; p < PY; p++) {
-            const int i = ib + p * TY;
-            if (i < nx) {
-                const size_t o = (size_t)i * P + j;
-                const vec2_t<R> v = vel[o];
-                const vec2_t<R> dudx = tdx<R>(u, o, i, nx, P);
-                const vec2_t<R> dudy = tdy<R>(u, o, j, ny);
-                const vec2_t<R> r = mk2<R>(v.x - dudx.x * v.x - dudy.x * v.y, v.y - dudx.y * v.x - dudy.y * v.y);
-                incr[o] = r;
-                const R s = maxabs_term<R>(r);
-                m = m < s ? s : m;
-            }
-        }
-    }
-    m = block_extreme<R, true>(m);
-    const double vals[1] = {(double)m};
-    double *part = K.partials + (size_t)pair * K.pstride;
-    if (publish_partials<1>(vals, part, &c->ticket[1], gridDim.x, blockIdx.x)) {
-        double o1[1];
-        reduce_partials<1>(part, gridDim.x, o1, 1u, 0u);
-        if (threadIdx.x == 0 && threadIdx.y == 0) {
-            const R maxabs = sizeof(R) == 4 ? (R)sqrtf((float)o1[0]) : (R)sqrt(o1[0]);   // Motion.cpp:57
-            const R dt = (R)0.65f / maxabs;                                              // OpticalFlowFluid.h:32, .cpp:93
-            c->maxabs = (double)maxabs;
-            c->dt = (double)dt;
-            c->skip = dt >= (R)65.0f;                                                    // .cpp:135-137
-            c->vsel ^= 1;
-            const int it = c->iter;
-            if (it < K.tr.cap) { K.tr.maxabs[(size_t)pair * K.tr.cap + it] = (double)maxabs; K.tr.dt[(size_t)pair * K.tr.cap + it] = (double)dt; }
-        }
-    }
-}
+// (the increment R = v - du/dx v.x - du/dy v.y and the time step, OpticalFlowFluid.cpp:60-95, are produced by the sweep kernel: sor_tile.cuh)
 
 // integrate u += dt R (OpticalFlowFluid.cpp:97-121) + Logger + Jacobian minimum of the new field
 // (Image.cpp:189-218, :96-104) + break / regrid decisions (ImageRegistrationFluid.cpp:99-124)
@@ -828,6 +764,7 @@ __global__ void __launch_bounds__(TX *TY) k_fl_integrate(EngK<R> K, const vec2_t
     const bool skip = h.skip != 0;
     const bool prev_other = h.prev_other != 0;
     const R dt = (R)__ldcg(&c->dt);
+    __shared__ vec2_t<R> s_new[(TILE + 2) * (TILE + 2)], s_old[(TILE + 2) * (TILE + 2)];   // halo tile of an interior tile: new and old field
     auto unew_at = [&](size_t o) -> vec2_t<R> {
         vec2_t<R> v = u[o];
         if (!skip) { const vec2_t<R> r = incr[o]; v.x += r.x * dt; v.y += r.y * dt; }
@@ -839,30 +776,46 @@ __global__ void __launch_bounds__(TX *TY) k_fl_integrate(EngK<R> K, const vec2_t
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
         const int j0 = T.tx(tile) * TILE, i0 = T.ty(tile) * TILE;
         if (!skip && j0 >= 1 && j0 + TILE < ny && i0 >= 1 && i0 + TILE < nx) {
-            // interior tile: a thread owns 4 consecutive i of one j, so the new field along its line (i-1 .. i+4) is
-            // evaluated once; all differences are central.  Same expressions as the general path below.
-            const size_t o0 = (size_t)(i0 + 4 * threadIdx.y) * P + (size_t)(j0 + threadIdx.x);
-            const vec2_t<R> *__restrict__ up = u + o0;
-            const vec2_t<R> *__restrict__ rp = incr + o0;
-            vec2_t<R> ce[6], rc[6], le[4], rl[4], ri[4], rr[4], pv[4];
+            // interior tile, two phases.  (1) The CTA evaluates the NEW field once per point of the 34 x 34 halo tile
+            // (coalesced loads of u and of the increment, all of a thread's loads issued before the arithmetic) into
+            // shared memory, next to the old values.  (2) A thread owns 4 consecutive i of one j and reads its line
+            // i-1 .. i+4 and its j-1 / j+1 neighbours from shared memory; all differences are central.  Same
+            // expressions as the general path below.
+            constexpr int HT = TILE + 2, NE = HT * HT, NR = (NE + TX * TY - 1) / (TX * TY);
+            const int tid = threadIdx.x + threadIdx.y * TX;
+            __syncthreads();   // the previous tile's phase 2 is over
+            {
+                vec2_t<R> uo[NR], rr[NR];
 #pragma unroll
-            for (int r = 0; r < 6; r++) { ce[r] = up[(ptrdiff_t)(r - 1) * P]; rc[r] = rp[(ptrdiff_t)(r - 1) * P]; }
+                for (int k = 0; k < NR; k++) {
+                    const int e = min(tid + k * TX * TY, NE - 1);
+                    const int r = e / HT, cc = e - r * HT;
+                    const size_t o = (size_t)(i0 - 1 + r) * P + (size_t)(j0 - 1 + cc);
+                    uo[k] = u[o]; rr[k] = incr[o];
+                }
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                le[q] = up[(ptrdiff_t)q * P - 1]; rl[q] = rp[(ptrdiff_t)q * P - 1];
-                ri[q] = up[(ptrdiff_t)q * P + 1]; rr[q] = rp[(ptrdiff_t)q * P + 1];
-                pv[q] = ce[q + 1];
+                for (int k = 0; k < NR; k++) {
+                    const int e = tid + k * TX * TY;
+                    if (e < NE) {
+                        s_old[e] = uo[k];
+                        s_new[e] = mk2<R>(uo[k].x + rr[k].x * dt, uo[k].y + rr[k].y * dt);
+                    }
+                }
             }
+            __syncthreads();
+            const size_t o0 = (size_t)(i0 + 4 * threadIdx.y) * P + (size_t)(j0 + threadIdx.x);
+            const int sb = (4 * threadIdx.y) * HT + threadIdx.x + 1;   // (line i-1 of the thread, its own j) in the halo tile
+            vec2_t<R> ce[6], le[4], ri[4], pv[4];
+#pragma unroll
+            for (int r = 0; r < 6; r++) ce[r] = s_new[sb + r * HT];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { le[q] = s_new[sb + (q + 1) * HT - 1]; ri[q] = s_new[sb + (q + 1) * HT + 1]; pv[q] = s_old[sb + (q + 1) * HT]; }
             if (prev_other) {
 #pragma unroll
                 for (int q = 0; q < 4; q++) pv[q] = un[o0 + (size_t)q * P];
             }
 #pragma unroll
-            for (int r = 0; r < 6; r++) { ce[r].x += rc[r].x * dt; ce[r].y += rc[r].y * dt; }
-#pragma unroll
             for (int q = 0; q < 4; q++) {
-                le[q].x += rl[q].x * dt; le[q].y += rl[q].y * dt;
-                ri[q].x += rr[q].x * dt; ri[q].y += rr[q].y * dt;
                 const vec2_t<R> nv = ce[q + 1];
                 acc.add(nv, pv[q]);
                 const vec2_t<R> dx = mk2<R>((ce[q + 2].x - ce[q].x) / (R)2.0f, (ce[q + 2].y - ce[q].y) / (R)2.0f);

@@ -56,6 +56,7 @@ struct SorTileArgs {
     int which;                     // 0: x = estimate (sel, Logger epilogue); 1: x = velocity (vsel)
     vec2_t<R> *x[2];
     const vec2_t<R> *uf[2];        // fluid: the estimate the force is evaluated on (picked by sel)
+    vec2_t<R> *incr;               // fluid: the increment R = v - du/dx v.x - du/dy v.y of the new velocity (OpticalFlowFluid.cpp:60-90), written here
     const vec2_t<R> *gradI;
     const R *It;
     R ck, cr, mu, mupl, a;
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
     const V *__restrict__ ufp = FLUID ? A.uf[__ldcg(&c->sel)] + (size_t)pair * A.nT : nullptr;
     const V *__restrict__ gp = A.gradI + (size_t)pair * A.nT;
     const R *__restrict__ tp = A.It + (size_t)pair * A.nT;
+    V *__restrict__ incr = FLUID ? A.incr + (size_t)pair * A.nT : nullptr;
 
     // stage layout: [x LR + 4 (2 pad elements in front)][gradI LR][uf LR (fluid)][It LR]; row r of the tile at index r
     const size_t x_bytes = (size_t)(LR + 4) * sizeof(V);
@@ -143,6 +145,14 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
 #pragma unroll
         for (int r = 0; r < RPT + 2; r++) { newW[r] = x0[r0 - 1 + r]; oldC[r] = x1[r0 - 1 + r]; }
     }
+    // fluid: the estimate u on the thread's rows of the column to the west (for du/dx of the fused increment)
+    V uW[RPT];
+    R mxr = (R)0;
+    if (FLUID) {
+        const V *u0 = st_u(0);
+#pragma unroll
+        for (int r = 0; r < RPT; r++) uW[r] = u0[r0 + r];
+    }
 
     // carry = sum_q cq[q] top[t-q]: the new value of the row below the thread's block from the zero-carry tops of the
     // threads below (coefficients a^(RPT (q-1)) while those threads are fully computed blocks; constant over columns)
@@ -183,17 +193,20 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
         }
         // everything of the reference's expression that does not involve the cell below (S):
         //   o = ck C + cr (b - mu (((E + W) + N) + S) - mupl (E + W + 0.25 (NE' - NW' - SE' + SW')))
-        V ckC[RPT], bb[RPT], sum3[RPT], k2[RPT], d[RPT], xt[RPT];
+        V ckC[RPT], bb[RPT], sum3[RPT], k2[RPT], d[RPT], xt[RPT], uC[RPT];
+        V uS = mk2<R>((R)0, (R)0), uN = uS;   // fluid: u on the rows below / above the thread's block, this column (read before the stage is refilled)
         {
             const V *gs = st_g(sC);
             const R *ts = st_t(sC);
             const V *us = st_u(sC);
+            if (FLUID && i >= is) { uS = us[r0 - 1]; uN = us[r0 + RPT]; }
 #pragma unroll
             for (int r = 0; r < RPT; r++) {
                 const V Cc = oldC[r + 1], N = oldC[r + 2];
                 const V W = newW[r + 1], SW = newW[r], NW = newW[r + 2];
                 const V E = oldE[r + 1], SE = oldE[r], NE = oldE[r + 2];
-                bb[r] = lssd_force<R>(gs[r0 + r], ts[r0 + r], FLUID ? us[r0 + r] : Cc);
+                uC[r] = FLUID ? us[r0 + r] : Cc;
+                bb[r] = lssd_force<R>(gs[r0 + r], ts[r0 + r], uC[r]);
                 const R ewx = E.x + W.x, ewy = E.y + W.y;
                 sum3[r] = mk2<R>(ewx + N.x, ewy + N.y);
                 k2[r] = mk2<R>(ewx + (R)0.25f * (NE.y - NW.y - SE.y + SW.y), ewy + (R)0.25f * (NE.x - NW.x - SE.x + SW.x));
@@ -265,11 +278,30 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
         if (t + 1 < NT) ntop = above_comp ? mk2<R>(a * xn[RPT - 1].x + d0_above.x, a * xn[RPT - 1].y + d0_above.y) : d0_above;
         else ntop = oldC[RPT + 1];
         if (i >= is) {
+            V uE[RPT];
+            if (FLUID) {   // u on the thread's rows of the column to the east (its stage is refilled one step from now)
+                const V *ue = st_u(sE);
+#pragma unroll
+                for (int r = 0; r < RPT; r++) uE[r] = ue[r0 + r];
+            }
 #pragma unroll
             for (int r = 0; r < RPT; r++) {
                 const int j = j0 + r;
                 if (own[r]) {
                     xout[(size_t)i * P + j] = xn[r];
+                    if (FLUID) {
+                        // the increment of the NEW velocity, OpticalFlowFluid.cpp:60-90 (own cells are interior: central differences,
+                        // gradients.h:9-32); border cells keep the 0 the buffer was created with (their velocity is never updated)
+                        const V a = uE[r], b = uW[r];
+                        const V dudx = mk2<R>((a.x - b.x) / (R)2.0f, (a.y - b.y) / (R)2.0f);
+                        const V nn = r + 1 < RPT ? uC[r + 1 < RPT ? r + 1 : r] : uN, ss = r > 0 ? uC[r > 0 ? r - 1 : 0] : uS;
+                        const V dudy = mk2<R>((nn.x - ss.x) / (R)2.0f, (nn.y - ss.y) / (R)2.0f);
+                        const V v = xn[r];
+                        const V rr = mk2<R>(v.x - dudx.x * v.x - dudy.x * v.y, v.y - dudx.y * v.x - dudy.y * v.y);
+                        incr[(size_t)i * P + j] = rr;
+                        const R sm = maxabs_term<R>(rr);
+                        mxr = mxr < sm ? sm : mxr;
+                    }
                     if (!FLUID) {
                         const V oc = oldC[r + 1];
                         const R dx = xn[r].x - oc.x, dy = xn[r].y - oc.y;
@@ -280,6 +312,10 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
             }
             if (sizeof(R) == 4 && !FLUID && (k & 15) == 0) { sdd += (double)sdf; spd += (double)spf; sdf = 0.0f; spf = 0.0f; }
         }
+        if (FLUID) {
+#pragma unroll
+            for (int r = 0; r < RPT; r++) uW[r] = uC[r];
+        }
         newW[0] = carry;
 #pragma unroll
         for (int r = 0; r < RPT; r++) newW[r + 1] = xn[r];
@@ -288,7 +324,28 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
         for (int r = 0; r < RPT + 2; r++) oldC[r] = oldE[r];
     }
 
-    if (FLUID) return;
+    if (FLUID) {
+        // time step from the maximum of the increment (OpticalFlowFluid.cpp:92-95, :135-137; Motion.cpp:51-58), taken by the last CTA
+        mxr = block_extreme<R, true>(mxr);
+        const double vals[1] = {(double)mxr};
+        const int nblocks = gridDim.x * gridDim.y, bid = blockIdx.x + blockIdx.y * gridDim.x;
+        double *part = A.partials + (size_t)pair * A.pstride;
+        if (publish_partials<1>(vals, part, &c->ticket[1], nblocks, bid)) {
+            double o1[1];
+            reduce_partials<1>(part, nblocks, o1, 1u, 0u);
+            if (t == 0) {
+                const R maxabs = sizeof(R) == 4 ? (R)sqrtf((float)o1[0]) : (R)sqrt(o1[0]);   // Motion.cpp:57
+                const R dt = (R)0.65f / maxabs;                                              // OpticalFlowFluid.h:32, .cpp:93
+                c->maxabs = (double)maxabs;
+                c->dt = (double)dt;
+                c->skip = dt >= (R)65.0f;                                                    // .cpp:135-137
+                c->vsel ^= 1;
+                const int it = c->iter;
+                if (it < A.tr.cap) { A.tr.maxabs[(size_t)pair * A.tr.cap + it] = (double)maxabs; A.tr.dt[(size_t)pair * A.tr.cap + it] = (double)dt; }
+            }
+        }
+        return;
+    }
     double sd = sdd + (double)sdf, sp = spd + (double)spf;
     block_sum2(sd, sp);
     const double vals[2] = {sd, sp};
@@ -349,13 +406,13 @@ static inline SorPlan sor_plan(int nx, int ny, int batch, double mu, double lamb
 
 template <class R>
 static int sor_tile_launch(of2d_ctx *ctx, const SorPlan &S, PairCtl *ctl, int *n_active, double *partials, size_t pstride, const TraceDev &tr, int which,
-                           vec2_t<R> *x0, vec2_t<R> *x1, const vec2_t<R> *uf0, const vec2_t<R> *uf1, const vec2_t<R> *gradI, const R *It) {
+                           vec2_t<R> *x0, vec2_t<R> *x1, const vec2_t<R> *uf0, const vec2_t<R> *uf1, const vec2_t<R> *gradI, const R *It, vec2_t<R> *incr = nullptr) {
     SorTileArgs<R> A;
     A.nx = S.nx; A.ny = S.ny; A.P = S.P; A.nT = S.nT; A.n = (size_t)S.nx * S.ny;
     A.BX = S.BX; A.BY = S.BY; A.HW = S.HW; A.HS = S.HS; A.HN = S.HN; A.M = S.M;
     A.LR = S.NT * S.RPT + 8;
     A.which = which;
-    A.x[0] = x0; A.x[1] = x1; A.uf[0] = uf0; A.uf[1] = uf1; A.gradI = gradI; A.It = It;
+    A.x[0] = x0; A.x[1] = x1; A.uf[0] = uf0; A.uf[1] = uf1; A.gradI = gradI; A.It = It; A.incr = incr;
     A.ck = (R)S.c_keep; A.cr = (R)S.c_relax; A.mu = (R)S.mu; A.mupl = (R)S.mupl;
     A.a = (R)(-S.c_relax * S.mu);
     A.ctl = ctl; A.n_active = n_active; A.partials = partials; A.pstride = pstride; A.tr = tr;
