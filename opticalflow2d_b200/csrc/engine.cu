@@ -37,7 +37,7 @@ struct of2d_engine {
     int P;
     size_t n, nT, elem;          // elem = sizeof(real)
     // device buffers (real-typed; vec2 fields have 2*elem per element)
-    void *aux, *gradI, *It, *est[2], *c[2], *lvl[2], *estN, *vel[2], *incr;
+    void *aux, *gradI, *It, *est[2], *c[2], *lvl[2], *vel[2], *incr;
     PairCtl *d_ctl;
     int *d_nactive;
     double *d_partials;
@@ -69,7 +69,6 @@ EngK<R> make_k(of2d_engine *E) {
     K.n = E->n; K.nT = E->nT;
     K.ctl = E->d_ctl; K.n_active = E->d_nactive; K.partials = E->d_partials; K.pstride = E->pstride; K.tr = E->tr;
     for (int k = 0; k < 2; k++) { K.est[k] = (vec2_t<R> *)E->est[k]; K.c[k] = (vec2_t<R> *)E->c[k]; K.lvl[k] = (vec2_t<R> *)E->lvl[k]; }
-    K.estN = (vec2_t<R> *)E->estN;
     K.ext = nullptr;
     return K;
 }
@@ -162,7 +161,7 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
             OF2D_LAUNCH_CHECK(E->ctx);
             if (d.method == 3) {
                 TRY((launch_conv<R, 0>(E, K, B_C0, B_C1, 0)));
-                { ProfScope _pc(E->ctx, "compose"); k_e_compose<R><<<grid_tiles(E, k_e_compose<R>), b, 0, s>>>(K, G_ACTIVE, B_EST_CUR, B_C1, B_C0, d.accumulation == 1); }
+                { ProfScope _pc(E->ctx, "compose"); k_e_compose<R, false><<<grid_tiles(E, k_e_compose<R, false>), b, 0, s>>>(K, G_ACTIVE, B_EST_CUR, B_C1, B_C0, d.accumulation == 1); }
                 OF2D_LAUNCH_CHECK(E->ctx);
                 TRY((launch_conv<R, 1>(E, K, B_C0, B_EST_NEXT, 1)));
             } else {
@@ -171,7 +170,7 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
                     { ProfScope _ps(E->ctx, "square"); k_e_square<R><<<grid_tiles(E, k_e_square<R>), b, 0, s>>>(K, q); }
                     OF2D_LAUNCH_CHECK(E->ctx);
                 }
-                { ProfScope _pc(E->ctx, "compose"); k_e_compose<R><<<grid_tiles(E, k_e_compose<R>), b, 0, s>>>(K, G_ACTIVE, B_EST_CUR, B_CRES, B_CTMP, 0); }
+                { ProfScope _pc(E->ctx, "compose"); k_e_compose<R, false><<<grid_tiles(E, k_e_compose<R, false>), b, 0, s>>>(K, G_ACTIVE, B_EST_CUR, B_CRES, B_CTMP, 0); }
                 OF2D_LAUNCH_CHECK(E->ctx);
                 TRY((launch_conv<R, 1>(E, K, B_CTMP, B_EST_NEXT, 1)));
             }
@@ -184,15 +183,9 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
             { ProfScope _ps(E->ctx, "fluid_integrate"); k_fl_integrate<R><<<grid_tiles(E, k_fl_integrate<R>), b, 0, s>>>(K, (const vec2_t<R> *)E->incr); }
             OF2D_LAUNCH_CHECK(E->ctx);
             // regrid (ImageRegistrationFluid.cpp:108-124): level <- est + level o (id + est); est <- 0; re-warp; derivatives
-            k_e_untranspose<R><<<grid_tiles(E, k_e_untranspose<R>), b, 0, s>>>(K, G_REGRID, B_EST_CUR, B_ESTN);
+            { ProfScope _pc(E->ctx, "regrid_compose"); k_e_compose<R, true><<<grid_tiles(E, k_e_compose<R, true>), b, 0, s>>>(K, G_REGRID, B_LVL_CUR, B_EST_CUR, B_LVL_NEXT, 0); }
             OF2D_LAUNCH_CHECK(E->ctx);
-            { ProfScope _pc(E->ctx, "regrid_compose"); k_e_compose<R><<<grid_tiles(E, k_e_compose<R>), b, 0, s>>>(K, G_REGRID, B_LVL_CUR, B_ESTN, B_LVL_NEXT, 0); }
-            OF2D_LAUNCH_CHECK(E->ctx);
-            k_e_zero<R><<<dim3(ceil_div(E->ctx->sm_count * 2, K.batch), K.batch), 256, 0, s>>>(K, G_REGRID, B_EST_NEXT, 1);
-            OF2D_LAUNCH_CHECK(E->ctx);
-            k_e_warp<R><<<grid_tiles(E, k_e_warp<R>), b, 0, s>>>(K, G_REGRID, (const R *)E->cur_Imov, B_LVL_NEXT, (R *)E->aux);
-            OF2D_LAUNCH_CHECK(E->ctx);
-            k_e_derivatives<R><<<grid_tiles(E, k_e_derivatives<R>), b, 0, s>>>(K, G_REGRID, d_Iref, (const R *)E->aux, (vec2_t<R> *)E->gradI, (R *)E->It, 1);
+            { ProfScope _pw(E->ctx, "regrid_rewarp"); k_fl_rewarp<R><<<grid_tiles(E, k_fl_rewarp<R>), b, 0, s>>>(K, G_REGRID, d_Iref, (const R *)E->cur_Imov, B_LVL_NEXT, (vec2_t<R> *)E->gradI, (R *)E->It, B_EST_NEXT); }
             OF2D_LAUNCH_CHECK(E->ctx);
             k_regrid_commit<<<ceil_div(K.batch, 128), 128, 0, s>>>(K.ctl, K.batch);
             OF2D_LAUNCH_CHECK(E->ctx);
@@ -256,12 +249,10 @@ int refine_impl(of2d_engine *E, const R *d_Iref, const R *d_Imov, R *d_motion, i
     }
 
     // ---- tear-down: motion <- estimate + motion o (id + estimate); the estimate is dropped (:136-137)
-    if (E->transposed) {
-        k_e_untranspose<R><<<grid_tiles(E, k_e_untranspose<R>), b, 0, s>>>(K, G_NONE, B_EST_CUR, B_ESTN);
-        OF2D_LAUNCH_CHECK(ctx);
-        { ProfScope _pc(E->ctx, "final_compose"); k_e_compose<R><<<grid_tiles(E, k_e_compose<R>), b, 0, s>>>(K, G_NONE, B_LVL_CUR, B_ESTN, B_EXT, 0); }
+    if (E->transposed) {   // the estimate lives in the transposed working layout: its tiles are turned in shared memory
+        { ProfScope _pc(E->ctx, "final_compose"); k_e_compose<R, true><<<grid_tiles(E, k_e_compose<R, true>), b, 0, s>>>(K, G_NONE, B_LVL_CUR, B_EST_CUR, B_EXT, 0); }
     } else {
-        { ProfScope _pc(E->ctx, "final_compose"); k_e_compose<R><<<grid_tiles(E, k_e_compose<R>), b, 0, s>>>(K, G_NONE, B_LVL_CUR, B_EST_CUR, B_EXT, 0); }
+        { ProfScope _pc(E->ctx, "final_compose"); k_e_compose<R, false><<<grid_tiles(E, k_e_compose<R, false>), b, 0, s>>>(K, G_NONE, B_LVL_CUR, B_EST_CUR, B_EXT, 0); }
     }
     OF2D_LAUNCH_CHECK(ctx);
     OF2D_CUDA_TRY(cudaMemcpyAsync(E->h_ctl.data(), E->d_ctl, sizeof(PairCtl) * K.batch, cudaMemcpyDeviceToHost, s));
@@ -326,7 +317,7 @@ int of2d_engine_create(of2d_ctx *ctx, const of2d_engine_desc *desc, of2d_engine 
     int st = OF2D_SUCCESS;
     auto fail = [&](int code) { of2d_engine_destroy(E); return code; };
     if (E->transposed) {
-        E->sor = sor_plan(nx, ny, B, desc->mu, desc->lambda, desc->omega, E->dbl);
+        E->sor = sor_plan(nx, ny, B, desc->mu, desc->lambda, desc->omega, E->dbl, m == 5);
         if (!E->sor.supported) {
             of2d_set_error("engine: SOR parameters (mu %g, lambda %g, omega %g) do not contract fast enough for the tiled sweep", desc->mu, desc->lambda, desc->omega);
             return fail(OF2D_ERR_UNSUPPORTED);
@@ -350,7 +341,6 @@ int of2d_engine_create(of2d_ctx *ctx, const of2d_engine_desc *desc, of2d_engine 
     if (m == 3 || m == 4) {
         for (int k = 0; k < 2; k++) if ((st = alloc(&E->c[k], v * nN))) return fail(st);
     }
-    if (E->transposed || m == 0 || m == 1) { if ((st = alloc(&E->estN, v * nN))) return fail(st); }
     if (m == 5) {
         for (int k = 0; k < 2; k++) if ((st = alloc(&E->vel[k], v * nTt))) return fail(st);
         if ((st = alloc(&E->incr, v * nTt))) return fail(st);
@@ -406,7 +396,7 @@ void of2d_engine_destroy(of2d_engine *E) {
     if (!E) return;
     cudaSetDevice(E->ctx->device);
     cudaStreamSynchronize(E->ctx->stream);
-    void *bufs[] = {E->aux, E->gradI, E->It, E->est[0], E->est[1], E->c[0], E->c[1], E->lvl[0], E->lvl[1], E->estN, E->vel[0], E->vel[1], E->incr,
+    void *bufs[] = {E->aux, E->gradI, E->It, E->est[0], E->est[1], E->c[0], E->c[1], E->lvl[0], E->lvl[1], E->vel[0], E->vel[1], E->incr,
                     E->d_ctl, E->d_nactive, E->d_partials, E->tr.err, E->tr.maxabs, E->tr.dt, E->tr.minjac, E->tr.regrid, E->tr.nsq, E->d_taps[0], E->d_taps[1]};
     for (void *p : bufs) if (p) cudaFree(p);
     if (E->plan) of2d_curvature_plan_destroy(E->plan);

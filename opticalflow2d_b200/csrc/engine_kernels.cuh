@@ -18,7 +18,7 @@ namespace {
 constexpr int TX = 32, TY = 8, PY = 4;
 constexpr int TILE = 32;
 
-enum Buf { B_C0 = 0, B_C1 = 1, B_EST_CUR = 2, B_EST_NEXT = 3, B_CRES = 4, B_CTMP = 5, B_LVL_CUR = 6, B_LVL_NEXT = 7, B_ESTN = 8, B_EXT = 9 };
+enum Buf { B_C0 = 0, B_C1 = 1, B_EST_CUR = 2, B_EST_NEXT = 3, B_CRES = 4, B_CTMP = 5, B_LVL_CUR = 6, B_LVL_NEXT = 7, B_EXT = 9 };
 enum Gate { G_NONE = 0, G_ACTIVE = 1, G_REGRID = 2 };
 
 template <class R>
@@ -34,7 +34,6 @@ struct EngK {
     vec2_t<R> *est[2];
     vec2_t<R> *c[2];
     vec2_t<R> *lvl[2];
-    vec2_t<R> *estN;
     vec2_t<R> *ext;                // caller-provided field (set per launch)
 };
 
@@ -70,7 +69,6 @@ __device__ __forceinline__ vec2_t<R> *pick(const EngK<R> &K, int which, const Ct
         case B_CTMP: return K.c[(h.nsquares & 1) ? 1 : 0] + off;
         case B_LVL_CUR: return K.lvl[h.msel] + off;
         case B_LVL_NEXT: return K.lvl[h.msel ^ 1] + off;
-        case B_ESTN: return K.estN + off;
         default: return K.ext + off;
     }
 }
@@ -288,26 +286,40 @@ __global__ void __launch_bounds__(TX *TY) k_e_warp(EngK<R> K, int gate, const R 
 }
 
 // out = v + u o (id + v)   (Motion::accumulate, Motion.cpp:113-178); add_only: out = u + v (Field::operator+=)
-template <class R>
+// VT: v is stored in the transposed working layout (element (i,j) at i*P + j): its tile is read with j fastest and turned
+// in shared memory, so the Fluid regrid composes straight from the running estimate (no untransposed copy)
+template <class R, bool VT>
 __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 4 : 2) k_e_compose(EngK<R> K, int gate, int u_buf, int v_buf, int out_buf, int add_only) {
+    __shared__ vec2_t<R> sT[VT ? TILE : 1][VT ? TILE + 1 : 1];
     const int pair = blockIdx.y;
     const CtlHot h = load_ctl(K.ctl + pair);
     if (!gate_open(h, gate)) return;
     const int nx = K.nx, ny = K.ny;
     const vec2_t<R> *__restrict__ u = pick(K, u_buf, h, pair);
-    const vec2_t<R> *__restrict__ v = pick(K, v_buf, h, pair);
+    const vec2_t<R> *__restrict__ v = pick(K, v_buf, h, pair, VT);
     vec2_t<R> *__restrict__ out = pick(K, out_buf, h, pair);
     const TileWalk T(nx, ny);
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
         const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
         const int i = i0 + threadIdx.x;
         const int jb = j0 + threadIdx.y;
+        if (VT) {
+            __syncthreads();
+            const int jt = j0 + threadIdx.x;
+#pragma unroll
+            for (int p = 0; p < PY; p++) {
+                const int il = threadIdx.y + p * TY, it = i0 + il;
+                if (it < nx && jt < ny) sT[il][threadIdx.x] = v[(size_t)it * K.P + jt];
+            }
+            __syncthreads();
+        }
+        auto v_at = [&](int p) -> vec2_t<R> { return VT ? sT[threadIdx.x][threadIdx.y + p * TY] : v[i + (jb + p * TY) * nx]; };
         if (i0 + TILE <= nx && j0 + TILE <= ny) {
             // full tile: the loads of the thread's 4 pixels are batched (4 x {v, u}, then the 16 gathers), so a warp
             // has up to 16 loads in flight instead of 2; same expressions as compose_pixel
             vec2_t<R> vv[PY], uu[PY];
 #pragma unroll
-            for (int p = 0; p < PY; p++) { const int idx = i + (jb + p * TY) * nx; vv[p] = v[idx]; uu[p] = u[idx]; }
+            for (int p = 0; p < PY; p++) { const int idx = i + (jb + p * TY) * nx; vv[p] = v_at(p); uu[p] = u[idx]; }
             if (add_only) {
 #pragma unroll
                 for (int p = 0; p < PY; p++) out[i + (jb + p * TY) * nx] = mk2<R>(uu[p].x + vv[p].x, uu[p].y + vv[p].y);
@@ -332,7 +344,7 @@ __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 4 : 2) k_e_compose(En
             const int j = jb + p * TY;
             if (j < ny) {
                 const int idx = i + j * nx;
-                const vec2_t<R> vv = v[idx], uu = u[idx];
+                const vec2_t<R> vv = v_at(p), uu = u[idx];
                 out[idx] = add_only ? mk2<R>(uu.x + vv.x, uu.y + vv.y) : compose_pixel<R>(u, nx, ny, i, j, vv, uu);
             }
         }
@@ -704,46 +716,6 @@ __global__ void __launch_bounds__(TX *TY) k_e_derivatives(EngK<R> K, int gate, c
     }
 }
 
-// transposed (i*P + j) -> normal (i + j*nx) copy of a vec2 field
-template <class R>
-__global__ void __launch_bounds__(TX *TY) k_e_untranspose(EngK<R> K, int gate, int src_buf, int dst_buf) {
-    __shared__ vec2_t<R> s[TILE][TILE + 1];
-    const int pair = blockIdx.y;
-    const CtlHot h = load_ctl(K.ctl + pair);
-    if (!gate_open(h, gate)) return;
-    const int nx = K.nx, ny = K.ny;
-    const vec2_t<R> *__restrict__ src = pick(K, src_buf, h, pair, true);
-    vec2_t<R> *__restrict__ dst = pick(K, dst_buf, h, pair, false);
-    const TileWalk T(nx, ny);
-    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
-        const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
-        __syncthreads();
-        const int jt = j0 + threadIdx.x;
-#pragma unroll
-        for (int p = 0; p < PY; p++) {
-            const int il = threadIdx.y + p * TY, it = i0 + il;
-            if (it < nx && jt < ny) s[il][threadIdx.x] = src[(size_t)it * K.P + jt];
-        }
-        __syncthreads();
-        const int i = i0 + threadIdx.x;
-#pragma unroll
-        for (int p = 0; p < PY; p++) {
-            const int jl = threadIdx.y + p * TY, j = j0 + jl;
-            if (i < nx && j < ny) dst[(size_t)i + (size_t)j * nx] = s[threadIdx.x][jl];
-        }
-    }
-}
-
-template <class R>
-__global__ void k_e_zero(EngK<R> K, int gate, int buf, int transposed) {
-    const int pair = blockIdx.y;
-    const CtlHot h = load_ctl(K.ctl + pair);
-    if (!gate_open(h, gate)) return;
-    vec2_t<R> *p = pick(K, buf, h, pair, transposed != 0);
-    const size_t cnt = transposed ? K.nT : K.n;
-    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < cnt; k += (size_t)gridDim.x * blockDim.x) p[k] = mk2<R>((R)0, (R)0);
-}
-
 // ---------------------------------------------------------------------------------------------
 // Fluid in the transposed layout (element (i,j) at i*P + j; threadIdx.x runs along j)
 // ---------------------------------------------------------------------------------------------
@@ -872,6 +844,70 @@ __global__ void __launch_bounds__(TX *TY) k_fl_integrate(EngK<R> K, const vec2_t
             c->regrid = rg;
             c->minjac = (double)minjac;
             if (it < K.tr.cap) { K.tr.regrid[(size_t)pair * K.tr.cap + it] = rg; K.tr.minjac[(size_t)pair * K.tr.cap + it] = (double)minjac; }
+        }
+    }
+}
+
+// Fluid regrid, second half (ImageRegistrationFluid.cpp:116-124): Iaux = Imov o (id + level motion), derivatives of
+// (Iref, Iaux) in the transposed layout, estimate <- 0 -- one kernel.  The warped image of a 32 x 32 tile (+1 halo) is
+// evaluated once into shared memory (Image::warp2d, Image.cpp:119-182) and never reaches HBM; the derivatives
+// (IterativeSolver.cpp:22-56) are turned through shared memory so that the transposed stores are coalesced.
+template <class R>
+__global__ void __launch_bounds__(TX *TY) k_fl_rewarp(EngK<R> K, int gate, const R *__restrict__ Iref_all, const R *__restrict__ Imov_all, int u_buf,
+                                                      vec2_t<R> *__restrict__ gradI_all, R *__restrict__ It_all, int zero_buf) {
+    __shared__ R sw[TILE + 2][TILE + 2 + 1];
+    __shared__ vec2_t<R> sg[TILE][TILE + 1];
+    __shared__ R st[TILE][TILE + 1];
+    const int pair = blockIdx.y;
+    const CtlHot h = load_ctl(K.ctl + pair);
+    if (!gate_open(h, gate)) return;
+    const int nx = K.nx, ny = K.ny;
+    const R *__restrict__ Iref = Iref_all + (size_t)pair * K.n;
+    const R *__restrict__ Imov = Imov_all + (size_t)pair * K.n;
+    const vec2_t<R> *__restrict__ u = pick(K, u_buf, h, pair);
+    vec2_t<R> *__restrict__ zero = pick(K, zero_buf, h, pair, true);
+    const int tid = threadIdx.x + threadIdx.y * TX;
+    const TileWalk T(nx, ny);
+    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
+        const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
+        __syncthreads();
+        for (int e = tid; e < (TILE + 2) * (TILE + 2); e += TX * TY) {
+            const int r = e / (TILE + 2), cc = e - r * (TILE + 2);
+            const int i = i0 + cc - 1, j = j0 + r - 1;
+            R w = (R)0;
+            if (i >= 0 && i < nx && j >= 0 && j < ny) { const int idx = i + j * nx; w = warp_pixel<R>(Imov, nx, ny, i, j, u[idx], Imov[idx]); }
+            sw[r][cc] = w;
+        }
+        __syncthreads();
+        const int i = i0 + threadIdx.x;
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int jl = threadIdx.y + p * TY, j = j0 + jl;
+            if (i < nx && j < ny) {
+                const int r = jl + 1, cc = threadIdx.x + 1;
+                const R ce = sw[r][cc];
+                R gx, gy;   // gradients.h:9-32 on the warped image
+                if (i == 0) gx = sw[r][cc + 1] - ce;
+                else if (i == nx - 1) gx = ce - sw[r][cc - 1];
+                else gx = (sw[r][cc + 1] - sw[r][cc - 1]) / (R)2.0f;
+                if (j == 0) gy = sw[r + 1][cc] - ce;
+                else if (j == ny - 1) gy = ce - sw[r - 1][cc];
+                else gy = (sw[r + 1][cc] - sw[r - 1][cc]) / (R)2.0f;
+                sg[jl][threadIdx.x] = mk2<R>(gx, gy);
+                st[jl][threadIdx.x] = ce - Iref[i + j * nx];
+            }
+        }
+        __syncthreads();
+        const int jt = j0 + threadIdx.x;   // fast thread index runs along j now
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int il = threadIdx.y + p * TY, it = i0 + il;
+            if (it < nx && jt < ny) {
+                const size_t o = (size_t)it * K.P + jt;
+                gradI_all[(size_t)pair * K.nT + o] = sg[threadIdx.x][il];
+                It_all[(size_t)pair * K.nT + o] = st[threadIdx.x][il];
+                zero[o] = mk2<R>((R)0, (R)0);
+            }
         }
     }
 }

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
 }  // namespace
 
 // halo widths from the contraction of the sweep; supported = 0 when the parameters do not contract
-static inline SorPlan sor_plan(int nx, int ny, int batch, double mu, double lambda, double omega, bool dbl) {
+static inline SorPlan sor_plan(int nx, int ny, int batch, double mu, double lambda, double omega, bool dbl, bool fluid) {
     SorPlan S;
     memset(&S, 0, sizeof(S));
     S.nx = nx; S.ny = ny; S.batch = batch;
@@ -391,7 +391,16 @@ static inline SorPlan sor_plan(int nx, int ny, int batch, double mu, double lamb
     S.nstrips = ceil_div(ny - 2, by_max);
     S.BY = ceil_div(ny - 2, S.nstrips);
     // column bands: as many as keep the GPU about `waves` CTAs per SM deep, but not narrower than the west halo
+    // one wave: as many CTAs per SM as the kernel's shared memory lets be resident (at most 4), so the grid is never a
+    // full wave plus a remainder (fp64 stages are twice as large: 2-3 CTAs per SM)
     int per_sm = 4;
+    {
+        const size_t ev = dbl ? 16 : 8, es = dbl ? 8 : 4, LR = (size_t)S.NT * S.RPT + 8;
+        const size_t stage = (LR + 4) * ev + LR * (ev * (fluid ? 2 : 1) + es);
+        const size_t smem = (size_t)S.NS * stage + 2 * (size_t)S.NT * 2 * ev + 1024;   // + per-CTA reservation
+        const int fit = (int)((227u * 1024u) / smem);
+        if (fit < per_sm) per_sm = fit < 1 ? 1 : fit;
+    }
     { const char *e = getenv("OF2D_SOR_PER_SM"); if (e && atoi(e) > 0) per_sm = atoi(e); }
     long want = 148L * per_sm / ((long)batch * S.nstrips);
     if (want < 1) want = 1;
