@@ -467,7 +467,7 @@ struct ConvW {
 };
 
 template <class R, int EPI, int KW>
-__global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int dst_buf, const __grid_constant__ ConvW<R> W, int nsq_cap) {
+__global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 5 : 1) k_e_conv(EngK<R> K, int src_buf, int dst_buf, const __grid_constant__ ConvW<R> W, int nsq_cap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int pair = blockIdx.y;
     PairCtl *c = K.ctl + pair;
@@ -498,7 +498,11 @@ __global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int d
         const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
         return (long)(j0 + r - cx) * nx + (i0 - cx - shift);
     };
-    auto tma_ok = [&](int tile) -> bool { return rows_aligned && tile_start(tile, 0) >= 0 && tile_start(tile, SH - 1) + SWp <= n; };
+    // tile rows 1 .. tiles_y - 3 have their whole window (and its extension to SWp) inside [0, n) for every kernel width
+    // up to kConvMaxW: only the first and the last two tile rows pay for the exact 64-bit test
+    const int tiles_y = T.ntiles / T.tiles_x;
+    auto mid_row = [&](int tile) -> bool { const int ty = T.ty(tile); return ty >= 1 && ty + 2 < tiles_y; };
+    auto tma_ok = [&](int tile) -> bool { return rows_aligned && (mid_row(tile) || (tile_start(tile, 0) >= 0 && tile_start(tile, SH - 1) + SWp <= n)); };
     auto issue = [&](int tile, int st) {   // warp 0
         const int lane = threadIdx.x;
         if (lane == 0) { proxy_fence_async(); mbar_expect_tx(&cbar[st], (unsigned)(SH * SWp * sizeof(vec2_t<R>))); }
@@ -531,8 +535,11 @@ __global__ void __launch_bounds__(TX *TY) k_e_conv(EngK<R> K, int src_buf, int d
         const int i = i0 + threadIdx.x;
         const int jl0 = 4 * threadIdx.y;
         // every tap of every pixel of the tile inside [0, n)?  (first / last flat index of the tile's windows)
-        const long lo = (long)(j0 - cx) * nx + (i0 - cx), hi = (long)(min(j0 + TILE, ny) - 1 + cx) * nx + (min(i0 + TILE, nx) - 1 + cx);
-        const bool tile_interior = lo >= 0 && hi < n;
+        bool tile_interior = mid_row(tile);
+        if (!tile_interior) {
+            const long lo = (long)(j0 - cx) * nx + (i0 - cx), hi = (long)(min(j0 + TILE, ny) - 1 + cx) * nx + (min(i0 + TILE, nx) - 1 + cx);
+            tile_interior = lo >= 0 && hi < n;
+        }
         auto epilogue = [&](vec2_t<R> o, vec2_t<R> prev) {
             if (EPI == 1) {
                 acc.add(o, prev);
