@@ -68,16 +68,18 @@ struct SorTileArgs {
 };
 
 template <class R, int RPT, bool FLUID, bool WARP>
-__global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) {
+__global__ void __launch_bounds__(WARP ? 32 : 288) k_sor_tile(SorTileArgs<R> A) {
     using V = vec2_t<R>;
     static_assert(RPT == 4, "row blocks of 4: 32-byte aligned vector loads from the ring");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t full[SOR_NS];
+    __shared__ uint64_t full[SOR_NS], empty[SOR_NS];
     const int pair = blockIdx.z;
     PairCtl *c = A.ctl + pair;
     if (!__ldcg(&c->active)) return;
 
-    const int NT = blockDim.x, t = threadIdx.x;
+    // !WARP: the CTA is NT compute threads plus one PRODUCER warp (threads NT .. NT+31) that does nothing but stream
+    // the column ring (TMA bulk copies), so the address arithmetic and the copy issue are off the sweep's critical path
+    const int NT = WARP ? blockDim.x : blockDim.x - 32, t = threadIdx.x;
     const int nx = A.nx, ny = A.ny, P = A.P, LR = A.LR;
     const int is = 1 + blockIdx.x * A.BX, ie = min(is + A.BX, nx - 1);
     const int js = 1 + blockIdx.y * A.BY, je = min(js + A.BY, ny - 1);
@@ -116,16 +118,28 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
     };
 
     if (t == 0) {
-        for (int s = 0; s < SOR_NS; s++) mbar_init(&full[s], 1);
+        for (int s = 0; s < SOR_NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    if (t == 0) {
+    float sdf = 0.0f, spf = 0.0f;
+    double sdd = 0.0, spd = 0.0;
+    R mxr = (R)0;
+    if (WARP ? t == 0 : t == NT) {
         const int pre = ncols < SOR_NS ? ncols : SOR_NS;
         for (int k = 0; k < pre; k++) issue(k);
+        if (!WARP) {
+            // column k goes into the stage column k - NS was in, once the compute threads have released it:
+            // the (k / NS - 1)-th completion of that stage's `empty` barrier
+            for (int k = SOR_NS; k < ncols; k++) {
+                mbar_wait(&empty[k % SOR_NS], (unsigned)((k / SOR_NS) - 1) & 1u);
+                proxy_fence_async();
+                issue(k);
+            }
+        }
     }
-
+    if (WARP || t < NT) {
     const int r0 = t * RPT;                      // ring index of the thread's first row
     const int j0 = jl0 + r0;                     // its image row
     bool comp[RPT];
@@ -147,7 +161,6 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
     }
     // fluid: the estimate u on the thread's rows of the column to the west (for du/dx of the fused increment)
     V uW[RPT];
-    R mxr = (R)0;
     if (FLUID) {
         const V *u0 = st_u(0);
 #pragma unroll
@@ -177,8 +190,6 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
 #pragma unroll
     for (int r = 0; r < RPT; r++) own[r] = (j0 + r >= js) && (j0 + r < je);
 
-    float sdf = 0.0f, spf = 0.0f;
-    double sdd = 0.0, spd = 0.0;
     for (int k = 1; k <= ncols - 2; k++) {
         const int i = ic0 - 1 + k;
         const int sC = k % SOR_NS, sE = (k + 1) % SOR_NS;
@@ -249,11 +260,10 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
                 me.d0 = d[0];
                 pb[t] = me;
             }
-            __syncthreads();
-            if (t == 0) {   // stage sC (and stage 0 after the first step) is free: stream the next column(s) in
-                proxy_fence_async();
-                if (k == 1 && SOR_NS < ncols) issue(SOR_NS);
-                if (k + SOR_NS < ncols) issue(k + SOR_NS);
+            asm volatile("bar.sync 1, %0;" ::"r"(NT) : "memory");   // the compute threads only
+            if (t == 0) {   // every compute thread has read stage sC (and stage 0 after the first step): the producer may refill it
+                if (k == 1) mbar_arrive(&empty[0]);
+                mbar_arrive(&empty[sC]);
             }
 #pragma unroll
             for (int q = 0; q < MQ; q++) {
@@ -305,7 +315,7 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
                     if (!FLUID) {
                         const V oc = oldC[r + 1];
                         const R dx = xn[r].x - oc.x, dy = xn[r].y - oc.y;
-                        if (sizeof(R) == 4) { sdf += __fsqrt_rn((float)(dx * dx + dy * dy)); spf += __fsqrt_rn((float)(oc.x * oc.x + oc.y * oc.y)); }
+                        if (sizeof(R) == 4) { sdf += sqrt_approx((float)(dx * dx + dy * dy)); spf += sqrt_approx((float)(oc.x * oc.x + oc.y * oc.y)); }   // Logger addends: as NormAcc (engine_kernels.cuh)
                         else { sdd += sqrt((double)(dx * dx + dy * dy)); spd += sqrt((double)(oc.x * oc.x + oc.y * oc.y)); }
                     }
                 }
@@ -323,6 +333,8 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
 #pragma unroll
         for (int r = 0; r < RPT + 2; r++) oldC[r] = oldE[r];
     }
+
+    }   // compute threads
 
     if (FLUID) {
         // time step from the maximum of the increment (OpticalFlowFluid.cpp:92-95, :135-137; Motion.cpp:51-58), taken by the last CTA
@@ -384,7 +396,7 @@ static inline SorPlan sor_plan(int nx, int ny, int batch, double mu, double lamb
     S.HW = halo(rx); S.HS = halo(rs); S.HN = halo(rn);
     S.RPT = 4;
     S.NT = 64;
-    { const char *e = getenv("OF2D_SOR_NT"); if (e && atoi(e) >= 32) S.NT = atoi(e) & ~31; }
+    { const char *e = getenv("OF2D_SOR_NT"); if (e && atoi(e) >= 32 && atoi(e) <= 256) S.NT = atoi(e) & ~31; }
     S.M = a <= 1e-12 ? 1 : (int)ceil(log(eps) / (S.RPT * log(a))) + 1;
     if (S.HW > 96 || S.HS + S.HN > S.NT * S.RPT / 2 || S.M > 8) { S.supported = 0; return S; }
     const int by_max = S.NT * S.RPT - S.HS - S.HN - 8;
@@ -433,7 +445,7 @@ static int sor_tile_launch(of2d_ctx *ctx, const SorPlan &S, PairCtl *ctl, int *n
         int st = of2d_ensure_dynamic_smem((const void *)kernel, smem);
         if (st) return st;
         ProfScope _ps(ctx, name);
-        kernel<<<grid, S.NT, smem, ctx->stream>>>(A);
+        kernel<<<grid, S.NT == 32 ? 32 : S.NT + 32, smem, ctx->stream>>>(A);
         return OF2D_SUCCESS;
     };
     int st;

@@ -90,9 +90,15 @@ for rep in sorted(glob.glob("gpurun_out/*.ncu-rep")):
         except Exception as e:
             lines.append(f"# source page unavailable: {e}")
         open(f"gpurun_out/summ/{name}.txt", "w").write("\n".join(lines) + "\n")
-json.dump(traffic, open(f"gpurun_out/summ/{tag}_traffic.json", "w"), indent=1)
+tj = f"gpurun_out/summ/{tag}_traffic.json"
+try:
+    prev = json.load(open(tj))
+except Exception:
+    prev = {}
+prev.update(traffic)
+json.dump(prev, open(tj, "w"), indent=1)
 # return-size guard
-reps = sorted(glob.glob("gpurun_out/*.ncu-rep"), key=os.path.getsize)
+reps = sorted(glob.glob("gpurun_out/*.ncu-rep"), key=os.path.getmtime, reverse=True)
 tot = 0
 for rep in reps:
     sz = os.path.getsize(rep) / 1e6
