@@ -184,37 +184,24 @@ __global__ void __launch_bounds__(TX *TY) k_hs_iter(EngK<R> K, const vec2_t<R> *
     const TileWalk T(nx, ny);
     NormAcc<R> acc;
     bool divzero = false;
-    __shared__ vec2_t<R> s_u[(TILE + 2) * (TILE + 2)];   // halo tile of u of an interior tile
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
         const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
         if (i0 >= 1 && i0 + TILE < nx && j0 >= 1 && j0 + TILE < ny) {
-            // interior tile: no edge cases.  The CTA stages the 34 x 34 halo tile of u in shared memory (coalesced loads,
-            // all of a thread's loads -- its share of the halo tile and the gradI / It of its own 4 pixels -- issued before
-            // any arithmetic); a thread owns 4 consecutive rows of one column and reads its column of u (rows j-1 .. j+4)
-            // and the left / right neighbours from shared memory.
-            constexpr int HT = TILE + 2, NE = HT * HT, NR = (NE + TX * TY - 1) / (TX * TY);
-            const int tid = threadIdx.x + threadIdx.y * TX;
+            // interior tile: no edge cases.  A thread owns 4 consecutive rows of one column, so the column of u it
+            // needs (rows j-1 .. j+4) is loaded once and every address is a row pointer plus an immediate offset.
             const size_t idx0 = (size_t)(i0 + threadIdx.x) + (size_t)(j0 + 4 * threadIdx.y) * nx;
-            vec2_t<R> uo[NR], dI[4];
+            const vec2_t<R> *__restrict__ up = u + idx0;
+            vec2_t<R> ce[6], le[4], ri[4], dI[4];
             R it[4];
 #pragma unroll
-            for (int k = 0; k < NR; k++) {
-                const int e = min(tid + k * TX * TY, NE - 1);
-                const int r = e / HT, cc = e - r * HT;
-                uo[k] = u[(size_t)(i0 - 1 + cc) + (size_t)(j0 - 1 + r) * nx];
+            for (int r = 0; r < 6; r++) ce[r] = up[(ptrdiff_t)(r - 1) * nx];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                le[q] = up[(ptrdiff_t)q * nx - 1];
+                ri[q] = up[(ptrdiff_t)q * nx + 1];
+                dI[q] = gradI[idx0 + (size_t)q * nx];
+                it[q] = It[idx0 + (size_t)q * nx];
             }
-#pragma unroll
-            for (int q = 0; q < 4; q++) { dI[q] = gradI[idx0 + (size_t)q * nx]; it[q] = It[idx0 + (size_t)q * nx]; }
-            __syncthreads();   // the previous tile's reads of s_u are over
-#pragma unroll
-            for (int k = 0; k < NR; k++) { const int e = tid + k * TX * TY; if (e < NE) s_u[e] = uo[k]; }
-            __syncthreads();
-            const int sb = (4 * threadIdx.y) * HT + threadIdx.x + 1;   // (row j-1 of the thread, its own column) in the halo tile
-            vec2_t<R> ce[6], le[4], ri[4];
-#pragma unroll
-            for (int r = 0; r < 6; r++) ce[r] = s_u[sb + r * HT];
-#pragma unroll
-            for (int q = 0; q < 4; q++) { le[q] = s_u[sb + (q + 1) * HT - 1]; ri[q] = s_u[sb + (q + 1) * HT + 1]; }
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const vec2_t<R> qm = mk2<R>((((le[q].x + ri[q].x) + ce[q].x) + ce[q + 2].x) / (R)4.0f, (((le[q].y + ri[q].y) + ce[q].y) + ce[q + 2].y) / (R)4.0f);   // gradients.h:78
