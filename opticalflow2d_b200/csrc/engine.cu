@@ -157,7 +157,10 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
         case 3:
         case 4: {
             const R si = (R)d.sigma_i, sx = (R)d.sigma_x;
-            { ProfScope _ps(E->ctx, "demons_force"); k_e_demons_force<R><<<grid_tiles(E, k_e_demons_force<R>), b, 0, s>>>(K, d_Iref, (const R *)E->aux, si * si, sx * sx); }
+            const R sxsq = sx * sx;
+            int ex = 0;
+            const R inv_sxsq = (sxsq > 0 && frexp((double)sxsq, &ex) == 0.5 && ex > -100 && ex < 100) ? (R)ldexp(1.0, 1 - ex) : (R)0;   // exact power of two only
+            { ProfScope _ps(E->ctx, "demons_force"); k_e_demons_force<R><<<grid_tiles(E, k_e_demons_force<R>), b, 0, s>>>(K, d_Iref, (const R *)E->aux, si * si, sxsq, inv_sxsq); }
             OF2D_LAUNCH_CHECK(E->ctx);
             if (d.method == 3) {
                 TRY((launch_conv<R, 0>(E, K, B_C0, B_C1, 0)));

@@ -396,7 +396,9 @@ __global__ void __launch_bounds__(TX *TY) k_e_square(EngK<R> K, int s) {
 // Demons force: warp + derivatives + demons_iteration (DemonsThirions.cpp:18-27, Demons.cpp:34-63).
 // The warped image of a 32 x 32 tile (+1 halo) is evaluated once into shared memory.
 template <class R>
-__global__ void __launch_bounds__(TX *TY) k_e_demons_force(EngK<R> K, const R *__restrict__ Iref_all, const R *__restrict__ Imov_all, R sigma_isq, R sigma_xsq) {
+// inv_sigma_xsq: 1 / sigma_xsq when sigma_xsq is a power of two (x / 2^k == x * 2^-k exactly, so the multiplication gives the
+// reference's bits without the IEEE division sequence), else 0
+__global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 8 : 1) k_e_demons_force(EngK<R> K, const R *__restrict__ Iref_all, const R *__restrict__ Imov_all, R sigma_isq, R sigma_xsq, R inv_sigma_xsq) {
     __shared__ R sw[TILE + 2][TILE + 2 + 1];
     const int pair = blockIdx.y;
     PairCtl *c = K.ctl + pair;
@@ -412,16 +414,39 @@ __global__ void __launch_bounds__(TX *TY) k_e_demons_force(EngK<R> K, const R *_
     bool divzero = false;
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
         const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
+        const int i = i0 + threadIdx.x;
+        const bool interior = i0 >= 1 && j0 >= 1 && i0 + TILE < nx && j0 + TILE < ny;   // central differences everywhere
+        R iref[PY];
+        if (interior) {   // in flight while the halo tile is warped
+#pragma unroll
+            for (int p = 0; p < PY; p++) iref[p] = Iref[i + (j0 + threadIdx.y + p * TY) * nx];
+        }
         __syncthreads();
         for (int e = tid; e < (TILE + 2) * (TILE + 2); e += TX * TY) {
             const int r = e / (TILE + 2), cc = e - r * (TILE + 2);
-            const int i = i0 + cc - 1, j = j0 + r - 1;
+            const int ii = i0 + cc - 1, j = j0 + r - 1;
             R w = (R)0;
-            if (i >= 0 && i < nx && j >= 0 && j < ny) { const int idx = i + j * nx; w = warp_pixel<R>(Imov, nx, ny, i, j, u[idx], Imov[idx]); }
+            if (ii >= 0 && ii < nx && j >= 0 && j < ny) { const int idx = ii + j * nx; w = warp_pixel<R>(Imov, nx, ny, ii, j, u[idx], Imov[idx]); }
             sw[r][cc] = w;
         }
         __syncthreads();
-        const int i = i0 + threadIdx.x;
+        if (interior) {
+#pragma unroll
+            for (int p = 0; p < PY; p++) {
+                const int jl = threadIdx.y + p * TY;
+                const int idx = i + (j0 + jl) * nx;
+                const int r = jl + 1, cc = threadIdx.x + 1;
+                const R ce = sw[r][cc];
+                const R gx = (sw[r][cc + 1] - sw[r][cc - 1]) / (R)2.0f;
+                const R gy = (sw[r + 1][cc] - sw[r - 1][cc]) / (R)2.0f;
+                const R It = ce - iref[p];
+                const R q = It * It * sigma_isq;
+                const R den = gx * gx + gy * gy + (inv_sigma_xsq != (R)0 ? q * inv_sigma_xsq : q / sigma_xsq);
+                if (den == 0) { divzero = true; corr[idx] = mk2<R>((R)0, (R)0); continue; }
+                corr[idx] = mk2<R>(gx * It / den * (R)-1, gy * It / den * (R)-1);
+            }
+            continue;
+        }
         if (i >= nx) continue;
 #pragma unroll
         for (int p = 0; p < PY; p++) {
