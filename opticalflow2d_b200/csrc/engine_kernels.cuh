@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(TX *TY) k_e_warp(EngK<R> K, int gate, const R 
 // VT: v is stored in the transposed working layout (element (i,j) at i*P + j): its tile is read with j fastest and turned
 // in shared memory, so the Fluid regrid composes straight from the running estimate (no untransposed copy)
 template <class R, bool VT>
-__global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 4 : 2) k_e_compose(EngK<R> K, int gate, int u_buf, int v_buf, int out_buf, int add_only) {
+__global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 4 : 1) k_e_compose(EngK<R> K, int gate, int u_buf, int v_buf, int out_buf, int add_only) {
     __shared__ vec2_t<R> sT[VT ? TILE : 1][VT ? TILE + 1 : 1];
     const int pair = blockIdx.y;
     const CtlHot h = load_ctl(K.ctl + pair);
@@ -314,8 +314,8 @@ __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 4 : 2) k_e_compose(En
             __syncthreads();
         }
         auto v_at = [&](int p) -> vec2_t<R> { return VT ? sT[threadIdx.x][threadIdx.y + p * TY] : v[i + (jb + p * TY) * nx]; };
-        if (i0 + TILE <= nx && j0 + TILE <= ny) {
-            // full tile: the loads of the thread's 4 pixels are batched (4 x {v, u}, then the 16 gathers), so a warp
+        if (sizeof(R) == 4 && i0 + TILE <= nx && j0 + TILE <= ny) {
+            // full tile (fp32; in fp64 the batch costs more registers than it hides latency): the loads of the thread's 4 pixels are batched (4 x {v, u}, then the 16 gathers), so a warp
             // has up to 16 loads in flight instead of 2; same expressions as compose_pixel
             vec2_t<R> vv[PY], uu[PY];
 #pragma unroll

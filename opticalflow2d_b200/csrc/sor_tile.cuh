@@ -68,7 +68,7 @@ struct SorTileArgs {
 };
 
 template <class R, int RPT, bool FLUID, bool WARP>
-__global__ void __launch_bounds__(WARP ? 32 : 288) k_sor_tile(SorTileArgs<R> A) {
+__global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) {
     using V = vec2_t<R>;
     static_assert(RPT == 4, "row blocks of 4: 32-byte aligned vector loads from the ring");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -396,7 +396,8 @@ static inline SorPlan sor_plan(int nx, int ny, int batch, double mu, double lamb
     S.HW = halo(rx); S.HS = halo(rs); S.HN = halo(rn);
     S.RPT = 4;
     S.NT = 64;
-    { const char *e = getenv("OF2D_SOR_NT"); if (e && atoi(e) >= 32 && atoi(e) <= 256) S.NT = atoi(e) & ~31; }
+    // + the producer warp: at most 128 threads (the kernel's launch bounds)
+    { const char *e = getenv("OF2D_SOR_NT"); if (e && atoi(e) >= 32 && atoi(e) <= 96) S.NT = atoi(e) & ~31; }
     S.M = a <= 1e-12 ? 1 : (int)ceil(log(eps) / (S.RPT * log(a))) + 1;
     if (S.HW > 96 || S.HS + S.HN > S.NT * S.RPT / 2 || S.M > 8) { S.supported = 0; return S; }
     const int by_max = S.NT * S.RPT - S.HS - S.HN - 8;
