@@ -26,7 +26,8 @@ struct alignas(16) PairCtl {
     int overflow;        // nsquares above the enqueued squarings: host must not trust the result
     int vsel;            // fluid: which velocity buffer is current (persists across refines and calls, like the velocity)
     int prev_other;      // fluid: Logger's prev is the other estimate buffer (set by a regrid, which zeroes the estimate)
-    int pad0[3];
+    int redo;            // diffusion: the two-step kernel met the break test after its FIRST step; the single-step kernel that follows redoes it
+    int pad0[2];
     unsigned ticket[4];  // last-block tickets (one per reduction kind)
     double err;          // last Logger error
     double maxabs;       // fluid / diffeo: sqrt(max(2 y^2))

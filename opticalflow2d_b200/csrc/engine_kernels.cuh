@@ -43,7 +43,7 @@ struct CtlHot {
     unsigned flags;
     int sel, regrid, skip, nsquares;
     int nregrid, msel, overflow, vsel;
-    int prev_other;
+    int prev_other, redo;
 };
 __device__ __forceinline__ CtlHot load_ctl(const PairCtl *c) {
     const int4 *p = reinterpret_cast<const int4 *>(c);
@@ -52,10 +52,10 @@ __device__ __forceinline__ CtlHot load_ctl(const PairCtl *c) {
     h.active = a.x; h.iter = a.y; h.niter = a.z; h.flags = (unsigned)a.w;
     h.sel = b.x; h.regrid = b.y; h.skip = b.z; h.nsquares = b.w;
     h.nregrid = d.x; h.msel = d.y; h.overflow = d.z; h.vsel = d.w;
-    h.prev_other = e.x;
+    h.prev_other = e.x; h.redo = e.y;
     return h;
 }
-static_assert(offsetof(PairCtl, sel) == 16 && offsetof(PairCtl, nregrid) == 32 && offsetof(PairCtl, prev_other) == 48, "CtlHot mirrors the head of PairCtl");
+static_assert(offsetof(PairCtl, sel) == 16 && offsetof(PairCtl, nregrid) == 32 && offsetof(PairCtl, prev_other) == 48 && offsetof(PairCtl, redo) == 52, "CtlHot mirrors the head of PairCtl");
 
 template <class R>
 __device__ __forceinline__ vec2_t<R> *pick(const EngK<R> &K, int which, const CtlHot &h, int pair, bool transposed = false) {
@@ -118,7 +118,7 @@ struct TileWalk {
 
 // Logger epilogue shared by the kernels that produce the next estimate
 template <class R>
-__device__ __forceinline__ void logger_epilogue(const EngK<R> &K, PairCtl *c, int pair, double sd, double sp) {
+__device__ __forceinline__ void logger_epilogue(const EngK<R> &K, PairCtl *c, int pair, double sd, double sp, bool clear_redo = false) {
     block_sum2(sd, sp);
     const double vals[2] = {sd, sp};
     double *part = K.partials + (size_t)pair * K.pstride;
@@ -126,6 +126,7 @@ __device__ __forceinline__ void logger_epilogue(const EngK<R> &K, PairCtl *c, in
         double out[2];
         reduce_partials<2>(part, gridDim.x, out, 0u, 0u);
         if (threadIdx.x == 0 && threadIdx.y == 0) {
+            if (clear_redo) c->redo = 0;
             c->sel ^= 1;
             finalize_logger<R>(c, K.tr, pair, out[0], out[1], (unsigned)K.n, K.n_active);
         }
@@ -151,6 +152,7 @@ __global__ void k_ctl_begin(PairCtl *ctl, int batch, int niter, int *n_active) {
     c->msel = 0;
     c->overflow = 0;
     c->prev_other = 0;
+    c->redo = 0;
     for (int k = 0; k < 4; k++) c->ticket[k] = 0u;
     c->err = 0.0;
 }
@@ -170,12 +172,14 @@ __global__ void k_regrid_commit(PairCtl *ctl, int batch) {
 // ---------------------------------------------------------------------------------------------
 // Horn-Schunck Jacobi step + Logger (OpticalFlowDiffusion.cpp:19-84, Logger.cpp:32-51)
 // ---------------------------------------------------------------------------------------------
+// fixup: 0 = a plain iteration (skipped while a redo of k_hs_pair is pending); 1 = runs only to redo the first step of a two-step
+// launch; 2 = the closing launch of a refine pass: a plain iteration that also serves a pending redo
 template <class R>
-__global__ void __launch_bounds__(TX *TY) k_hs_iter(EngK<R> K, const vec2_t<R> *__restrict__ gradI_all, const R *__restrict__ It_all, R alphasq) {
+__global__ void __launch_bounds__(TX *TY) k_hs_iter(EngK<R> K, const vec2_t<R> *__restrict__ gradI_all, const R *__restrict__ It_all, R alphasq, int fixup) {
     const int pair = blockIdx.y;
     PairCtl *c = K.ctl + pair;
     const CtlHot h = load_ctl(c);
-    if (!h.active) return;
+    if (!h.active || (fixup == 0 && h.redo) || (fixup == 1 && !h.redo)) return;   // fixup 2: whether or not a redo is pending
     const int nx = K.nx, ny = K.ny;
     const vec2_t<R> *__restrict__ u = pick(K, B_EST_CUR, h, pair);
     vec2_t<R> *__restrict__ un = pick(K, B_EST_NEXT, h, pair);
@@ -254,7 +258,150 @@ __global__ void __launch_bounds__(TX *TY) k_hs_iter(EngK<R> K, const vec2_t<R> *
         acc.flush();
     }
     if (divzero) atomicOr(&c->flags, OF2D_FLAG_DIVZERO);
-    logger_epilogue<R>(K, c, pair, acc.dsd, acc.dsp);
+    logger_epilogue<R>(K, c, pair, acc.dsd, acc.dsp, fixup != 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two Horn-Schunck Jacobi steps per launch: temporal blocking in shared memory.  A CTA stages u^k on the 36 x 36 halo
+// of its 32 x 32 tile, evaluates u^(k+1) on the 34 x 34 halo (its own pixels plus the 132 ring points) into shared
+// memory, then u^(k+2) on the tile: u, gradI, It are read once and u written once per TWO iterations.  Every pixel
+// value is the same expression as in k_hs_iter (bit-identical); the Logger sums of both steps are reduced together and
+// the last CTA replays the driver's loop for the two iterations (Logger.cpp:32-51, ImageRegistrationOpticalFlow.cpp:131-134).
+// If the break test fires after the FIRST step the launch leaves the state untouched and raises `redo`: the next launch
+// (this kernel again, or the closing k_hs_iter of the refine pass) finds the flag and redoes that one step from the
+// intact u^k as a single-step iteration.
+// ---------------------------------------------------------------------------------------------
+template <class R>
+__device__ __forceinline__ vec2_t<R> hs_point(vec2_t<R> a, vec2_t<R> b, vec2_t<R> cc, vec2_t<R> d, bool border, vec2_t<R> dI, R it, R alphasq, bool &divzero) {
+    vec2_t<R> q;
+    if (border) q = mk2<R>((R)0.0f, (R)0.0f);
+    else q = mk2<R>((((a.x + b.x) + cc.x) + d.x) / (R)4.0f, (((a.y + b.y) + cc.y) + d.y) / (R)4.0f);   // gradients.h:78
+    const vec2_t<R> f = lssd_force<R>(dI, it, q);
+    const R den = alphasq + dI.x * dI.x + dI.y * dI.y;
+    if (den == 0) { divzero = true; return q; }
+    return mk2<R>(q.x - f.x / den, q.y - f.y / den);
+}
+
+template <class R>
+__global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 3 : 2) k_hs_pair(EngK<R> K, const vec2_t<R> *__restrict__ gradI_all, const R *__restrict__ It_all, R alphasq) {
+    constexpr int H0 = TILE + 4, H1 = TILE + 2, NRING = 4 * H1 - 4;
+    __shared__ vec2_t<R> s0[H0 * H0];   // u^k on the 36 x 36 halo tile
+    __shared__ vec2_t<R> s1[H1 * H1];   // u^(k+1) on the 34 x 34 halo tile
+    const int pair = blockIdx.y;
+    PairCtl *c = K.ctl + pair;
+    const CtlHot h = load_ctl(c);
+    if (!h.active) return;
+    const bool single = h.redo != 0;   // redo of the first step of the previous two-step launch: one step only
+    const int nx = K.nx, ny = K.ny;
+    const vec2_t<R> *__restrict__ u = pick(K, B_EST_CUR, h, pair);
+    vec2_t<R> *__restrict__ un = pick(K, B_EST_NEXT, h, pair);
+    const vec2_t<R> *__restrict__ gradI = gradI_all + (size_t)pair * K.n;
+    const R *__restrict__ It = It_all + (size_t)pair * K.n;
+    const int tid = threadIdx.x + threadIdx.y * TX;
+    // the ring point of this thread (threads 0 .. 131): coordinates in the 34 x 34 halo tile
+    int rr = 0, rc = 0;
+    if (tid < H1) { rr = 0; rc = tid; }
+    else if (tid < 2 * H1) { rr = H1 - 1; rc = tid - H1; }
+    else if (tid < 2 * H1 + TILE) { rr = tid - 2 * H1 + 1; rc = 0; }
+    else { rr = tid - (2 * H1 + TILE) + 1; rc = H1 - 1; }
+    const bool has_ring = tid < NRING;
+    const TileWalk T(nx, ny);
+    NormAcc<R> acc1, acc2;
+    bool divzero = false;
+    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
+        const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
+        const int i = i0 + threadIdx.x;
+        // loads first: the thread's share of the u^k halo tile, gradI / It of its 4 pixels and of its ring point
+        constexpr int NR0 = (H0 * H0 + TX * TY - 1) / (TX * TY);
+        vec2_t<R> u0[NR0], dI[PY], dIr;
+        R it[PY], itr;
+#pragma unroll
+        for (int k = 0; k < NR0; k++) {
+            const int e = min(tid + k * TX * TY, H0 * H0 - 1);
+            const int r = e / H0, cc = e - r * H0;
+            const int gi = min(max(i0 - 2 + cc, 0), nx - 1), gj = min(max(j0 - 2 + r, 0), ny - 1);   // clamped: out-of-image halo values are never used
+            u0[k] = u[gi + gj * nx];
+        }
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int gi = min(i, nx - 1), gj = min(j0 + threadIdx.y + p * TY, ny - 1);
+            dI[p] = gradI[gi + gj * nx]; it[p] = It[gi + gj * nx];
+        }
+        const int ri = i0 - 1 + rc, rj = j0 - 1 + rr;
+        const bool ring_in = has_ring && ri >= 0 && ri < nx && rj >= 0 && rj < ny;
+        {
+            const int gi = min(max(ri, 0), nx - 1), gj = min(max(rj, 0), ny - 1);
+            dIr = gradI[gi + gj * nx]; itr = It[gi + gj * nx];
+        }
+        __syncthreads();   // the previous tile's reads of s0 / s1 are over
+#pragma unroll
+        for (int k = 0; k < NR0; k++) { const int e = tid + k * TX * TY; if (e < H0 * H0) s0[e] = u0[k]; }
+        __syncthreads();
+        // first step on the 34 x 34 halo: own pixels, then the ring point
+        vec2_t<R> u1[PY];
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int jl = threadIdx.y + p * TY, j = j0 + jl;
+            const int e0 = (jl + 2) * H0 + threadIdx.x + 2;
+            const bool border = i == 0 || i >= nx - 1 || j == 0 || j >= ny - 1;
+            u1[p] = hs_point<R>(s0[e0 - 1], s0[e0 + 1], s0[e0 - H0], s0[e0 + H0], border, dI[p], it[p], alphasq, divzero);
+            s1[(jl + 1) * H1 + threadIdx.x + 1] = u1[p];
+            if (i < nx && j < ny) {
+                acc1.add(u1[p], s0[e0]);
+                if (single) un[i + j * nx] = u1[p];
+            }
+        }
+        if (single) { acc1.flush(); continue; }
+        if (has_ring) {
+            const int e0 = (rr + 1) * H0 + rc + 1;
+            const bool border = ri <= 0 || ri >= nx - 1 || rj <= 0 || rj >= ny - 1;
+            bool dz = false;
+            const vec2_t<R> v = hs_point<R>(s0[e0 - 1], s0[e0 + 1], s0[e0 - H0], s0[e0 + H0], border, dIr, itr, alphasq, dz);
+            s1[rr * H1 + rc] = ring_in ? v : mk2<R>((R)0, (R)0);
+        }
+        acc1.flush();
+        __syncthreads();
+        // second step on the tile
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int jl = threadIdx.y + p * TY, j = j0 + jl;
+            const int e1 = (jl + 1) * H1 + threadIdx.x + 1;
+            const bool border = i == 0 || i >= nx - 1 || j == 0 || j >= ny - 1;
+            bool dz = false;
+            const vec2_t<R> o = hs_point<R>(s1[e1 - 1], s1[e1 + 1], s1[e1 - H1], s1[e1 + H1], border, dI[p], it[p], alphasq, dz);
+            if (i < nx && j < ny) {
+                un[i + j * nx] = o;
+                acc2.add(o, u1[p]);
+            }
+        }
+        acc2.flush();
+    }
+    if (divzero) atomicOr(&c->flags, OF2D_FLAG_DIVZERO);
+    if (single) { logger_epilogue<R>(K, c, pair, acc1.dsd, acc1.dsp, true); return; }
+    double sd1 = acc1.dsd, sp1 = acc1.dsp, sd2 = acc2.dsd, sp2 = acc2.dsp;
+    block_sum2(sd1, sp1);
+    block_sum2(sd2, sp2);
+    const double vals[4] = {sd1, sp1, sd2, sp2};
+    double *part = K.partials + (size_t)pair * K.pstride;
+    if (publish_partials<4>(vals, part, &c->ticket[0], gridDim.x, blockIdx.x)) {
+        double out[4];
+        reduce_partials<4>(part, gridDim.x, out, 0u, 0u);
+        if (tid == 0) {
+            const R n = (R)(unsigned)K.n;
+            const R dn = (R)out[0] / n, pn = (R)out[1] / n;                       // Motion.cpp:47
+            const R err1 = pn == 0 ? (R)0.0f : dn / pn;                           // Logger.cpp:39
+            const int itc = c->iter;
+            if ((err1 < (R)0.001f && itc > 1) || itc + 1 >= c->niter) {
+                c->redo = 1;   // the loop ends after the first step: state untouched, the single-step launch redoes it
+            } else {
+                c->err = (double)err1;
+                if (itc < K.tr.cap) K.tr.err[(size_t)pair * K.tr.cap + itc] = (double)err1;
+                c->iter = itc + 1;
+                c->sel ^= 1;
+                finalize_logger<R>(c, K.tr, pair, out[2], out[3], (unsigned)K.n, K.n_active);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

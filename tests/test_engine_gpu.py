@@ -52,6 +52,34 @@ def test_engine_is_bit_identical_to_strict(bits, reg, params, niter, dimx, dimy)
     assert maxdiff(mf, ms) == 0.0
 
 
+# Diffusion runs two Jacobi steps per launch (k_hs_pair, temporal blocking).  These pairs converge and break after an odd
+# (145, 147) or an even (188, 192) number of iterations on the CPU reference: the break lands on the first / the second
+# step of a two-step launch, and on the first one the launch must leave the state to the single-step kernel that follows.
+BREAKS = [("blob", (0.3, -0.2), 0.02, 145), ("lattice", (0.4, 0.1), 0.02, 147), ("lattice", (0.4, 0.1), 0.05, 188), ("blob", (1.0, 0.5), 0.02, 192)]
+
+
+@pytest.mark.parametrize("kind,shift,alpha,want_iter", BREAKS, ids=[f"{b[0]}-{b[3]}" for b in BREAKS])
+def test_two_step_diffusion_breaks_where_the_reference_does(kind, shift, alpha, want_iter):
+    dimx, dimy = 64, 48
+    R, T = S.make_pair(dimx, dimy, kind, shift=shift)
+    mf, tf = run(32, False, (dimx, dimy), R, T, of.DIFFUSION, [alpha], [300])
+    want = oracle(32).register(R, T, of.DIFFUSION, [alpha], [300], nscales=0, nrefine=1, verbose=1)
+    assert len(want["err"]) == want_iter
+    assert tf["total_iterations"] == want_iter
+    assert np.allclose(series(tf, "err"), np.asarray(want["err"], dtype=np.float64), rtol=5e-4, atol=1e-12)
+    assert maxdiff(mf, want["motion"]) == 0.0
+
+
+@pytest.mark.parametrize("niter", [1, 2, 3, 8, 9])
+def test_two_step_diffusion_iteration_caps(niter):
+    dimx, dimy = 97, 70
+    R, T = S.make_pair(dimx, dimy, "lattice", shift=(1.5, -0.75))
+    mf, tf = run(32, False, (dimx, dimy), R, T, of.DIFFUSION, [0.5], [niter])
+    want = oracle(32).register(R, T, of.DIFFUSION, [0.5], [niter], nscales=0, nrefine=1, verbose=1)
+    assert tf["total_iterations"] == len(want["err"])
+    assert maxdiff(mf, want["motion"]) == 0.0
+
+
 @pytest.mark.parametrize("bits", [32, 64])
 @pytest.mark.parametrize("dimx,dimy", [(128, 128), (256, 64), (512, 512), (1024, 512)])
 def test_engine_curvature_fast_dct(bits, dimx, dimy):
