@@ -69,6 +69,28 @@ struct ProfScope {
         OF2D_CUDA_TRY(cudaGetLastError());                         \
     } while (0)
 
+// ---- programmatic dependent launch (sm_90+) -------------------------------------------------------
+// Every kernel of the iteration engine starts with pdl_enter(): wait until the previous kernel of the stream has
+// completed and its writes are visible (griddepcontrol.wait), then let the NEXT kernel of the stream be launched
+// (griddepcontrol.launch_dependents): its CTAs are scheduled while this kernel runs and sit in their own wait, so the
+// launch latency between the ~4 000 dependent kernels of a step is hidden.  Without the launch attribute (pdl_launch below
+// its level, or a plain <<<>>> launch) both instructions are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+int of2d_pdl_level();   // OF2D_PDL: 0 = off, 1 = on except for the SOR sweep (default), 2 = every engine kernel
+template <int LEVEL = 1, class... KArgs, class... Args>
+inline cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = of2d_pdl_level() >= LEVEL ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- vector types -------------------------------------------------------------------------------
 template <class R> struct Vec2T;
 template <> struct Vec2T<float> { using type = float2; };

@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // ctx.cu -- context, memory and stream plumbing of libof2d_cuda.
 #include <stdarg.h>
 #include <string.h>
@@ -200,3 +201,9 @@ int of2d_d2d(of2d_ctx *c, void *dst, const void *src, size_t bytes) {
 }
 
 }  // extern "C"
+
+int of2d_pdl_level() {
+    static int lvl = -1;
+    if (lvl < 0) { const char *e = getenv("OF2D_PDL"); lvl = e ? atoi(e) : 1; if (lvl < 0) lvl = 0; }
+    return lvl;
+}

@@ -412,12 +412,12 @@ int launch_reg_rows(of2d_curvature_plan *P, bool fwd, const R *u, R *unew, const
     if (fwd) {
         { int st = of2d_ensure_dynamic_smem((const void *)rg::k_rg_rows_fwd<R, LX, LPC>, smem); if (st) return st; }
         ProfScope _ps(ctx, "curv_rows_fwd");
-        rg::k_rg_rows_fwd<R, LX, LPC><<<dim3(P->ny / LPC, batch), NT, smem, ctx->stream>>>(P->ny, (const vec2_t<R> *)u, (const vec2_t<R> *)unew, (const vec2_t<R> *)gradI, It,
+        pdl_launch(rg::k_rg_rows_fwd<R, LX, LPC>, dim3(P->ny / LPC, batch), NT, smem, ctx->stream, P->ny, (const vec2_t<R> *)u, (const vec2_t<R> *)unew, (const vec2_t<R> *)gradI, It,
                                                                                        (R)P->tau, (double2 *)P->d_spec, (const double2 *)P->Tx.q, T, H);
     } else {
         { int st = of2d_ensure_dynamic_smem((const void *)rg::k_rg_rows_inv<R, LX, LPC>, smem); if (st) return st; }
         ProfScope _ps(ctx, "curv_rows_inv");
-        rg::k_rg_rows_inv<R, LX, LPC><<<dim3(P->ny / LPC, batch), NT, smem, ctx->stream>>>(P->ny, (const double2 *)P->d_spec2, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN,
+        pdl_launch(rg::k_rg_rows_inv<R, LX, LPC>, dim3(P->ny / LPC, batch), NT, smem, ctx->stream, P->ny, (const double2 *)P->d_spec2, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN,
                                                                                        (const double2 *)P->Tx.q, T, H);
     }
     OF2D_LAUNCH_CHECK(ctx);
@@ -431,7 +431,7 @@ int launch_reg_cols(of2d_curvature_plan *P, const CurvHook &H, int batch) {
     const rg::Tw16 T{(const double2 *)P->Ty.tw16a, (const double2 *)P->Ty.tw16b};
     { int st = of2d_ensure_dynamic_smem((const void *)rg::k_rg_cols<LY>, smem); if (st) return st; }
     ProfScope _ps(ctx, "curv_cols");
-    rg::k_rg_cols<LY><<<dim3(P->nx / 2, batch), NT, smem, ctx->stream>>>(P->nx, (const double2 *)P->d_spec, (double2 *)P->d_spec2, P->d_cosx, P->d_cosy, P->tau_alpha,
+    pdl_launch(rg::k_rg_cols<LY>, dim3(P->nx / 2, batch), NT, smem, ctx->stream, P->nx, (const double2 *)P->d_spec, (double2 *)P->d_spec2, P->d_cosx, P->d_cosy, P->tau_alpha,
                                                                       (const double2 *)P->Ty.q, T, H);
     OF2D_LAUNCH_CHECK(ctx);
     return OF2D_SUCCESS;

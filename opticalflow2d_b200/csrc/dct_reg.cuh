@@ -215,6 +215,7 @@ template <class R, int L, int LPC>
 __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 2 : 1) k_rg_rows_fwd(int ny, const vec2_t<R> *est0, const vec2_t<R> *est1, const vec2_t<R> *__restrict__ gradI,
                                                                    const R *__restrict__ It, R tau, double2 *__restrict__ specT, const double2 *__restrict__ q, Tw16 T,
                                                                    CurvHook H) {
+    pdl_enter();
     using G = Geo<L>;
     constexpr int N = G::N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -264,6 +265,7 @@ template <int L>
 __global__ void __launch_bounds__(2 * Geo<L>::TPL, 2 * Geo<L>::TPL <= 256 ? 2 : 1) k_rg_cols(int nx, const double2 *__restrict__ specT, double2 *__restrict__ specN,
                                                                                         const double *__restrict__ cosx, const double *__restrict__ cosy, double tau_alpha,
                                                                                         const double2 *__restrict__ q, Tw16 T, CurvHook H) {
+    pdl_enter();
     using G = Geo<L>;
     constexpr int N = G::N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -328,6 +330,7 @@ __global__ void __launch_bounds__(2 * Geo<L>::TPL, 2 * Geo<L>::TPL <= 256 ? 2 : 
 template <class R, int L, int LPC>
 __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 2 : 1) k_rg_rows_inv(int ny, const double2 *__restrict__ specN, vec2_t<R> *est0, vec2_t<R> *est1, R fourN,
                                                                    const double2 *__restrict__ q, Tw16 T, CurvHook H) {
+    pdl_enter();
     using G = Geo<L>;
     constexpr int N = G::N;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -117,7 +117,7 @@ int launch_conv_kw(of2d_engine *E, const EngK<R> &K, int src, int dst, int which
     const int shift = sizeof(vec2_t<R>) == 8 ? (cx & 1) : 0;
     const size_t smem = 2 * sizeof(vec2_t<R>) * (size_t)(TILE + 2 * cx) * (size_t)((TILE + 2 * cx + shift + 1) & ~1);
     TRY(of2d_ensure_dynamic_smem((const void *)k_e_conv<R, EPI, KW>, smem));
-    { ProfScope _ps(E->ctx, EPI == 1 ? "conv_logger" : EPI == 2 ? "conv_maxabs" : "conv"); k_e_conv<R, EPI, KW><<<grid_tiles(E, k_e_conv<R, EPI, KW>, smem), dim3(TX, TY), smem, E->ctx->stream>>>(K, src, dst, W, E->nsq_cap); }
+    { ProfScope _ps(E->ctx, EPI == 1 ? "conv_logger" : EPI == 2 ? "conv_maxabs" : "conv"); pdl_launch(k_e_conv<R, EPI, KW>, grid_tiles(E, k_e_conv<R, EPI, KW>, smem), dim3(TX, TY), smem, E->ctx->stream, K, src, dst, W, E->nsq_cap); }
     OF2D_LAUNCH_CHECK(E->ctx);
     return OF2D_SUCCESS;
 }
@@ -143,7 +143,7 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
     switch (d.method) {
         case 0: {
             const R alpha = (R)d.alpha;
-            { ProfScope _ps(E->ctx, "hs_iter"); k_hs_iter<R><<<grid_tiles(E, k_hs_iter<R>), b, 0, s>>>(K, (const vec2_t<R> *)E->gradI, (const R *)E->It, alpha * alpha, 0); }
+            { ProfScope _ps(E->ctx, "hs_iter"); pdl_launch(k_hs_iter<R>, grid_tiles(E, k_hs_iter<R>), b, 0, s, K, (const vec2_t<R> *)E->gradI, (const R *)E->It, alpha * alpha, 0); }
             OF2D_LAUNCH_CHECK(E->ctx);
             break;
         }
@@ -160,20 +160,20 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
             const R sxsq = sx * sx;
             int ex = 0;
             const R inv_sxsq = (sxsq > 0 && frexp((double)sxsq, &ex) == 0.5 && ex > -100 && ex < 100) ? (R)ldexp(1.0, 1 - ex) : (R)0;   // exact power of two only
-            { ProfScope _ps(E->ctx, "demons_force"); k_e_demons_force<R><<<grid_tiles(E, k_e_demons_force<R>), b, 0, s>>>(K, d_Iref, (const R *)E->aux, si * si, sxsq, inv_sxsq); }
+            { ProfScope _ps(E->ctx, "demons_force"); pdl_launch(k_e_demons_force<R>, grid_tiles(E, k_e_demons_force<R>), b, 0, s, K, d_Iref, (const R *)E->aux, si * si, sxsq, inv_sxsq); }
             OF2D_LAUNCH_CHECK(E->ctx);
             if (d.method == 3) {
                 TRY((launch_conv<R, 0>(E, K, B_C0, B_C1, 0)));
-                { ProfScope _pc(E->ctx, "compose"); k_e_compose<R, false><<<grid_tiles(E, k_e_compose<R, false>), b, 0, s>>>(K, G_ACTIVE, B_EST_CUR, B_C1, B_C0, d.accumulation == 1); }
+                { ProfScope _pc(E->ctx, "compose"); pdl_launch(k_e_compose<R, false>, grid_tiles(E, k_e_compose<R, false>), b, 0, s, K, G_ACTIVE, B_EST_CUR, B_C1, B_C0, d.accumulation == 1); }
                 OF2D_LAUNCH_CHECK(E->ctx);
                 TRY((launch_conv<R, 1>(E, K, B_C0, B_EST_NEXT, 1)));
             } else {
                 TRY((launch_conv<R, 2>(E, K, B_C0, B_C1, 0)));
                 for (int q = 0; q < E->nsq_cap; q++) {
-                    { ProfScope _ps(E->ctx, "square"); k_e_square<R><<<grid_tiles(E, k_e_square<R>), b, 0, s>>>(K, q); }
+                    { ProfScope _ps(E->ctx, "square"); pdl_launch(k_e_square<R>, grid_tiles(E, k_e_square<R>), b, 0, s, K, q); }
                     OF2D_LAUNCH_CHECK(E->ctx);
                 }
-                { ProfScope _pc(E->ctx, "compose"); k_e_compose<R, false><<<grid_tiles(E, k_e_compose<R, false>), b, 0, s>>>(K, G_ACTIVE, B_EST_CUR, B_CRES, B_CTMP, 0); }
+                { ProfScope _pc(E->ctx, "compose"); pdl_launch(k_e_compose<R, false>, grid_tiles(E, k_e_compose<R, false>), b, 0, s, K, G_ACTIVE, B_EST_CUR, B_CRES, B_CTMP, 0); }
                 OF2D_LAUNCH_CHECK(E->ctx);
                 TRY((launch_conv<R, 1>(E, K, B_CTMP, B_EST_NEXT, 1)));
             }
@@ -183,14 +183,14 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
             TRY(sor_tile_launch<R>(E->ctx, E->sor, K.ctl, K.n_active, K.partials, K.pstride, K.tr, 1, (vec2_t<R> *)E->vel[0], (vec2_t<R> *)E->vel[1],
                                    (const vec2_t<R> *)E->est[0], (const vec2_t<R> *)E->est[1], (const vec2_t<R> *)E->gradI, (const R *)E->It, (vec2_t<R> *)E->incr));
             // (the increment of the new velocity and the time step are produced by the sweep kernel itself)
-            { ProfScope _ps(E->ctx, "fluid_integrate"); k_fl_integrate<R><<<grid_tiles(E, k_fl_integrate<R>), b, 0, s>>>(K, (const vec2_t<R> *)E->incr); }
+            { ProfScope _ps(E->ctx, "fluid_integrate"); pdl_launch(k_fl_integrate<R>, grid_tiles(E, k_fl_integrate<R>), b, 0, s, K, (const vec2_t<R> *)E->incr); }
             OF2D_LAUNCH_CHECK(E->ctx);
             // regrid (ImageRegistrationFluid.cpp:108-124): level <- est + level o (id + est); est <- 0; re-warp; derivatives
-            { ProfScope _pc(E->ctx, "regrid_compose"); k_e_compose<R, true><<<grid_tiles(E, k_e_compose<R, true>), b, 0, s>>>(K, G_REGRID, B_LVL_CUR, B_EST_CUR, B_LVL_NEXT, 0); }
+            { ProfScope _pc(E->ctx, "regrid_compose"); pdl_launch(k_e_compose<R, true>, grid_tiles(E, k_e_compose<R, true>), b, 0, s, K, G_REGRID, B_LVL_CUR, B_EST_CUR, B_LVL_NEXT, 0); }
             OF2D_LAUNCH_CHECK(E->ctx);
-            { ProfScope _pw(E->ctx, "regrid_rewarp"); k_fl_rewarp<R><<<grid_tiles(E, k_fl_rewarp<R>), b, 0, s>>>(K, G_REGRID, d_Iref, (const R *)E->cur_Imov, B_LVL_NEXT, (vec2_t<R> *)E->gradI, (R *)E->It, B_EST_NEXT); }
+            { ProfScope _pw(E->ctx, "regrid_rewarp"); pdl_launch(k_fl_rewarp<R>, grid_tiles(E, k_fl_rewarp<R>), b, 0, s, K, G_REGRID, d_Iref, (const R *)E->cur_Imov, B_LVL_NEXT, (vec2_t<R> *)E->gradI, (R *)E->It, B_EST_NEXT); }
             OF2D_LAUNCH_CHECK(E->ctx);
-            k_regrid_commit<<<ceil_div(K.batch, 128), 128, 0, s>>>(K.ctl, K.batch);
+            pdl_launch(k_regrid_commit, ceil_div(K.batch, 128), 128, 0, s, K.ctl, K.batch);
             OF2D_LAUNCH_CHECK(E->ctx);
             break;
         }
@@ -208,7 +208,7 @@ int enqueue_hs_pair(of2d_engine *E, const EngK<R> &K) {
     cudaStream_t s = E->ctx->stream;
     const dim3 b(TX, TY);
     const R alpha = (R)E->d.alpha;
-    { ProfScope _ps(E->ctx, "hs_pair"); k_hs_pair<R><<<grid_tiles(E, k_hs_pair<R>), b, 0, s>>>(K, (const vec2_t<R> *)E->gradI, (const R *)E->It, alpha * alpha); }
+    { ProfScope _ps(E->ctx, "hs_pair"); pdl_launch(k_hs_pair<R>, grid_tiles(E, k_hs_pair<R>), b, 0, s, K, (const vec2_t<R> *)E->gradI, (const R *)E->It, alpha * alpha); }
     OF2D_LAUNCH_CHECK(E->ctx);
     return OF2D_SUCCESS;
 }
@@ -233,12 +233,12 @@ int refine_impl(of2d_engine *E, const R *d_Iref, const R *d_Imov, R *d_motion, i
 
     // ---- set-up: Iaux = Imov o (id + motion); derivatives; estimate = 0 (e.g. ImageRegistrationDemons.cpp:97-106)
     OF2D_CUDA_TRY(cudaMemcpyAsync(E->lvl[0], d_motion, vbytes, cudaMemcpyDeviceToDevice, s));
-    k_ctl_begin<<<ceil_div(K.batch, 128), 128, 0, s>>>(K.ctl, K.batch, niter, K.n_active);
+    pdl_launch(k_ctl_begin, ceil_div(K.batch, 128), 128, 0, s, K.ctl, K.batch, niter, K.n_active);
     OF2D_LAUNCH_CHECK(ctx);
-    k_e_warp<R><<<grid_tiles(E, k_e_warp<R>), b, 0, s>>>(K, G_NONE, d_Imov, B_LVL_CUR, (R *)E->aux);
+    pdl_launch(k_e_warp<R>, grid_tiles(E, k_e_warp<R>), b, 0, s, K, G_NONE, d_Imov, B_LVL_CUR, (R *)E->aux);
     OF2D_LAUNCH_CHECK(ctx);
     if (d.method != 3 && d.method != 4) {
-        k_e_derivatives<R><<<grid_tiles(E, k_e_derivatives<R>), b, 0, s>>>(K, G_NONE, d_Iref, (const R *)E->aux, (vec2_t<R> *)E->gradI, (R *)E->It, E->transposed ? 1 : 0);
+        pdl_launch(k_e_derivatives<R>, grid_tiles(E, k_e_derivatives<R>), b, 0, s, K, G_NONE, d_Iref, (const R *)E->aux, (vec2_t<R> *)E->gradI, (R *)E->It, E->transposed ? 1 : 0);
         OF2D_LAUNCH_CHECK(ctx);
     }
     const size_t eb = E->transposed ? vbytesT : vbytes;
@@ -275,15 +275,15 @@ int refine_impl(of2d_engine *E, const R *d_Iref, const R *d_Imov, R *d_motion, i
     // on the test, the error being within rounding of 0.001); an empty launch otherwise
     if (d.method == 0 && niter >= 2 && hs_pair_enabled()) {
         const R alpha = (R)d.alpha;
-        { ProfScope _ps(E->ctx, "hs_iter"); k_hs_iter<R><<<grid_tiles(E, k_hs_iter<R>), b, 0, s>>>(K, (const vec2_t<R> *)E->gradI, (const R *)E->It, alpha * alpha, 2); }
+        { ProfScope _ps(E->ctx, "hs_iter"); pdl_launch(k_hs_iter<R>, grid_tiles(E, k_hs_iter<R>), b, 0, s, K, (const vec2_t<R> *)E->gradI, (const R *)E->It, alpha * alpha, 2); }
         OF2D_LAUNCH_CHECK(ctx);
     }
 
     // ---- tear-down: motion <- estimate + motion o (id + estimate); the estimate is dropped (:136-137)
     if (E->transposed) {   // the estimate lives in the transposed working layout: its tiles are turned in shared memory
-        { ProfScope _pc(E->ctx, "final_compose"); k_e_compose<R, true><<<grid_tiles(E, k_e_compose<R, true>), b, 0, s>>>(K, G_NONE, B_LVL_CUR, B_EST_CUR, B_EXT, 0); }
+        { ProfScope _pc(E->ctx, "final_compose"); pdl_launch(k_e_compose<R, true>, grid_tiles(E, k_e_compose<R, true>), b, 0, s, K, G_NONE, B_LVL_CUR, B_EST_CUR, B_EXT, 0); }
     } else {
-        { ProfScope _pc(E->ctx, "final_compose"); k_e_compose<R, false><<<grid_tiles(E, k_e_compose<R, false>), b, 0, s>>>(K, G_NONE, B_LVL_CUR, B_EST_CUR, B_EXT, 0); }
+        { ProfScope _pc(E->ctx, "final_compose"); pdl_launch(k_e_compose<R, false>, grid_tiles(E, k_e_compose<R, false>), b, 0, s, K, G_NONE, B_LVL_CUR, B_EST_CUR, B_EXT, 0); }
     }
     OF2D_LAUNCH_CHECK(ctx);
     OF2D_CUDA_TRY(cudaMemcpyAsync(E->h_ctl.data(), E->d_ctl, sizeof(PairCtl) * K.batch, cudaMemcpyDeviceToHost, s));

@@ -137,6 +137,7 @@ __device__ __forceinline__ void logger_epilogue(const EngK<R> &K, PairCtl *c, in
 // control
 // ---------------------------------------------------------------------------------------------
 __global__ void k_ctl_begin(PairCtl *ctl, int batch, int niter, int *n_active) {
+    pdl_enter();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p == 0) *n_active = niter > 0 ? batch : 0;
     if (p >= batch) return;
@@ -158,6 +159,7 @@ __global__ void k_ctl_begin(PairCtl *ctl, int batch, int niter, int *n_active) {
 }
 
 __global__ void k_regrid_commit(PairCtl *ctl, int batch) {
+    pdl_enter();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= batch) return;
     PairCtl *c = ctl + p;
@@ -176,6 +178,7 @@ __global__ void k_regrid_commit(PairCtl *ctl, int batch) {
 // launch; 2 = the closing launch of a refine pass: a plain iteration that also serves a pending redo
 template <class R>
 __global__ void __launch_bounds__(TX *TY) k_hs_iter(EngK<R> K, const vec2_t<R> *__restrict__ gradI_all, const R *__restrict__ It_all, R alphasq, int fixup) {
+    pdl_enter();
     const int pair = blockIdx.y;
     PairCtl *c = K.ctl + pair;
     const CtlHot h = load_ctl(c);
@@ -284,6 +287,7 @@ __device__ __forceinline__ vec2_t<R> hs_point(vec2_t<R> a, vec2_t<R> b, vec2_t<R
 
 template <class R>
 __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 3 : 2) k_hs_pair(EngK<R> K, const vec2_t<R> *__restrict__ gradI_all, const R *__restrict__ It_all, R alphasq) {
+    pdl_enter();
     constexpr int H0 = TILE + 4, H1 = TILE + 2, NRING = 4 * H1 - 4;
     __shared__ vec2_t<R> s0[H0 * H0];   // u^k on the 36 x 36 halo tile
     __shared__ vec2_t<R> s1[H1 * H1];   // u^(k+1) on the 34 x 34 halo tile
@@ -409,6 +413,7 @@ __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 3 : 2) k_hs_pair(EngK
 // ---------------------------------------------------------------------------------------------
 template <class R>
 __global__ void __launch_bounds__(TX *TY) k_e_warp(EngK<R> K, int gate, const R *__restrict__ src_all, int u_buf, R *__restrict__ dst_all) {
+    pdl_enter();
     const int pair = blockIdx.y;
     const CtlHot h = load_ctl(K.ctl + pair);
     if (!gate_open(h, gate)) return;
@@ -437,6 +442,7 @@ __global__ void __launch_bounds__(TX *TY) k_e_warp(EngK<R> K, int gate, const R 
 // in shared memory, so the Fluid regrid composes straight from the running estimate (no untransposed copy)
 template <class R, bool VT>
 __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 4 : 1) k_e_compose(EngK<R> K, int gate, int u_buf, int v_buf, int out_buf, int add_only) {
+    pdl_enter();
     __shared__ vec2_t<R> sT[VT ? TILE : 1][VT ? TILE + 1 : 1];
     const int pair = blockIdx.y;
     const CtlHot h = load_ctl(K.ctl + pair);
@@ -502,6 +508,7 @@ __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 4 : 1) k_e_compose(En
 // a power of two, so scaling the taps on the fly is exact)
 template <class R>
 __global__ void __launch_bounds__(TX *TY) k_e_square(EngK<R> K, int s) {
+    pdl_enter();
     const int pair = blockIdx.y;
     const PairCtl *c = K.ctl + pair;
     const CtlHot h = load_ctl(c);
@@ -546,6 +553,7 @@ template <class R>
 // inv_sigma_xsq: 1 / sigma_xsq when sigma_xsq is a power of two (x / 2^k == x * 2^-k exactly, so the multiplication gives the
 // reference's bits without the IEEE division sequence), else 0
 __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 8 : 1) k_e_demons_force(EngK<R> K, const R *__restrict__ Iref_all, const R *__restrict__ Imov_all, R sigma_isq, R sigma_xsq, R inv_sigma_xsq) {
+    pdl_enter();
     __shared__ R sw[TILE + 2][TILE + 2 + 1];
     const int pair = blockIdx.y;
     PairCtl *c = K.ctl + pair;
@@ -640,6 +648,7 @@ struct ConvW {
 
 template <class R, int EPI, int KW>
 __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 5 : 1) k_e_conv(EngK<R> K, int src_buf, int dst_buf, const __grid_constant__ ConvW<R> W, int nsq_cap) {
+    pdl_enter();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int pair = blockIdx.y;
     PairCtl *c = K.ctl + pair;
@@ -851,6 +860,7 @@ __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 5 : 1) k_e_conv(EngK<
 template <class R>
 __global__ void __launch_bounds__(TX *TY) k_e_derivatives(EngK<R> K, int gate, const R *__restrict__ Iref_all, const R *__restrict__ Imov_all,
                                                           vec2_t<R> *__restrict__ gradI_all, R *__restrict__ It_all, int transposed) {
+    pdl_enter();
     __shared__ vec2_t<R> sg[TILE][TILE + 1];
     __shared__ R st[TILE][TILE + 1];
     const int pair = blockIdx.y;
@@ -904,6 +914,7 @@ __global__ void __launch_bounds__(TX *TY) k_e_derivatives(EngK<R> K, int gate, c
 // (Image.cpp:189-218, :96-104) + break / regrid decisions (ImageRegistrationFluid.cpp:99-124)
 template <class R>
 __global__ void __launch_bounds__(TX *TY) k_fl_integrate(EngK<R> K, const vec2_t<R> *__restrict__ incr_all) {
+    pdl_enter();
     const int pair = blockIdx.y;
     PairCtl *c = K.ctl + pair;
     const CtlHot h = load_ctl(c);
@@ -1034,6 +1045,7 @@ __global__ void __launch_bounds__(TX *TY) k_fl_integrate(EngK<R> K, const vec2_t
 template <class R>
 __global__ void __launch_bounds__(TX *TY) k_fl_rewarp(EngK<R> K, int gate, const R *__restrict__ Iref_all, const R *__restrict__ Imov_all, int u_buf,
                                                       vec2_t<R> *__restrict__ gradI_all, R *__restrict__ It_all, int zero_buf) {
+    pdl_enter();
     __shared__ R sw[TILE + 2][TILE + 2 + 1];
     __shared__ vec2_t<R> sg[TILE][TILE + 1];
     __shared__ R st[TILE][TILE + 1];
