@@ -181,7 +181,7 @@ def workload_config(size: int) -> dict:
 KERNEL_BYTES_PER_PX = {
     "hs_iter": 28, "hs_pair": 28, "conv": 16, "conv_logger": 24, "conv_maxabs": 16, "demons_force": 24, "compose": 24, "square": 16,
     "sor_tile_elastic": 28, "sor_tile_fluid": 44, "fluid_integrate": 24,
-    "curv_rows_fwd": 36, "curv_cols": 32, "curv_rows_inv": 32, "regrid_compose": 24, "regrid_rewarp": 36, "final_compose": 24,
+    "curv_rows_fwd": 36, "curv_cols": 32, "curv_rows_inv": 32, "curv_rows_inv_fwd": 60, "regrid_compose": 24, "regrid_rewarp": 36, "final_compose": 24,
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/), 2048^2 fp32
 NCU_TRAFFIC_BYTES = {}

@@ -402,8 +402,9 @@ struct of2d_curvature_plan {
 namespace {
 
 // dct_reg.cuh: register-blocked radix-16 path (both line lengths in 512 .. 4096)
+// fuse_next: the inverse row pass also runs the forward row pass of the next iteration (k_rg_rows_inv<.., FUSE>)
 template <class R, int LX>
-int launch_reg_rows(of2d_curvature_plan *P, bool fwd, const R *u, R *unew, const R *gradI, const R *It, const CurvHook &H, int batch) {
+int launch_reg_rows(of2d_curvature_plan *P, bool fwd, const R *u, R *unew, const R *gradI, const R *It, const CurvHook &H, int batch, bool fuse_next = false) {
     of2d_ctx *ctx = P->ctx;
     constexpr int LPC = 2, NT = LPC * rg::Geo<LX>::TPL;
     const size_t smem = sizeof(double2) * (size_t)P->nx * LPC;
@@ -414,11 +415,16 @@ int launch_reg_rows(of2d_curvature_plan *P, bool fwd, const R *u, R *unew, const
         ProfScope _ps(ctx, "curv_rows_fwd");
         pdl_launch(rg::k_rg_rows_fwd<R, LX, LPC>, dim3(P->ny / LPC, batch), NT, smem, ctx->stream, P->ny, (const vec2_t<R> *)u, (const vec2_t<R> *)unew, (const vec2_t<R> *)gradI, It,
                                                                                        (R)P->tau, (double2 *)P->d_spec, (const double2 *)P->Tx.q, T, H);
+    } else if (fuse_next) {
+        { int st = of2d_ensure_dynamic_smem((const void *)rg::k_rg_rows_inv<R, LX, LPC, true>, smem); if (st) return st; }
+        ProfScope _ps(ctx, "curv_rows_inv_fwd");
+        pdl_launch(rg::k_rg_rows_inv<R, LX, LPC, true>, dim3(P->ny / LPC, batch), NT, smem, ctx->stream, P->ny, (const double2 *)P->d_spec2, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN,
+                   (const double2 *)P->Tx.q, T, H, (const vec2_t<R> *)gradI, It, (R)P->tau, (double2 *)P->d_spec);
     } else {
-        { int st = of2d_ensure_dynamic_smem((const void *)rg::k_rg_rows_inv<R, LX, LPC>, smem); if (st) return st; }
+        { int st = of2d_ensure_dynamic_smem((const void *)rg::k_rg_rows_inv<R, LX, LPC, false>, smem); if (st) return st; }
         ProfScope _ps(ctx, "curv_rows_inv");
-        pdl_launch(rg::k_rg_rows_inv<R, LX, LPC>, dim3(P->ny / LPC, batch), NT, smem, ctx->stream, P->ny, (const double2 *)P->d_spec2, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN,
-                                                                                       (const double2 *)P->Tx.q, T, H);
+        pdl_launch(rg::k_rg_rows_inv<R, LX, LPC, false>, dim3(P->ny / LPC, batch), NT, smem, ctx->stream, P->ny, (const double2 *)P->d_spec2, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN,
+                   (const double2 *)P->Tx.q, T, H, (const vec2_t<R> *)nullptr, (const R *)nullptr, (R)0, (double2 *)nullptr);
     }
     OF2D_LAUNCH_CHECK(ctx);
     return OF2D_SUCCESS;
@@ -436,11 +442,14 @@ int launch_reg_cols(of2d_curvature_plan *P, const CurvHook &H, int batch) {
     OF2D_LAUNCH_CHECK(ctx);
     return OF2D_SUCCESS;
 }
+// flags (engine loop only): OF2D_CURV_SKIP_FWD = the forward row pass of this iteration was already run by the previous
+// iteration's fused inverse pass; OF2D_CURV_FUSE_NEXT = this iteration's inverse pass runs the next iteration's forward pass
 template <class R>
-int curvature_step_reg(of2d_curvature_plan *P, const R *u, R *unew, const R *gradI, const R *It, const CurvHook &H) {
+int curvature_step_reg(of2d_curvature_plan *P, const R *u, R *unew, const R *gradI, const R *It, const CurvHook &H, int flags) {
     const int batch = H.enabled ? P->batch : 1;
     int st = OF2D_SUCCESS;
-    for (int phase = 0; phase < 3 && st == OF2D_SUCCESS; phase++) {
+    const bool fuse_next = H.enabled && (flags & OF2D_CURV_FUSE_NEXT);
+    for (int phase = (H.enabled && (flags & OF2D_CURV_SKIP_FWD)) ? 1 : 0; phase < 3 && st == OF2D_SUCCESS; phase++) {
         if (phase == 1) {
             switch (P->Ty.log2n) {
                 case 9: st = launch_reg_cols<9>(P, H, batch); break;
@@ -450,10 +459,10 @@ int curvature_step_reg(of2d_curvature_plan *P, const R *u, R *unew, const R *gra
             }
         } else {
             switch (P->Tx.log2n) {
-                case 9: st = launch_reg_rows<R, 9>(P, phase == 0, u, unew, gradI, It, H, batch); break;
-                case 10: st = launch_reg_rows<R, 10>(P, phase == 0, u, unew, gradI, It, H, batch); break;
-                case 11: st = launch_reg_rows<R, 11>(P, phase == 0, u, unew, gradI, It, H, batch); break;
-                default: st = launch_reg_rows<R, 12>(P, phase == 0, u, unew, gradI, It, H, batch); break;
+                case 9: st = launch_reg_rows<R, 9>(P, phase == 0, u, unew, gradI, It, H, batch, phase == 2 && fuse_next); break;
+                case 10: st = launch_reg_rows<R, 10>(P, phase == 0, u, unew, gradI, It, H, batch, phase == 2 && fuse_next); break;
+                case 11: st = launch_reg_rows<R, 11>(P, phase == 0, u, unew, gradI, It, H, batch, phase == 2 && fuse_next); break;
+                default: st = launch_reg_rows<R, 12>(P, phase == 0, u, unew, gradI, It, H, batch, phase == 2 && fuse_next); break;
             }
         }
     }
@@ -461,13 +470,13 @@ int curvature_step_reg(of2d_curvature_plan *P, const R *u, R *unew, const R *gra
 }
 
 template <class R, class S>
-int curvature_step_impl(of2d_curvature_plan *P, const R *u, R *unew, const R *gradI, const R *It, const CurvHook &H) {
+int curvature_step_impl(of2d_curvature_plan *P, const R *u, R *unew, const R *gradI, const R *It, const CurvHook &H, int flags = 0) {
     of2d_ctx *ctx = P->ctx;
     const int batch = H.enabled ? P->batch : 1;
     const int nx = P->nx, ny = P->ny;
     cplx_t<S> *spec = (cplx_t<S> *)P->d_spec;
     const R fourN = (R)4.0f * (R)(unsigned)(nx * ny);
-    if (P->Tx.tw16a && P->Ty.tw16a && !getenv("OF2D_NO_REG_FFT")) return curvature_step_reg<R>(P, u, unew, gradI, It, H);
+    if (P->Tx.tw16a && P->Ty.tw16a && !getenv("OF2D_NO_REG_FFT")) return curvature_step_reg<R>(P, u, unew, gradI, It, H, flags);
     constexpr int LPC = 2;
     const bool fast = P->Tx.pow2 && P->Ty.pow2 && P->Tx.log2n >= 6 && P->Ty.log2n >= 6 && sizeof(double2) * (size_t)nx * LPC <= kMaxSmem &&
                       sizeof(double2) * (size_t)ny <= kMaxSmem;
@@ -593,11 +602,17 @@ int of2d_curvature_plan_set_batch(of2d_curvature_plan *P, int batch) {
 }
 
 int of2d_curvature_engine_step(of2d_curvature_plan *P, PairCtl *ctl, int *n_active, double *partials, size_t pstride, TraceDev tr, void *est0, void *est1,
-                               const void *gradI, const void *It) {
+                               const void *gradI, const void *It, int flags) {
     CurvHook H;
     H.ctl = ctl; H.n_active = n_active; H.partials = partials; H.pstride = pstride; H.tr = tr; H.enabled = 1;
-    if (P->real_is_double) return curvature_step_impl<double, double>(P, (const double *)est0, (double *)est1, (const double *)gradI, (const double *)It, H);
-    return curvature_step_impl<float, double>(P, (const float *)est0, (float *)est1, (const float *)gradI, (const float *)It, H);
+    if (P->real_is_double) return curvature_step_impl<double, double>(P, (const double *)est0, (double *)est1, (const double *)gradI, (const double *)It, H, flags);
+    return curvature_step_impl<float, double>(P, (const float *)est0, (float *)est1, (const float *)gradI, (const float *)It, H, flags);
+}
+int of2d_curvature_plan_fuses_rows(const of2d_curvature_plan *P) {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("OF2D_CURV_FUSE"); on = e ? atoi(e) != 0 : 1; }
+    // fp32 fields only: in fp64 the fused kernel holds the new estimate as 16 more double2 registers and spills at 2048 / 4096
+    return on && !P->real_is_double && P->Tx.tw16a && P->Ty.tw16a && !getenv("OF2D_NO_REG_FFT");
 }
 
 extern "C" {

@@ -327,9 +327,14 @@ __global__ void __launch_bounds__(2 * Geo<L>::TPL, 2 * Geo<L>::TPL <= 256 ? 2 : 
 }
 
 // ---- P3: LPC rows per CTA.  DCT-III along x, u' = rhs / (4 N), Logger epilogue ------------------------------------------
-template <class R, int L, int LPC>
+// FUSE: the kernel goes on with P1 of the NEXT iteration on the same rows -- rhs = u' - tau f(u') from the registers that
+// hold u' (same pixel-pair mapping as k_rg_rows_fwd), DCT-II along x, spectrum written transposed -- so an iteration is
+// two launches (columns, rows) and u' is not read back.  The forward part runs whatever the Logger decides: if the
+// loop ends here its spectrum is simply never used.
+template <class R, int L, int LPC, bool FUSE>
 __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 2 : 1) k_rg_rows_inv(int ny, const double2 *__restrict__ specN, vec2_t<R> *est0, vec2_t<R> *est1, R fourN,
-                                                                   const double2 *__restrict__ q, Tw16 T, CurvHook H) {
+                                                                   const double2 *__restrict__ q, Tw16 T, CurvHook H, const vec2_t<R> *__restrict__ gradI,
+                                                                   const R *__restrict__ It, R tau, double2 *__restrict__ specT) {
     pdl_enter();
     using G = Geo<L>;
     constexpr int N = G::N;
@@ -392,6 +397,7 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
     if constexpr (PREFETCH) fft_inv<L>(a, x + l * N, u, k, T, fetch_prev);
     else { fft_inv<L>(a, x + l * N, u, k, T); fetch_prev(); }
     double sd = 0.0, sp = 0.0;
+    vec2_t<R> ue[FUSE ? 8 : 1], uo[FUSE ? 8 : 1];   // FUSE: the new estimate at the thread's 8 pixel pairs
     {
 #pragma unroll
         for (int qq = 0; qq < 8; qq++) {
@@ -401,6 +407,7 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
             const vec2_t<R> os = mk2<R>((R)vs.x / fourN, (R)vs.y / fourN);
             const vec2_t<R> o1 = mk2<R>(__shfl_xor_sync(0xffffffffu, os.x, 16), __shfl_xor_sync(0xffffffffu, os.y, 16));
             store_px_pair<R>(unew + row + 2 * (k + G::S1 * qq), o0, o1);
+            if (FUSE) { ue[qq] = o0; uo[qq] = o1; }
             if (H.enabled) {
                 const vec2_t<R> p0 = pv[2 * qq], p1 = pv[2 * qq + 1];
                 const vec2_t<R> d0 = mk2<R>(o0.x - p0.x, o0.y - p0.y), d1 = mk2<R>(o1.x - p1.x, o1.y - p1.y);
@@ -412,6 +419,32 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
                     sp += sqrt((double)(p0.x * p0.x + p0.y * p0.y)) + sqrt((double)(p1.x * p1.x + p1.y * p1.y));
                 }
             }
+        }
+    }
+    if constexpr (FUSE) {
+        // P1 of the next iteration (k_rg_rows_fwd) on the new estimate held in registers
+        gradI += pair_off; It += pair_off; specT += pair_off;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const size_t g = row + 2 * (k + G::S1 * j);
+            vec2_t<R> g0, g1; R t0, t1;
+            load_px_pair<R>(gradI + g, g0, g1); load_s_pair<R>(It + g, t0, t1);
+            const vec2_t<R> u0 = ue[j], u1 = uo[j];
+            const vec2_t<R> f0 = lssd_force<R>(g0, t0, u0), f1 = lssd_force<R>(g1, t1, u1);                  // OpticalFlow.cpp:33
+            const R ex = u0.x - tau * f0.x, ey = u0.y - tau * f0.y, ox = u1.x - tau * f1.x, oy = u1.y - tau * f1.y;   // OpticalFlowCurvature.cpp:90-91
+            a[j] = make_double2((double)ex, (double)ey);
+            a[15 - j] = make_double2((double)__shfl_xor_sync(0xffffffffu, ox, 16), (double)__shfl_xor_sync(0xffffffffu, oy, 16));
+        }
+        __syncthreads();   // every thread has left the last shared-memory phase of the inverse transform
+        fft_fwd<L>(a, x + l * N, u, k, T);
+        constexpr int hp = (N >> 1) + 1;
+        for (int e = tid; e < LPC * hp; e += LPC * G::TPL) {
+            const int ll = e % LPC, kk = e / LPC, nk = (N - kk) & (N - 1);
+            const double2 *base = x + ll * N;
+            double2 ok, on;
+            post_pair(base[swz(G::pos(kk))], base[swz(G::pos(nk))], q[kk], ok, on);
+            specT[(size_t)kk * ny + j0 + ll] = ok;
+            if (nk != kk) specT[(size_t)nk * ny + j0 + ll] = on;
         }
     }
     if (!H.enabled) return;

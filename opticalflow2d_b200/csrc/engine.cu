@@ -136,7 +136,7 @@ int launch_conv(of2d_engine *E, const EngK<R> &K, int src, int dst, int which) {
 
 // one iteration of method `m`, enqueued on the context's stream
 template <class R>
-int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
+int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref, int curv_flags = 0) {
     cudaStream_t s = E->ctx->stream;
     const dim3 b(TX, TY);
     const of2d_engine_desc &d = E->d;
@@ -148,7 +148,7 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
             break;
         }
         case 1:
-            TRY(of2d_curvature_engine_step(E->plan, K.ctl, K.n_active, K.partials, K.pstride, K.tr, E->est[0], E->est[1], E->gradI, E->It));
+            TRY(of2d_curvature_engine_step(E->plan, K.ctl, K.n_active, K.partials, K.pstride, K.tr, E->est[0], E->est[1], E->gradI, E->It, curv_flags));
             break;
         case 2:
             TRY(sor_tile_launch<R>(E->ctx, E->sor, K.ctl, K.n_active, K.partials, K.pstride, K.tr, 0, (vec2_t<R> *)E->est[0], (vec2_t<R> *)E->est[1], nullptr, nullptr,
@@ -254,7 +254,13 @@ int refine_impl(of2d_engine *E, const R *d_Iref, const R *d_Imov, R *d_motion, i
         const int m = niter - enq < chunk ? niter - enq : chunk;
         for (int q = 0; q < m;) {
             if (d.method == 0 && m - q >= 2 && hs_pair_enabled()) { TRY(enqueue_hs_pair<R>(E, K)); q += 2; }
-            else { TRY(enqueue_iteration<R>(E, K, d_Iref)); q += 1; }
+            else {
+                // Curvature (register-blocked path): iteration k's inverse row pass runs iteration k+1's forward row pass
+                int cf = 0;
+                if (d.method == 1 && of2d_curvature_plan_fuses_rows(E->plan)) cf = (enq + q > 0 ? OF2D_CURV_SKIP_FWD : 0) | (enq + q + 1 < niter ? OF2D_CURV_FUSE_NEXT : 0);
+                TRY(enqueue_iteration<R>(E, K, d_Iref, cf));
+                q += 1;
+            }
         }
         enq += m;
         E->iterations_enqueued += (uint64_t)m;
