@@ -610,9 +610,10 @@ int of2d_curvature_engine_step(of2d_curvature_plan *P, PairCtl *ctl, int *n_acti
 }
 int of2d_curvature_plan_fuses_rows(const of2d_curvature_plan *P) {
     static int on = -1;
-    if (on < 0) { const char *e = getenv("OF2D_CURV_FUSE"); on = e ? atoi(e) != 0 : 1; }
-    // fp32 fields only: in fp64 the fused kernel holds the new estimate as 16 more double2 registers and spills at 2048 / 4096
-    return on && !P->real_is_double && P->Tx.tw16a && P->Ty.tw16a && !getenv("OF2D_NO_REG_FFT");
+    if (on < 0) { const char *e = getenv("OF2D_CURV_FUSE"); on = e ? atoi(e) : 1; }
+    // fp32 fields by default: in fp64 the fused kernel holds the new estimate as 16 more double2 registers and spills at
+    // 2048 / 4096 (OF2D_CURV_FUSE=2 fuses there too)
+    return on && (on >= 2 || !P->real_is_double) && P->Tx.tw16a && P->Ty.tw16a && !getenv("OF2D_NO_REG_FFT");
 }
 
 extern "C" {
