@@ -75,3 +75,27 @@ def test_batch_early_convergence_is_per_pair():
         b.estimate()
         its, _ = b.iterations()
     assert its[1] == 3 and its[0] > 3 and its[2] > 3, its
+
+
+def test_batch_two_step_diffusion_breaks_per_pair():
+    """Diffusion runs two Jacobi steps per launch (k_hs_pair).  The pair of identical images meets the break test on the
+    FIRST step of the second launch (iteration index 2): that launch must leave its state alone and the next one redo the
+    single step for this pair only, while its neighbours in the batch go on two steps at a time."""
+    dimx, dimy, niter = 64, 64, 31
+    of.set_strict(False, 32)
+    R, T = _pairs(3, dimx, dimy)
+    T[1] = R[1]
+    with of.Batch((dimx, dimy), 3, niter, of.DIFFUSION, [0.5], wave=3) as b:
+        b.set_images(R, T)
+        b.estimate()
+        got = b.motion()
+        its, _ = b.iterations()
+    assert its[1] == 3 and its[0] > 3 and its[2] > 3, its
+    for k in range(3):
+        with of.Session((dimx, dimy), [niter], 0, of.DIFFUSION, [0.5], nrefine=1, verbose=0, bits=32) as s:
+            s.set_images(R[k], T[k])
+            s.estimate()
+            assert s.trace()["total_iterations"] == its[k]
+            assert maxdiff(got[k], s.motion()) == 0.0
+    want = oracle(32).register(R[0], T[0], of.DIFFUSION, [0.5], [niter], nscales=0, nrefine=1, verbose=1)
+    assert len(want["err"]) == its[0] and maxdiff(got[0], want["motion"]) == 0.0
