@@ -60,11 +60,38 @@ struct SorTileArgs {
     const vec2_t<R> *gradI;
     const R *It;
     R ck, cr, mu, mupl, a;
+    float neg_zero;                // -0.0f, opaque to the compiler (PairOps<float>)
     PairCtl *ctl;
     int *n_active;
     double *partials;
     size_t pstride;
     TraceDev tr;
+};
+
+// Component-wise arithmetic on (x, y) pairs in the reference's rounding (a multiplication and an addition are two roundings).
+// fp32: the packed sm_100a instructions (SASS FFMA2 / FADD2, both components in one issue slot); the product is
+// fma(a, b, -0) with the -0 taken from a kernel argument, which rounds exactly like the multiplication (signed zeros
+// included) and keeps ptxas from contracting it with the addition that follows (it does contract mul.f32x2 + add.f32x2
+// even under -fmad=false).  fp64: plain component arithmetic.
+template <class R> struct PairOps;
+template <> struct PairOps<double> {
+    __device__ __forceinline__ explicit PairOps(float) {}
+    __device__ __forceinline__ double2 add(double2 a, double2 b) const { return make_double2(a.x + b.x, a.y + b.y); }
+    __device__ __forceinline__ double2 sub(double2 a, double2 b) const { return make_double2(a.x - b.x, a.y - b.y); }
+    __device__ __forceinline__ double2 mul(double2 a, double2 b) const { return make_double2(a.x * b.x, a.y * b.y); }
+    __device__ __forceinline__ double2 scale(double s, double2 a) const { return make_double2(s * a.x, s * a.y); }
+};
+template <> struct PairOps<float> {
+    unsigned long long nz2;
+    __device__ __forceinline__ explicit PairOps(float neg_zero) : nz2(pack_f32x2(neg_zero, neg_zero)) {}
+    __device__ __forceinline__ float2 add(float2 a, float2 b) const { return unpack_f32x2(add_f32x2(pack_f32x2(a.x, a.y), pack_f32x2(b.x, b.y))); }
+    __device__ __forceinline__ float2 sub(float2 a, float2 b) const {
+        unsigned long long r;
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pack_f32x2(a.x, a.y)), "l"(pack_f32x2(b.x, b.y)));
+        return unpack_f32x2(r);
+    }
+    __device__ __forceinline__ float2 mul(float2 a, float2 b) const { return unpack_f32x2(fma_f32x2(pack_f32x2(a.x, a.y), pack_f32x2(b.x, b.y), nz2)); }
+    __device__ __forceinline__ float2 scale(float s, float2 a) const { return unpack_f32x2(fma_f32x2(pack_f32x2(s, s), pack_f32x2(a.x, a.y), nz2)); }
 };
 
 template <class R, int RPT, bool FLUID, bool WARP>
@@ -150,6 +177,7 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
     const bool above_comp = (j0 + RPT >= jc0) && (j0 + RPT < jc1);
     const R a = A.a;
     const R aR = (a * a) * (a * a);
+    const PairOps<R> po(A.neg_zero);
 
     // rows j0-1 .. j0+RPT of the previous (new) column, rows j0-1 .. j0+RPT of the current (old) column
     V newW[RPT + 2], oldC[RPT + 2];
@@ -205,7 +233,7 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
         }
         // everything of the reference's expression that does not involve the cell below (S):
         //   o = ck C + cr (b - mu (((E + W) + N) + S) - mupl (E + W + 0.25 (NE' - NW' - SE' + SW')))
-        V ckC[RPT], bb[RPT], sum3[RPT], k2[RPT], d[RPT], xt[RPT], uC[RPT];
+        V ckC[RPT], bb[RPT], sum3[RPT], k2[RPT], mk2v[RPT], d[RPT], xt[RPT], uC[RPT];   // mk2v = mupl * k2
         V uS = mk2<R>((R)0, (R)0), uN = uS;   // fluid: u on the rows below / above the thread's block, this column (read before the stage is refilled)
         {
             const V *gs = st_g(sC);
@@ -218,12 +246,19 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
                 const V W = newW[r + 1], SW = newW[r], NW = newW[r + 2];
                 const V E = oldE[r + 1], SE = oldE[r], NE = oldE[r + 2];
                 uC[r] = FLUID ? us[r0 + r] : Cc;
-                bb[r] = lssd_force<R>(gs[r0 + r], ts[r0 + r], uC[r]);
-                const R ewx = E.x + W.x, ewy = E.y + W.y;
-                sum3[r] = mk2<R>(ewx + N.x, ewy + N.y);
-                k2[r] = mk2<R>(ewx + (R)0.25f * (NE.y - NW.y - SE.y + SW.y), ewy + (R)0.25f * (NE.x - NW.x - SE.x + SW.x));
-                ckC[r] = mk2<R>(A.ck * Cc.x, A.ck * Cc.y);
-                const V dd = mk2<R>(ckC[r].x + A.cr * (bb[r].x - A.mu * sum3[r].x - A.mupl * k2[r].x), ckC[r].y + A.cr * (bb[r].y - A.mu * sum3[r].y - A.mupl * k2[r].y));
+                {   // OpticalFlow::get_force (OpticalFlow.cpp:33): s = It + u.x dI.x + u.y dI.y; f = dI s
+                    const V dI = gs[r0 + r];
+                    const V pr = po.mul(uC[r], dI);
+                    const R sf = ts[r0 + r] + pr.x + pr.y;
+                    bb[r] = po.scale(sf, dI);
+                }
+                const V ew = po.add(E, W);
+                sum3[r] = po.add(ew, N);
+                const V cr4 = po.scale((R)0.25f, po.add(po.sub(po.sub(NE, NW), SE), SW));   // ((NE - NW) - SE) + SW per component
+                k2[r] = po.add(ew, mk2<R>(cr4.y, cr4.x));                                    // the x equation takes the y differences and vice versa
+                mk2v[r] = po.scale(A.mupl, k2[r]);
+                ckC[r] = po.scale(A.ck, Cc);
+                const V dd = po.add(ckC[r], po.scale(A.cr, po.sub(po.sub(bb[r], po.scale(A.mu, sum3[r])), mk2v[r])));
                 d[r] = comp[r] ? dd : Cc;
             }
         }
@@ -232,7 +267,7 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
 #pragma unroll
         for (int r = 1; r < RPT; r++) {
             const R ar = comp[r] ? a : (R)0;
-            xt[r] = mk2<R>(ar * xt[r - 1].x + d[r].x, ar * xt[r - 1].y + d[r].y);
+            xt[r] = po.add(po.scale(ar, xt[r - 1]), d[r]);
         }
         V carry = mk2<R>((R)0, (R)0);   // the new value of the row below the thread's block
         V d0_above = mk2<R>((R)0, (R)0);
@@ -248,7 +283,7 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
             for (int q = 0; q < MQ; q++) {
                 if (q < A.M) {
                     const R tx_ = __shfl_up_sync(0xffffffffu, top.x, q + 1), ty_ = __shfl_up_sync(0xffffffffu, top.y, q + 1);
-                    carry.x += cq[q] * tx_; carry.y += cq[q] * ty_;
+                    carry = po.add(carry, po.scale(cq[q], mk2<R>(tx_, ty_)));
                 }
             }
             d0_above.x = __shfl_down_sync(0xffffffffu, d[0].x, 1);
@@ -269,7 +304,7 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
 #pragma unroll
             for (int q = 0; q < MQ; q++) {
                 const V tv = pb[tqi[q]].top;
-                carry.x += cq[q] * tv.x; carry.y += cq[q] * tv.y;
+                carry = po.add(carry, po.scale(cq[q], tv));
             }
             if (t + 1 < NT) d0_above = pb[t + 1].d0;
         }
@@ -279,14 +314,14 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
             V S = carry;
 #pragma unroll
             for (int r = 0; r < RPT; r++) {
-                const V lit = mk2<R>(ckC[r].x + A.cr * (bb[r].x - A.mu * (sum3[r].x + S.x) - A.mupl * k2[r].x),
-                                     ckC[r].y + A.cr * (bb[r].y - A.mu * (sum3[r].y + S.y) - A.mupl * k2[r].y));
+                // ckC + cr (b - mu (sum3 + S) - mupl k2), OpticalFlowElastic.cpp:41-48 / OpticalFlowFluid.cpp:27-34
+                const V lit = po.add(ckC[r], po.scale(A.cr, po.sub(po.sub(bb[r], po.scale(A.mu, po.add(sum3[r], S))), mk2v[r])));
                 xn[r] = comp[r] ? lit : oldC[r + 1];
                 S = xn[r];
             }
         }
         V ntop;
-        if (t + 1 < NT) ntop = above_comp ? mk2<R>(a * xn[RPT - 1].x + d0_above.x, a * xn[RPT - 1].y + d0_above.y) : d0_above;
+        if (t + 1 < NT) ntop = above_comp ? po.add(po.scale(a, xn[RPT - 1]), d0_above) : d0_above;
         else ntop = oldC[RPT + 1];
         if (i >= is) {
             V uE[RPT];
@@ -303,21 +338,21 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
                     if (FLUID) {
                         // the increment of the NEW velocity, OpticalFlowFluid.cpp:60-90 (own cells are interior: central differences,
                         // gradients.h:9-32); border cells keep the 0 the buffer was created with (their velocity is never updated)
-                        const V a = uE[r], b = uW[r];
-                        const V dudx = mk2<R>((a.x - b.x) / (R)2.0f, (a.y - b.y) / (R)2.0f);
+                        // (x / 2 == x * 0.5 exactly)
+                        const V dudx = po.scale((R)0.5f, po.sub(uE[r], uW[r]));
                         const V nn = r + 1 < RPT ? uC[r + 1 < RPT ? r + 1 : r] : uN, ss = r > 0 ? uC[r > 0 ? r - 1 : 0] : uS;
-                        const V dudy = mk2<R>((nn.x - ss.x) / (R)2.0f, (nn.y - ss.y) / (R)2.0f);
+                        const V dudy = po.scale((R)0.5f, po.sub(nn, ss));
                         const V v = xn[r];
-                        const V rr = mk2<R>(v.x - dudx.x * v.x - dudy.x * v.y, v.y - dudx.y * v.x - dudy.y * v.y);
+                        const V rr = po.sub(po.sub(v, po.scale(v.x, dudx)), po.scale(v.y, dudy));   // (v - du/dx v.x) - du/dy v.y
                         incr[(size_t)i * P + j] = rr;
                         const R sm = maxabs_term<R>(rr);
                         mxr = mxr < sm ? sm : mxr;
                     }
                     if (!FLUID) {
                         const V oc = oldC[r + 1];
-                        const R dx = xn[r].x - oc.x, dy = xn[r].y - oc.y;
-                        if (sizeof(R) == 4) { sdf += sqrt_approx((float)(dx * dx + dy * dy)); spf += sqrt_approx((float)(oc.x * oc.x + oc.y * oc.y)); }   // Logger addends: as NormAcc (engine_kernels.cuh)
-                        else { sdd += sqrt((double)(dx * dx + dy * dy)); spd += sqrt((double)(oc.x * oc.x + oc.y * oc.y)); }
+                        const V df = po.sub(xn[r], oc), dsq = po.mul(df, df), osq = po.mul(oc, oc);
+                        if (sizeof(R) == 4) { sdf += sqrt_approx((float)(dsq.x + dsq.y)); spf += sqrt_approx((float)(osq.x + osq.y)); }   // Logger addends: as NormAcc (engine_kernels.cuh)
+                        else { sdd += sqrt((double)(dsq.x + dsq.y)); spd += sqrt((double)(osq.x + osq.y)); }
                     }
                 }
             }
@@ -438,6 +473,7 @@ static int sor_tile_launch(of2d_ctx *ctx, const SorPlan &S, PairCtl *ctl, int *n
     A.x[0] = x0; A.x[1] = x1; A.uf[0] = uf0; A.uf[1] = uf1; A.gradI = gradI; A.It = It; A.incr = incr;
     A.ck = (R)S.c_keep; A.cr = (R)S.c_relax; A.mu = (R)S.mu; A.mupl = (R)S.mupl;
     A.a = (R)(-S.c_relax * S.mu);
+    A.neg_zero = -0.0f;
     A.ctl = ctl; A.n_active = n_active; A.partials = partials; A.pstride = pstride; A.tr = tr;
     const bool fluid = which == 1;
     const size_t stage = (size_t)(A.LR + 4) * sizeof(vec2_t<R>) + (size_t)A.LR * (sizeof(vec2_t<R>) * (fluid ? 2 : 1) + sizeof(R));
