@@ -424,7 +424,8 @@ static inline SorPlan sor_plan(int nx, int ny, int batch, double mu, double lamb
     const double cr = fabs(S.c_relax);
     const double a = cr * fabs(mu), aW = cr * (fabs(mu) + fabs(mu + lambda)), aD = 0.25 * cr * fabs(mu + lambda);
     // eps: relative to the step of the iteration; 2^-46 puts the halo error ~2^-12 ulp below the field values
-    const double eps = dbl ? ldexp(1.0, -70) : ldexp(1.0, -40);
+    double eps = dbl ? ldexp(1.0, -70) : ldexp(1.0, -40);
+    { const char *e = getenv("OF2D_SOR_EPS_LOG2"); if (e && atoi(e) <= -20 && atoi(e) >= -100) eps = ldexp(1.0, atoi(e)); }   // halo truncation (tuning / experiments)
     S.supported = 1;
     if (!(a < 0.6) || !(aW + 2 * aD < 0.6) || !(1.0 - a - aW - aD > 0.15)) { S.supported = 0; return S; }
     const double rx = (aW + 2 * aD) / (1.0 - a), rs = a / (1.0 - aW - 2 * aD), rn = aD / (1.0 - a - aW - aD);
