@@ -10,7 +10,7 @@
 // cells further along the sweep decays geometrically: about 0.33 per column and 0.14 per row.  A tile
 // that starts the same sequential sweep HW columns to the west / HS rows to the south / HN rows to the
 // north of the cells it owns, taking OLD values on that outer ring, reproduces the exact sweep on its
-// own cells up to eps = 2^-34 (fp32) / 2^-62 (fp64) of the iteration's step size -- below half an ulp,
+// own cells up to eps = 2^-40 (fp32) / 2^-70 (fp64) of the iteration's step size (sor_plan) -- far below half an ulp,
 // i.e. bit-identical in practice (tests/test_engine_gpu.py compares with the exact wavefront kernel).
 // sor_plan() derives HW / HS / HN / M from the parameters and refuses (-> exact wavefront path) when
 // they do not contract fast enough.
@@ -36,7 +36,8 @@ struct SorPlan {
     int NT, RPT, NS;
     int BX, BY, HW, HS, HN, M;
     int nbands, nstrips;
-    double c_keep, c_relax, mu, mupl;
+    double c_keep, c_relax, mu, mupl;   // double copies: halo / contraction estimates only
+    double lambda, omega;               // the kernel's coefficients are formed in the field precision (sor_tile_launch)
     size_t nT;
     int supported;
 };
@@ -419,11 +420,11 @@ static inline SorPlan sor_plan(int nx, int ny, int batch, double mu, double lamb
     S.P = (ny + 3) & ~3;
     S.NS = SOR_NS;
     const double den = -6.0 * mu - 2.0 * lambda;
-    S.c_keep = 1.0 - omega; S.c_relax = den != 0 ? omega / den : 0.0; S.mu = mu; S.mupl = mu + lambda;
+    S.c_keep = 1.0 - omega; S.c_relax = den != 0 ? omega / den : 0.0; S.mu = mu; S.mupl = mu + lambda; S.lambda = lambda; S.omega = omega;
     if (den == 0 || nx < 3 || ny < 3) { S.supported = 0; return S; }
     const double cr = fabs(S.c_relax);
     const double a = cr * fabs(mu), aW = cr * (fabs(mu) + fabs(mu + lambda)), aD = 0.25 * cr * fabs(mu + lambda);
-    // eps: relative to the step of the iteration; 2^-46 puts the halo error ~2^-12 ulp below the field values
+    // eps: halo truncation relative to the step of the iteration: 2^-40 (fp32) / 2^-70 (fp64) keep the halo error ~2^-16 ulp below the field values
     double eps = dbl ? ldexp(1.0, -70) : ldexp(1.0, -40);
     { const char *e = getenv("OF2D_SOR_EPS_LOG2"); if (e && atoi(e) <= -20 && atoi(e) >= -100) eps = ldexp(1.0, atoi(e)); }   // halo truncation (tuning / experiments)
     S.supported = 1;
@@ -472,8 +473,15 @@ static int sor_tile_launch(of2d_ctx *ctx, const SorPlan &S, PairCtl *ctl, int *n
     A.LR = S.NT * S.RPT + 8;
     A.which = which;
     A.x[0] = x0; A.x[1] = x1; A.uf[0] = uf0; A.uf[1] = uf1; A.gradI = gradI; A.It = It; A.incr = incr;
-    A.ck = (R)S.c_keep; A.cr = (R)S.c_relax; A.mu = (R)S.mu; A.mupl = (R)S.mupl;
-    A.a = (R)(-S.c_relax * S.mu);
+    {   // the coefficients exactly as the reference's expression rounds them in the field precision
+        // (OpticalFlowElastic.cpp:41: (1.0f-omega), omega / (-6*mu-2*lambda), (mu+lambda)); same as the strict path, solvers.cu
+        const R mu = (R)S.mu, lambda = (R)S.lambda, omega = (R)S.omega;
+        A.ck = (R)1.0f - omega;
+        A.cr = omega / ((R)-6 * mu - (R)2 * lambda);
+        A.mu = mu;
+        A.mupl = mu + lambda;
+        A.a = -(A.cr * A.mu);
+    }
     A.neg_zero = -0.0f;
     A.ctl = ctl; A.n_active = n_active; A.partials = partials; A.pstride = pstride; A.tr = tr;
     const bool fluid = which == 1;

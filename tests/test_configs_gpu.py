@@ -1,0 +1,119 @@
+"""Parity on BASELINE.json's configurations AT THEIR OWN SIZES (-m gpu), against fixtures sampled from the COMPILED
+REFERENCE (tests/golden/make_golden_configs.py: oracle/_ref/libof2d_ref32.so, and libof2d_ref64.so = the reference after
+s/float/double/ for the fp64 mode):
+
+  config 2  Thirion 512^2, smooth deformation, 200 iterations          c2_thirion_512
+  config 3  Diffeomorphic 1024^2, sigma_x = 2 (squarings active)       c3_diffeomorphic_1024
+  config 4  2048^2 in fp64, all six methods                            full2048f64_*   (fp32: tests/test_fullsize_gpu.py)
+            2048^2 Fluid at caps 40 / 60 / 80 / 100, fp32 and fp64     full2048[f64]_fluid_c*
+  config 5  batch_pair(k) of 512^2, Thirion and Fluid, k = 0..7        c5[f64]_*_pair*
+  demo      Fluid, nscales 1, niter [25 25], 278 x 256                 demo_fluid_278x256   (test_opticalflow2d.m:23-38)
+
+Gates (north star): fp32 max |du| <= 1e-3 px and final SSD within 1e-4 relative; fp64 max |du| <= 1e-6 px; identical
+iteration counts and regrid traces.  STRICT mode must reproduce the compiled reference bit for bit everywhere.
+
+Fluid is ill-conditioned beyond ~60 iterations on these inputs (43 regrids in 100 iterations at 2048^2): the reference's
+OWN float and double builds differ by 4.6e-2 px at cap 80 and 0.2 px at cap 100 (regrid traces differ from event 32 on),
+and by up to 8.6e-3 px on the 512^2 batch pairs at cap 100.  Strict mode is bit-exact at every cap; the default (fast)
+mode -- whose tiled sweep perturbs the velocity by ~1 ulp -- is held to the north-star bar at the caps bench.py uses
+(2048^2: 40, where the reference's two builds still agree to 1.6e-4 px / 8e-5 in SSD; 512^2 batch pairs: 60) and, beyond,
+to 4x the reference's own fp32 <-> fp64 spread on the same case.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import opticalflow2d_b200 as of
+from golden import make_golden_configs as G
+
+pytestmark = pytest.mark.gpu
+
+CASES = {n: s for n, s in G.cases().items() if os.path.exists(os.path.join(G.GOLD, n + ".npz"))}
+
+
+def run(name, strict):
+    spec = CASES[name]
+    g = np.load(os.path.join(G.GOLD, name + ".npz"))
+    R, T = G.make_inputs(spec)
+    dimy, dimx = R.shape
+    bits = int(g["bits"])
+    of.set_strict(strict, bits)
+    try:
+        with of.Session((dimx, dimy), [int(v) for v in g["niter"]], int(g["nscales"]), int(g["reg"]), list(g["regparams"]),
+                        nrefine=1, verbose=0, bits=bits) as s:
+            s.set_images(R, T)
+            s.estimate()
+            mo, tr, warped = s.motion(), s.trace(), s.warp(T)
+    finally:
+        of.set_strict(False, bits)
+    st, off = int(g["stride"]), int(g["offset"])
+    err = np.concatenate([l["err"] for l in tr["levels"]])
+    rg = np.concatenate([np.asarray(l["regrid_iter"], dtype=int) for l in tr["levels"]])
+    return dict(g=g, bits=bits, du=float(np.abs(mo[off::st, off::st] - g["sample"].astype(np.float64)).max()), mo=mo, err=err, regrid=rg,
+                iters=int(tr["total_iterations"]), ssd1=float(((warped - R) ** 2).sum()))
+
+
+def ref_spread(name):
+    """The reference's own sensitivity to rounding on this case: (max |du| on the samples, relative SSD difference, same regrid
+    trace?) between its fp32 and fp64 builds; None if the twin fixture is absent."""
+    twin = name.replace("f64_", "_", 1) if "f64_" in name else name.replace("_", "f64_", 1)
+    pa, pb = os.path.join(G.GOLD, name + ".npz"), os.path.join(G.GOLD, twin + ".npz")
+    if not os.path.exists(pb):
+        return None
+    a, b = np.load(pa), np.load(pb)
+    if a["sample"].shape != b["sample"].shape:
+        return None
+    return (float(np.abs(a["sample"].astype(np.float64) - b["sample"].astype(np.float64)).max()),
+            abs(float(a["ssd1"]) - float(b["ssd1"])) / float(b["ssd1"]),
+            bool(np.array_equal(a["regrid_iter"], b["regrid_iter"]) and len(a["err"]) == len(b["err"])))
+
+
+# the caps bench.py runs Fluid at: there the reference agrees with its own fp64 build to the north-star tolerances, and so must we
+BENCH_FLUID = ["full2048_fluid_c40"] + [f"c5_fluid_c60_pair{k}" for k in G.C5_PAIRS]
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_fast_mode_matches_compiled_reference(name):
+    r = run(name, strict=False)
+    g, spec = r["g"], CASES[name]
+    tol_du = 1e-3 if r["bits"] == 32 else 1e-6
+    tol_ssd = 1e-4 if r["bits"] == 32 else 1e-9
+    same_trace = True
+    if spec["method"] == "fluid" and r["bits"] == 32 and name not in BENCH_FLUID[:1]:
+        # Fluid amplifies rounding noise: beyond the north-star tolerance fast mode is held to the reference's OWN fp32 <-> fp64
+        # spread on the same case (where its two builds take different regrid decisions the trace is not a property of the method)
+        sp = ref_spread(name)
+        if sp is not None:
+            tol_du, tol_ssd, same_trace = max(tol_du, 4.0 * sp[0]), max(tol_ssd, 4.0 * sp[1]), sp[2]
+    if same_trace:
+        assert r["iters"] == len(g["err"])
+        assert np.array_equal(r["regrid"], g["regrid_iter"].astype(int))
+    assert r["du"] <= tol_du, (r["du"], tol_du)
+    assert abs(r["ssd1"] - float(g["ssd1"])) <= tol_ssd * float(g["ssd1"]), (r["ssd1"], float(g["ssd1"]), tol_ssd)
+    if spec["method"] != "fluid":
+        assert np.allclose(r["mo"].mean(axis=(0, 1)), g["mean"], rtol=0, atol=1e-5 if r["bits"] == 32 else 1e-9)
+    assert r["ssd1"] < float(g["ssd0"])   # it registers
+
+
+@pytest.mark.parametrize("name", [n for n in BENCH_FLUID if n in CASES])
+def test_fluid_at_the_bench_caps_meets_the_north_star_bar(name):
+    r = run(name, strict=False)
+    g = r["g"]
+    assert r["iters"] == len(g["err"])
+    assert np.array_equal(r["regrid"], g["regrid_iter"].astype(int))
+    assert r["du"] <= 1e-3, r["du"]
+
+
+STRICT = sorted(n for n in CASES if n.startswith(("full2048_fluid", "full2048f64_fluid_c100", "c2_", "c3_", "demo_")) or n in
+                ("c5_fluid_pair3", "c5_thirion_pair3", "c5f64_fluid_pair3", "full2048f64_elastic", "full2048f64_diffusion"))
+
+
+@pytest.mark.parametrize("name", STRICT)
+def test_strict_mode_is_bit_identical_to_compiled_reference(name):
+    r = run(name, strict=True)
+    g = r["g"]
+    assert r["iters"] == len(g["err"])
+    assert np.array_equal(r["regrid"], g["regrid_iter"].astype(int))
+    assert r["du"] == 0.0
+    assert abs(r["ssd1"] - float(g["ssd1"])) <= 1e-12 * float(g["ssd1"])
