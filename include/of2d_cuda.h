@@ -51,8 +51,15 @@ int of2d_ctx_set_stream(of2d_ctx *ctx, void *cuda_stream);
 int of2d_ctx_use_own_stream(of2d_ctx *ctx);
 void *of2d_ctx_get_stream(of2d_ctx *ctx);
 int of2d_ctx_sync(of2d_ctx *ctx);
-/* 1: FMA contraction allowed in the flop-heavy kernels (default); 0: reproduce the reference's
-   unfused mul/add sequence bit for bit (used by the parity tests) */
+/* arithmetic level of the context (read when an engine is created / a driver loop starts):
+     0  strict : the host classes run the reference's loop literally, one per-step kernel per call; every value is
+                 the reference's expression in the reference's operation order, unfused (bit-exact parity pin);
+     1  exact  : the device-resident engine with the same unfused arithmetic (bit-identical fields to level 0 for
+                 Diffusion / Thirion / Diffeomorphic; Elastic / Fluid to 2^-40 of a step; Curvature to 1e-9 px);
+     2  relaxed: the engine compiled a second time with FMA contraction, approximate division and algebraically
+                 equivalent shortcuts (separable Gaussian taps, linear carry correction in the SOR sweep): results
+                 within the north-star tolerances (1e-3 px / 1e-4 SSD in fp32, 1e-6 px in fp64), not bit-identical.
+   Default 2; the environment variable OF2D_MATH = strict | exact | relaxed sets the initial level. */
 int of2d_ctx_set_fast_math(of2d_ctx *ctx, int on);
 int of2d_ctx_get_fast_math(of2d_ctx *ctx);
 const char *of2d_last_error(void);
@@ -224,6 +231,8 @@ int of2d_engine_pair_result(of2d_engine *engine, int pair, int *iterations, int 
    2 fluid time step, 3 fluid min Jacobian, 4 fluid regrid flag, 5 diffeomorphic squarings */
 int of2d_engine_trace(of2d_engine *engine, int pair, int which, double *h_out, int count);
 uint64_t of2d_engine_iterations_enqueued(of2d_engine *engine);
+/* 1 when the engine was created at arithmetic level 2 (relaxed), 0 for the exact build */
+int of2d_engine_is_relaxed(of2d_engine *engine);
 
 #ifdef __cplusplus
 }

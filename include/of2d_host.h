@@ -30,7 +30,9 @@ int of2d_host_real_bits(void);                 /* 32 or 64 */
 const char *of2d_host_last_error(void);
 void of2d_host_capture_printf(int on);         /* collect mexPrintf output instead of dropping it */
 const char *of2d_host_printed(void);
-int of2d_host_set_strict(int strict);          /* 1: no FMA contraction anywhere (bit-exact parity mode) */
+int of2d_host_set_strict(int strict);          /* 1: arithmetic level 0 (the reference's loop literally, bit-exact); 0: back to the default level */
+int of2d_host_set_math(int level);             /* arithmetic level of the process context: 0 strict, 1 exact engine, 2 relaxed engine (of2d_cuda.h) */
+int of2d_host_get_math(void);
 int of2d_host_set_stream(void *cuda_stream);   /* run on the caller's cudaStream_t (NULL = legacy default stream) */
 int of2d_host_use_own_stream(void);
 int of2d_host_sync(void);

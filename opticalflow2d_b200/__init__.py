@@ -341,6 +341,20 @@ def set_strict(strict: bool, bits: int = 32):
     _check(lib, lib.of2d_host_set_strict(int(strict)))
 
 
+MATH_LEVELS = {"strict": 0, "exact": 1, "relaxed": 2}
+
+
+def set_math(level, bits: int = 32):
+    """Arithmetic level: 'strict' (0, the reference's loop literally), 'exact' (1, the engine with unfused arithmetic),
+    'relaxed' (2, default: the engine with FMA contraction / approximate division / equivalent shortcuts)."""
+    lib = host(bits)
+    _check(lib, lib.of2d_host_set_math(int(MATH_LEVELS.get(level, level))))
+
+
+def get_math(bits: int = 32) -> int:
+    return int(host(bits).of2d_host_get_math())
+
+
 def set_stream(cuda_stream: int, bits: int = 32):
     lib = host(bits)
     _check(lib, lib.of2d_host_set_stream(C.c_void_p(cuda_stream)))

@@ -25,12 +25,15 @@ OBJDIR = os.path.join(PKG, "build")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-fmad=false",              # reproduce the reference's unfused mul/add rounding (explicit fma() where allowed)
     "-Xcompiler", "-fPIC",
     "-Xcompiler", "-fno-fast-math",
     "--expt-relaxed-constexpr",
     "-I" + os.path.join(ROOT, "include"),
 ]
+# arithmetic: every translation unit reproduces the reference's unfused mul/add rounding and IEEE division ...
+EXACT_FLAGS = ["-fmad=false"]
+# ... except *_relaxed.cu (the second build of the iteration engine, arithmetic level 2)
+RELAXED_FLAGS = ["-fmad=true", "-prec-div=false", "-prec-sqrt=false"]
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-Wno-unused-function", "-I" + os.path.join(ROOT, "include"), "-I" + HOST, "-I" + os.path.join(HOST, "mex")]
 
 
@@ -70,8 +73,8 @@ def build_cuda(force=False, verbose=False) -> str:
     for s in srcs:
         o = os.path.join(OBJDIR, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
-        if force or _newer(o, [s] + hdrs):
-            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+        if force or _newer(o, [s] + hdrs + ([s.replace("_relaxed.cu", ".cu")] if s.endswith("_relaxed.cu") else [])):
+            jobs.append([nvcc] + NVCC_FLAGS + (RELAXED_FLAGS if s.endswith("_relaxed.cu") else EXACT_FLAGS) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
         list(ex.map(lambda c: _run(c, verbose), jobs))
     if jobs or force or _newer(out, objs):

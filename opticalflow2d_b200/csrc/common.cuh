@@ -17,7 +17,7 @@ struct of2d_ctx {
     int sm_count;
     cudaStream_t own_stream;
     cudaStream_t stream;
-    bool fast_math;
+    int fast_math;           // arithmetic level: 0 strict (per-step kernels, the reference loop literally), 1 exact engine, 2 relaxed engine (default)
     uint64_t launches;
     // scratch for reductions: per-block partials + a pinned mailbox for scalar results
     double *d_partials;      // [kMaxPartialBlocks * 4]

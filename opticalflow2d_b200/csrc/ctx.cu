@@ -68,7 +68,11 @@ int of2d_ctx_create(int device, of2d_ctx **out) {
     of2d_ctx *c = new of2d_ctx();
     memset(c, 0, sizeof(*c));
     c->device = device;
-    c->fast_math = true;
+    c->fast_math = 2;
+    {   // OF2D_MATH = strict | exact | relaxed (or 0 | 1 | 2): the arithmetic level new contexts start in
+        const char *e = getenv("OF2D_MATH");
+        if (e && *e) c->fast_math = !strcmp(e, "strict") ? 0 : !strcmp(e, "exact") ? 1 : !strcmp(e, "relaxed") ? 2 : (atoi(e) < 0 ? 0 : atoi(e) > 2 ? 2 : atoi(e));
+    }
     OF2D_CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     OF2D_CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     {   // keep freed blocks in the pool instead of returning them to the driver at every synchronisation
@@ -116,10 +120,10 @@ int of2d_ctx_sync(of2d_ctx *c) {
     return OF2D_SUCCESS;
 }
 int of2d_ctx_set_fast_math(of2d_ctx *c, int on) {
-    c->fast_math = on != 0;
+    c->fast_math = on < 0 ? 0 : on > 2 ? 2 : on;
     return OF2D_SUCCESS;
 }
-int of2d_ctx_get_fast_math(of2d_ctx *c) { return c->fast_math ? 1 : 0; }
+int of2d_ctx_get_fast_math(of2d_ctx *c) { return c->fast_math; }
 uint64_t of2d_ctx_launch_count(of2d_ctx *c) { return c->launches; }
 
 int of2d_ctx_profile_enable(of2d_ctx *c, int on) {

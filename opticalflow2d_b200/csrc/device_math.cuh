@@ -6,6 +6,13 @@
 
 #include "common.cuh"
 
+// OF2D_RELAXED (engine_relaxed.cu only): arithmetic level 2.  The translation unit is compiled with FMA contraction and
+// approximate division, and the functions below may take shortcuts that are algebraically equal to the reference's
+// expression (marked `#if OF2D_RELAXED`); every other translation unit sees OF2D_RELAXED == 0 and the literal expressions.
+#ifndef OF2D_RELAXED
+#define OF2D_RELAXED 0
+#endif
+
 // ---- gradients.h:9-32 on a scalar image ----------------------------------------------------------
 template <class R>
 __device__ __forceinline__ R partial_x(const R *__restrict__ f, int idx, int i, int nx) {
@@ -53,8 +60,14 @@ struct Bilin {
 template <class R>
 __device__ __forceinline__ Bilin<R> bilin_setup(int i, int j, R ux, R uy, int nx, int ny) {
     Bilin<R> b;
+#if OF2D_RELAXED
+    // (R)dx == floor(px) exactly for every coordinate that can be inside the image: the same bits without the int -> real conversion
+    const R px = (R)i + ux, flx = r_floor(px); const int dx = (int)flx; b.fx = px - flx;
+    const R py = (R)j + uy, fly = r_floor(py); const int dy = (int)fly; b.fy = py - fly;
+#else
     const R px = (R)i + ux; const int dx = (int)r_floor(px); b.fx = px - (R)dx;
     const R py = (R)j + uy; const int dy = (int)r_floor(py); b.fy = py - (R)dy;
+#endif
     b.inside = !(dx < 0 || dx >= nx || dy < 0 || dy >= ny);
     b.idxO = dx + dy * nx;
     b.hx = dx < nx - 1;
@@ -67,6 +80,13 @@ template <class R>
 __device__ __forceinline__ R warp_pixel(const R *__restrict__ src, int nx, int ny, int i, int j, vec2_t<R> u, R keep) {
     const Bilin<R> b = bilin_setup<R>(i, j, u.x, u.y, nx, ny);
     if (!b.inside) return keep;
+#if OF2D_RELAXED
+    if (b.hx && b.hy) {   // all four taps inside: the weights sum to 1 (the reference's float sum is 1 +- 1 ulp), so no renormalisation
+        const R s00 = src[b.idxO], s10 = src[b.idxO + 1], s01 = src[b.idxO + nx], s11 = src[b.idxO + nx + 1];
+        const R lo = s00 + b.fx * (s10 - s00), hi = s01 + b.fx * (s11 - s01);
+        return lo + b.fy * (hi - lo);
+    }
+#endif
     const R one = (R)1;
     R val = src[b.idxO] * (one - b.fx) * (one - b.fy);
     R weight = (one - b.fx) * (one - b.fy);
@@ -76,11 +96,40 @@ __device__ __forceinline__ R warp_pixel(const R *__restrict__ src, int nx, int n
     return weight != 0 ? val / weight : keep;
 }
 
+// the same, with the value the pixel keeps (src[idx_self]) read only when the reference keeps it
+template <class R>
+__device__ __forceinline__ R warp_pixel_lazy(const R *__restrict__ src, int nx, int ny, int i, int j, vec2_t<R> u, int idx_self) {
+    const Bilin<R> b = bilin_setup<R>(i, j, u.x, u.y, nx, ny);
+    if (!b.inside) return src[idx_self];
+#if OF2D_RELAXED
+    if (b.hx && b.hy) {
+        const R s00 = src[b.idxO], s10 = src[b.idxO + 1], s01 = src[b.idxO + nx], s11 = src[b.idxO + nx + 1];
+        const R lo = s00 + b.fx * (s10 - s00), hi = s01 + b.fx * (s11 - s01);
+        return lo + b.fy * (hi - lo);
+    }
+#endif
+    const R one = (R)1;
+    R val = src[b.idxO] * (one - b.fx) * (one - b.fy);
+    R weight = (one - b.fx) * (one - b.fy);
+    if (b.hx) { val += src[b.idxO + 1] * b.fx * (one - b.fy); weight += b.fx * (one - b.fy); }
+    if (b.hy) { val += src[b.idxO + nx] * (one - b.fx) * b.fy; weight += (one - b.fx) * b.fy; }
+    if (b.hx && b.hy) { val += src[b.idxO + 1 + nx] * b.fx * b.fy; weight += b.fx * b.fy; }
+    return weight != 0 ? val / weight : src[idx_self];
+}
+
 // Motion::accumulate for one pixel: v + u o (id + v); `keep` = u at this pixel (Motion.cpp:141-169)
 template <class R>
 __device__ __forceinline__ vec2_t<R> compose_pixel(const vec2_t<R> *__restrict__ u, int nx, int ny, int i, int j, vec2_t<R> v, vec2_t<R> keep) {
     const Bilin<R> b = bilin_setup<R>(i, j, v.x, v.y, nx, ny);
     if (!b.inside) return keep;
+#if OF2D_RELAXED
+    if (b.hx && b.hy) {
+        const vec2_t<R> s00 = u[b.idxO], s10 = u[b.idxO + 1], s01 = u[b.idxO + nx], s11 = u[b.idxO + nx + 1];
+        const R lx = s00.x + b.fx * (s10.x - s00.x), hx = s01.x + b.fx * (s11.x - s01.x);
+        const R ly = s00.y + b.fx * (s10.y - s00.y), hy = s01.y + b.fx * (s11.y - s01.y);
+        return mk2<R>(v.x + (lx + b.fy * (hx - lx)), v.y + (ly + b.fy * (hy - ly)));
+    }
+#endif
     const R one = (R)1;
     vec2_t<R> s = u[b.idxO];
     R vx = s.x * (one - b.fx) * (one - b.fy), vy = s.y * (one - b.fx) * (one - b.fy);
@@ -110,6 +159,13 @@ __device__ __forceinline__ BilinTaps<R> bilin_taps(const Bilin<R> &b, int idx_se
 template <class R>
 __device__ __forceinline__ vec2_t<R> compose_taps(const Bilin<R> &b, vec2_t<R> s00, vec2_t<R> s10, vec2_t<R> s01, vec2_t<R> s11, vec2_t<R> v, vec2_t<R> keep) {
     if (!b.inside) return keep;
+#if OF2D_RELAXED
+    if (b.hx && b.hy) {
+        const R lx = s00.x + b.fx * (s10.x - s00.x), hx = s01.x + b.fx * (s11.x - s01.x);
+        const R ly = s00.y + b.fx * (s10.y - s00.y), hy = s01.y + b.fx * (s11.y - s01.y);
+        return mk2<R>(v.x + (lx + b.fy * (hx - lx)), v.y + (ly + b.fy * (hy - ly)));
+    }
+#endif
     const R one = (R)1;
     R vx = s00.x * (one - b.fx) * (one - b.fy), vy = s00.y * (one - b.fx) * (one - b.fy);
     R weight = (one - b.fx) * (one - b.fy);
@@ -122,6 +178,12 @@ __device__ __forceinline__ vec2_t<R> compose_taps(const Bilin<R> &b, vec2_t<R> s
 template <class R>
 __device__ __forceinline__ R warp_taps(const Bilin<R> &b, R s00, R s10, R s01, R s11, R keep) {
     if (!b.inside) return keep;
+#if OF2D_RELAXED
+    if (b.hx && b.hy) {
+        const R lo = s00 + b.fx * (s10 - s00), hi = s01 + b.fx * (s11 - s01);
+        return lo + b.fy * (hi - lo);
+    }
+#endif
     const R one = (R)1;
     R val = s00 * (one - b.fx) * (one - b.fy);
     R weight = (one - b.fx) * (one - b.fy);

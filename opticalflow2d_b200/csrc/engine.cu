@@ -13,6 +13,19 @@
 //
 // Elastic and Fluid keep their fields in a TRANSPOSED working layout (element (i,j) at i*P + j) for
 // the whole loop so that the column-sequential SOR sweep (sor_tile.cuh) streams contiguous memory.
+//
+// This file is compiled TWICE (build.py): as is (-fmad=false, IEEE division: the "exact" engine, arithmetic level 1) and
+// through engine_relaxed.cu (OF2D_RELAXED=1, -fmad=true -prec-div=false: the "relaxed" engine, level 2, where the kernels
+// also take algebraically equivalent shortcuts).  engine_dispatch.cu exports the C ABI and forwards to one of the two.
+#ifndef OF2D_RELAXED
+#define OF2D_RELAXED 0
+#endif
+#if OF2D_RELAXED
+#define ENG(name) of2d_engine_##name##_relaxed
+#else
+#define ENG(name) of2d_engine_##name##_exact
+#endif
+
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -30,7 +43,9 @@
 // =================================================================================================
 // host side
 // =================================================================================================
-struct of2d_engine {
+namespace {
+struct Engine {
+    of2d_engine_head head;       // first member: engine_dispatch.cu reads which build owns the object
     of2d_ctx *ctx;
     of2d_engine_desc d;
     bool dbl, transposed;
@@ -57,8 +72,7 @@ struct of2d_engine {
     const void *cur_Imov;
     int last_niter;
 };
-
-namespace {
+#define of2d_engine Engine
 
 #define TRY(x) do { int _s = (x); if (_s) return _s; } while (0)
 
@@ -107,6 +121,28 @@ ConvW<R> conv_weights(of2d_engine *E, int which) {
     for (int t = 0; t < kw * kw; t++) W.w[t] = (R)E->h_taps[which][(size_t)t];
     W.full_weight = E->full_weight[which];
     W.neg_zero = -0.0f;
+#if OF2D_RELAXED
+    {   // rank-1 test in double: w[ii + jj kw] == w[ii + c kw] w[c + jj kw] / w[c + c kw] to 1e-6 of the largest tap
+        const std::vector<double> &h = E->h_taps[which];
+        const int c = (kw - 1) / 2;
+        const double wc = h[(size_t)(c + c * kw)];
+        double worst = 0.0, big = 0.0;
+        W.separable = (kw & 1) && wc != 0.0 && W.full_weight != 0.0;
+        if (W.separable) {
+            for (int jj = 0; jj < kw; jj++)
+                for (int ii = 0; ii < kw; ii++) {
+                    const double w = h[(size_t)(ii + jj * kw)], prod = h[(size_t)(ii + c * kw)] * h[(size_t)(c + jj * kw)] / wc;
+                    worst = fmax(worst, fabs(w - prod)); big = fmax(big, fabs(w));
+                }
+            W.separable = worst <= 1e-6 * big;
+        }
+        if (W.separable)
+            for (int t = 0; t < kw; t++) {
+                W.sx[t] = (R)(h[(size_t)(t + c * kw)] / wc);
+                W.sy[t] = (R)(h[(size_t)(c + t * kw)] / W.full_weight);
+            }
+    }
+#endif
     return W;
 }
 
@@ -340,19 +376,21 @@ int upload_taps(of2d_engine *E, int which, const double *h_kernel) {
 
 extern "C" {
 
-int of2d_engine_create(of2d_ctx *ctx, const of2d_engine_desc *desc, of2d_engine **out) {
+int ENG(create)(of2d_ctx *ctx, const of2d_engine_desc *desc, of2d_engine_head **out_head) {
+    Engine **out = reinterpret_cast<Engine **>(out_head);
     *out = nullptr;
     OF2D_REQUIRE(desc && desc->dimx > 1 && desc->dimy > 1 && desc->batch > 0 && desc->method >= 0 && desc->method <= 5 && desc->max_iter >= 0, "bad engine description");
     OF2D_CUDA_TRY(cudaSetDevice(ctx->device));
     of2d_engine *E = new (std::nothrow) of2d_engine();
     OF2D_REQUIRE(E, "out of host memory");
+    E->head.relaxed = OF2D_RELAXED;
     E->ctx = ctx; E->d = *desc; E->dbl = desc->real_is_double != 0;
     E->elem = E->dbl ? 8 : 4;
     const int nx = desc->dimx, ny = desc->dimy, B = desc->batch, m = desc->method;
     E->n = (size_t)nx * ny;
     E->transposed = (m == 2 || m == 5);
     int st = OF2D_SUCCESS;
-    auto fail = [&](int code) { of2d_engine_destroy(E); return code; };
+    auto fail = [&](int code) { ENG(destroy)(&E->head); return code; };
     if (E->transposed) {
         E->sor = sor_plan(nx, ny, B, desc->mu, desc->lambda, desc->omega, E->dbl, m == 5);
         if (!E->sor.supported) {
@@ -429,7 +467,8 @@ int of2d_engine_create(of2d_ctx *ctx, const of2d_engine_desc *desc, of2d_engine 
     return OF2D_SUCCESS;
 }
 
-void of2d_engine_destroy(of2d_engine *E) {
+void ENG(destroy)(of2d_engine_head *H) {
+    Engine *E = reinterpret_cast<Engine *>(H);
     if (!E) return;
     cudaSetDevice(E->ctx->device);
     cudaStreamSynchronize(E->ctx->stream);
@@ -442,7 +481,8 @@ void of2d_engine_destroy(of2d_engine *E) {
     delete E;
 }
 
-int of2d_engine_reset_state(of2d_engine *E) {
+int ENG(reset_state)(of2d_engine_head *H) {
+    Engine *E = reinterpret_cast<Engine *>(H);
     if (E->d.method != 5) return OF2D_SUCCESS;
     const size_t bytes = 2 * E->elem * E->nT * E->d.batch;
     OF2D_CUDA_TRY(cudaMemsetAsync(E->vel[0], 0, bytes, E->ctx->stream));
@@ -450,16 +490,19 @@ int of2d_engine_reset_state(of2d_engine *E) {
     return OF2D_SUCCESS;
 }
 
-int of2d_engine_refine_f32(of2d_engine *E, const float *d_Iref, const float *d_Imov, float *d_motion, int niter) {
+int ENG(refine_f32)(of2d_engine_head *H, const float *d_Iref, const float *d_Imov, float *d_motion, int niter) {
+    Engine *E = reinterpret_cast<Engine *>(H);
     OF2D_REQUIRE(!E->dbl, "engine was created for double fields");
     return refine_impl<float>(E, d_Iref, d_Imov, d_motion, niter);
 }
-int of2d_engine_refine_f64(of2d_engine *E, const double *d_Iref, const double *d_Imov, double *d_motion, int niter) {
+int ENG(refine_f64)(of2d_engine_head *H, const double *d_Iref, const double *d_Imov, double *d_motion, int niter) {
+    Engine *E = reinterpret_cast<Engine *>(H);
     OF2D_REQUIRE(E->dbl, "engine was created for float fields");
     return refine_impl<double>(E, d_Iref, d_Imov, d_motion, niter);
 }
 
-int of2d_engine_pair_result(of2d_engine *E, int pair, int *iterations, int *nregrid, double *last_err) {
+int ENG(pair_result)(of2d_engine_head *H, int pair, int *iterations, int *nregrid, double *last_err) {
+    Engine *E = reinterpret_cast<Engine *>(H);
     OF2D_REQUIRE(pair >= 0 && pair < E->d.batch, "pair out of range");
     const PairCtl &c = E->h_ctl[(size_t)pair];
     if (iterations) *iterations = c.iter;
@@ -468,7 +511,8 @@ int of2d_engine_pair_result(of2d_engine *E, int pair, int *iterations, int *nreg
     return OF2D_SUCCESS;
 }
 
-int of2d_engine_trace(of2d_engine *E, int pair, int which, double *h_out, int count) {
+int ENG(trace)(of2d_engine_head *H, int pair, int which, double *h_out, int count) {
+    Engine *E = reinterpret_cast<Engine *>(H);
     OF2D_REQUIRE(pair >= 0 && pair < E->d.batch && which >= 0 && which <= 5 && count >= 0 && count <= E->tr.cap, "bad trace request");
     if (count == 0) return OF2D_SUCCESS;
     const size_t off = (size_t)pair * E->tr.cap;
@@ -486,6 +530,6 @@ int of2d_engine_trace(of2d_engine *E, int pair, int which, double *h_out, int co
     return OF2D_SUCCESS;
 }
 
-uint64_t of2d_engine_iterations_enqueued(of2d_engine *E) { return E->iterations_enqueued; }
+uint64_t ENG(iterations_enqueued)(of2d_engine_head *H) { return reinterpret_cast<Engine *>(H)->iterations_enqueued; }
 
 }  // extern "C"

@@ -532,6 +532,14 @@ __global__ void __launch_bounds__(TX *TY) k_e_square(EngK<R> K, int s) {
             v.x *= sc; v.y *= sc;
             const Bilin<R> b = bilin_setup<R>(i, j, v.x, v.y, nx, ny);
             vec2_t<R> o = v;   // out of bounds: keeps the (scaled) value
+#if OF2D_RELAXED
+            if (b.inside && b.hx && b.hy) {   // all four taps inside: weights sum to 1; the power-of-two scale commutes with the interpolation
+                const vec2_t<R> s00 = src[b.idxO], s10 = src[b.idxO + 1], s01 = src[b.idxO + nx], s11 = src[b.idxO + nx + 1];
+                const R lx = s00.x + b.fx * (s10.x - s00.x), hx = s01.x + b.fx * (s11.x - s01.x);
+                const R ly = s00.y + b.fx * (s10.y - s00.y), hy = s01.y + b.fx * (s11.y - s01.y);
+                o = mk2<R>(v.x + sc * (lx + b.fy * (hx - lx)), v.y + sc * (ly + b.fy * (hy - ly)));
+            } else
+#endif
             if (b.inside) {
                 const R one = (R)1;
                 vec2_t<R> t = src[b.idxO];
@@ -567,6 +575,9 @@ __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 8 : 1) k_e_demons_for
     const int tid = threadIdx.x + threadIdx.y * TX;
     const TileWalk T(nx, ny);
     bool divzero = false;
+#if OF2D_RELAXED
+    const R sratio = sigma_isq / sigma_xsq;
+#endif
     for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x) {
         const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
         const int i = i0 + threadIdx.x;
@@ -581,7 +592,14 @@ __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 8 : 1) k_e_demons_for
             const int r = e / (TILE + 2), cc = e - r * (TILE + 2);
             const int ii = i0 + cc - 1, j = j0 + r - 1;
             R w = (R)0;
-            if (ii >= 0 && ii < nx && j >= 0 && j < ny) { const int idx = ii + j * nx; w = warp_pixel<R>(Imov, nx, ny, ii, j, u[idx], Imov[idx]); }
+            if (ii >= 0 && ii < nx && j >= 0 && j < ny) {
+                const int idx = ii + j * nx;
+#if OF2D_RELAXED
+                w = warp_pixel_lazy<R>(Imov, nx, ny, ii, j, u[idx], idx);
+#else
+                w = warp_pixel<R>(Imov, nx, ny, ii, j, u[idx], Imov[idx]);
+#endif
+            }
             sw[r][cc] = w;
         }
         __syncthreads();
@@ -595,10 +613,17 @@ __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 8 : 1) k_e_demons_for
                 const R gx = (sw[r][cc + 1] - sw[r][cc - 1]) / (R)2.0f;
                 const R gy = (sw[r + 1][cc] - sw[r - 1][cc]) / (R)2.0f;
                 const R It = ce - iref[p];
+#if OF2D_RELAXED
+                const R den = gx * gx + gy * gy + (It * It) * sratio;
+                if (den == 0) { divzero = true; corr[idx] = mk2<R>((R)0, (R)0); continue; }
+                const R s = -It / den;   // one (approximate, fp32) division per pixel
+                corr[idx] = mk2<R>(gx * s, gy * s);
+#else
                 const R q = It * It * sigma_isq;
                 const R den = gx * gx + gy * gy + (inv_sigma_xsq != (R)0 ? q * inv_sigma_xsq : q / sigma_xsq);
                 if (den == 0) { divzero = true; corr[idx] = mk2<R>((R)0, (R)0); continue; }
                 corr[idx] = mk2<R>(gx * It / den * (R)-1, gy * It / den * (R)-1);
+#endif
             }
             continue;
         }
@@ -644,6 +669,12 @@ struct ConvW {
     double full_weight;           // sum over the visiting order
     int kw;
     float neg_zero;               // -0.0f, opaque to the compiler (see the packed fast path of k_e_conv)
+#if OF2D_RELAXED
+    // relaxed build: a Gaussian (Kernel::set_gaussian, Kernel.cpp:45-73) is a product w[ii][jj] = sx[ii] sy[jj] up to rounding:
+    // full windows take kw + kw taps instead of kw * kw; 1 / full_weight is folded into sy.  separable == 0: dense taps.
+    R sx[kConvMaxW], sy[kConvMaxW];
+    int separable;
+#endif
 };
 
 template <class R, int EPI, int KW>
@@ -737,6 +768,62 @@ __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 5 : 1) k_e_conv(EngK<
                 for (int q = 0; q < 4; q++) prev[q] = est_cur[idx0 + (long)q * nx];
             }
             R ax[4], ay[4];
+#if OF2D_RELAXED
+            if (W.separable) {
+                // row pass over the KW + 3 window rows of the thread's 4 outputs, then the column pass: KW + KW taps per output
+                // instead of KW * KW (the normalisation is folded into sy)
+                constexpr int NRW = 4 + (KW > 0 ? KW : 1) - 1;
+                if constexpr (sizeof(R) == 4) {
+                    unsigned long long hrow[NRW];
+#pragma unroll
+                    for (int r = 0; r < NRW; r++) {
+                        const float2 e0 = tile_s[(jl0 + r) * SWp + threadIdx.x];
+                        hrow[r] = fma_f32x2(pack_f32x2(e0.x, e0.y), pack_f32x2(W.sx[0], W.sx[0]), pack_f32x2(0.0f, 0.0f));
+#pragma unroll
+                        for (int ii = 1; ii < KW; ii++) {
+                            const float2 e = tile_s[(jl0 + r) * SWp + threadIdx.x + ii];
+                            hrow[r] = fma_f32x2(pack_f32x2(e.x, e.y), pack_f32x2(W.sx[ii], W.sx[ii]), hrow[r]);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        unsigned long long a2 = fma_f32x2(hrow[q], pack_f32x2(W.sy[0], W.sy[0]), pack_f32x2(0.0f, 0.0f));
+#pragma unroll
+                        for (int jj = 1; jj < KW; jj++) a2 = fma_f32x2(hrow[q + jj], pack_f32x2(W.sy[jj], W.sy[jj]), a2);
+                        const float2 e = unpack_f32x2(a2);
+                        ax[q] = e.x; ay[q] = e.y;
+                    }
+                } else {
+                    vec2_t<R> hrow[NRW];
+#pragma unroll
+                    for (int r = 0; r < NRW; r++) {
+                        R hx = (R)0, hy = (R)0;
+#pragma unroll
+                        for (int ii = 0; ii < KW; ii++) {
+                            const vec2_t<R> e = tile_s[(jl0 + r) * SWp + threadIdx.x + ii];
+                            hx += e.x * W.sx[ii]; hy += e.y * W.sx[ii];
+                        }
+                        hrow[r] = mk2<R>(hx, hy);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        R sxq = (R)0, syq = (R)0;
+#pragma unroll
+                        for (int jj = 0; jj < KW; jj++) { sxq += hrow[q + jj].x * W.sy[jj]; syq += hrow[q + jj].y * W.sy[jj]; }
+                        ax[q] = sxq; ay[q] = syq;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const vec2_t<R> o = mk2<R>(ax[q], ay[q]);
+                    out[idx0 + (long)q * nx] = o;
+                    epilogue(o, prev[q]);
+                }
+                if (EPI == 1) acc.flush();
+                __syncthreads();
+                continue;
+            }
+#endif
             if constexpr (sizeof(R) == 4) {
                 // both components of a tap in one packed instruction: FFMA2 with the -0 addend rounds exactly like the
                 // reference's multiply (x*t + -0 == x*t, signed zeros included) and FADD2 is its add, so the result is
@@ -1066,7 +1153,7 @@ __global__ void __launch_bounds__(TX *TY) k_fl_rewarp(EngK<R> K, int gate, const
             const int r = e / (TILE + 2), cc = e - r * (TILE + 2);
             const int i = i0 + cc - 1, j = j0 + r - 1;
             R w = (R)0;
-            if (i >= 0 && i < nx && j >= 0 && j < ny) { const int idx = i + j * nx; w = warp_pixel<R>(Imov, nx, ny, i, j, u[idx], Imov[idx]); }
+            if (i >= 0 && i < nx && j >= 0 && j < ny) { const int idx = i + j * nx; w = warp_pixel_lazy<R>(Imov, nx, ny, i, j, u[idx], idx); }
             sw[r][cc] = w;
         }
         __syncthreads();

@@ -100,8 +100,26 @@ int of2d_host_real_bits(void) { return (int)sizeof(of2d_real) * 8; }
 const char* of2d_host_last_error(void) { return g_error.c_str(); }
 void of2d_host_capture_printf(int on) { g_capture = on != 0; g_printed.clear(); }
 const char* of2d_host_printed(void) { return g_printed.c_str(); }
+static int default_math_level() {
+    const char* e = std::getenv("OF2D_MATH");
+    if (!e || !*e) return 2;
+    const std::string s(e);
+    if (s == "strict") return 0;
+    if (s == "exact") return 1;
+    if (s == "relaxed") return 2;
+    const int v = std::atoi(e);
+    return v < 0 ? 0 : v > 2 ? 2 : v;
+}
 int of2d_host_set_strict(int strict) {
-    return guarded([&] { of2d::check(of2d_ctx_set_fast_math(of2d::context(), strict ? 0 : 1)); });
+    return guarded([&] { of2d::check(of2d_ctx_set_fast_math(of2d::context(), strict ? 0 : default_math_level())); });
+}
+int of2d_host_set_math(int level) {
+    return guarded([&] { of2d::check(of2d_ctx_set_fast_math(of2d::context(), level)); });
+}
+int of2d_host_get_math(void) {
+    int level = -1;
+    guarded([&] { level = of2d_ctx_get_fast_math(of2d::context()); });
+    return level;
 }
 int of2d_host_set_stream(void* cuda_stream) {
     return guarded([&] { of2d::check(of2d_ctx_set_stream(of2d::context(), cuda_stream)); });

@@ -8,7 +8,7 @@ import opticalflow2d_b200 as of
 import make_golden_configs as G
 
 pat = sys.argv[1:] or ["full2048_fluid_c", "full2048f64_", "c2_", "c3_", "c5_", "demo_"]
-modes = os.environ.get("MODES", "fast,strict").split(",")
+modes = os.environ.get("MODES", "relaxed,exact,strict").split(",")
 cases = G.cases()
 rows = []
 for name, spec in cases.items():
@@ -24,7 +24,7 @@ for name, spec in cases.items():
     for mode in modes:
         if mode == "strict" and spec["method"] in ("elastic", "fluid") and dimx >= 2048 and os.environ.get("STRICT_BIG", "1") == "0":
             continue
-        of.set_strict(mode == "strict", bits)
+        of.set_math(mode, bits)
         t0 = time.time()
         with of.Session((dimx, dimy), [int(v) for v in g["niter"]], int(g["nscales"]), int(g["reg"]), list(g["regparams"]), nrefine=1, verbose=0, bits=bits) as s:
             s.set_images(R, T)
@@ -44,5 +44,5 @@ for name, spec in cases.items():
                    err_rel=rel, ssd_rel=abs(ssd1 - float(g["ssd1"])) / float(g["ssd1"]), mean_d=float(np.abs(mo.mean(axis=(0, 1)) - g["mean"]).max()), sec=time.time() - t0)
         rows.append(row)
         print(json.dumps(row), flush=True)
-of.set_strict(False, 32); of.set_strict(False, 64)
-json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "parity_survey.json"), "w"), indent=1)
+of.set_math("relaxed", 32); of.set_math("relaxed", 64)
+json.dump(rows, open(os.path.join(ROOT, "gpurun_out", os.environ.get("SURVEY_OUT", "parity_survey.json")), "w"), indent=1)

@@ -8,7 +8,8 @@ import opticalflow2d_b200 as of
 from gpu_common import maxdiff, oracle
 from opticalflow2d_b200 import synthetic as S
 
-pytestmark = pytest.mark.gpu
+# these tests pin the EXACT engine (arithmetic level 1) bit for bit; the default relaxed engine: tests/test_relaxed_gpu.py
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("exact_engine")]
 
 CASES = [
     (of.THIRION, [1.0, 0.25, 1.5, 1.5, 5, 0], 12),

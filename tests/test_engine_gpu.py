@@ -15,7 +15,8 @@ import opticalflow2d_b200 as of
 from gpu_common import maxdiff, oracle
 from opticalflow2d_b200 import synthetic as S
 
-pytestmark = pytest.mark.gpu
+# these tests pin the EXACT engine (arithmetic level 1) bit for bit; the default relaxed engine: tests/test_relaxed_gpu.py
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("exact_engine")]
 
 
 def run(bits, strict, dims, R, T, reg, params, niter, nscales=0, nrefine=1):

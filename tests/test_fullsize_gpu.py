@@ -13,7 +13,8 @@ import opticalflow2d_b200 as of
 from gpu_common import maxdiff
 
 pytestmark = pytest.mark.gpu
-FULL = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "full2048_*.npz")))
+FULL = [p for p in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "full2048_*.npz")))
+        if os.path.basename(p)[9:-4] in bench.REG]   # make_golden_full.py's six files (the full2048_fluid_c* caps: tests/test_configs_gpu.py)
 
 
 def run(method, size, niter, strict=False):
@@ -44,6 +45,7 @@ def test_full_size_matches_compiled_reference(path):
     assert ssd1 < ssd0                                                    # it registers
 
 
+@pytest.mark.usefixtures("exact_engine")
 @pytest.mark.parametrize("method", ["diffusion", "thirion", "diffeomorphic"])
 def test_full_size_engine_is_bit_identical_to_strict(method):
     """Exact-arithmetic methods: interior of the field must agree bit for bit; on the outermost rows / columns the
