@@ -15,8 +15,13 @@ same step on its own pair (weak scaling, no collective in the solve); value = su
 `e2e`    : the same step through the C-ABI session (include/of2d_host.h) with HOST double buffers:
            H2D of both images, estimate, D2H of the planar double motion inside the timed region.
 `roofline`: the dominant kernel of the step, timed alone on L2-flushed 2048^2 inputs.
-`cpu_baseline` / `--impl reference`: the reference's own sources (oracle/_ref, compiled unchanged)
-           timed on the host cores on a bounded sample (few iterations per method).
+`cpu_baseline` / `--impl reference`: the reference's own sources (oracle/_ref, compiled unchanged) on the host cores.
+           A full step at the GPU arm's caps takes the reference about a minute, so each CPU step is a bounded sample:
+           every method at 3 and at 6 iterations -> set-up cost and per-iteration cost per method; `value` is the work
+           of the GPU arm's step (same caps) over set-up + cap x per-iteration, i.e. what the full step would take.
+`parity`  : the result of the timed configuration compared with the fixtures sampled from the compiled reference at the
+           same size and caps (tests/golden/full2048_*.npz): iteration counts, regrid traces, max |du| on the samples.
+`batch`   : BASELINE.json configs[4], 4096 pairs of 512^2 sharded over the ranks; the LAST key of the line.
 """
 from __future__ import annotations
 
@@ -53,6 +58,8 @@ NITER = {"diffusion": 50, "curvature": 50, "elastic": 50, "thirion": 50, "diffeo
 SIGMA_B = {"fluid": 6.0}
 # algorithmic bytes per pixel per iteration, fp32 (SURVEY.md 8d / DESIGN.md)
 BYTES_PER_PX_ITER = {"diffusion": 28, "curvature": 92, "elastic": 28, "thirion": 48, "diffeomorphic": 48, "fluid": 60}
+# SURVEY.md 8(d)'s own table where it differs from the layout built here: Curvature with a 4-byte spectrum (here: double, as the reference)
+BYTES_PER_PX_ITER_SURVEY = {"diffusion": 28, "curvature": 60, "elastic": 28, "thirion": 48, "diffeomorphic": 48, "fluid": 60}
 
 
 def make_inputs(method: str, size: int):
@@ -115,31 +122,56 @@ class ClockSampler:
 # reference arm / cpu baseline: the compiled reference on host cores, bounded sample
 # --------------------------------------------------------------------------------------------------
 def _cpu_one(args):
-    method, size, niter = args
+    """One method of the step on the compiled reference: runs at n1 = 3 (its minimum) and n2 = 6 iterations; from the two
+    wall times the set-up (warp + derivatives + final compose) and the per-iteration cost follow."""
+    method, size, replica = args
     from oracle import refapi
     kind = "ref" if refapi.available("ref", 32) else "oracle"
     lib = refapi.get(kind, 32)
     R, T = make_inputs(method, size)
-    t0 = time.perf_counter()
-    out = lib.register(R, T, REG[method], PARAMS[method], [niter], nscales=0, nrefine=1, verbose=1)
-    dt = time.perf_counter() - t0
-    return method, len(out["err"]), dt, kind
+    ts, its = [], []
+    for niter in CPU_SAMPLE_ITERS:
+        t0 = time.perf_counter()
+        out = lib.register(R, T, REG[method], PARAMS[method], [niter], nscales=0, nrefine=1, verbose=1)
+        ts.append(time.perf_counter() - t0)
+        its.append(len(out["err"]))
+    return method, its, ts, kind
 
 
-def cpu_reference_step(size: int, niter: int, workers: int):
-    """One bounded CPU sample: every method for `niter` iterations (the reference always runs >= 3).
-    The reference is single-threaded per pair; the six methods run in `workers` processes."""
+CPU_SAMPLE_ITERS = (3, 6)
+
+
+def cpu_reference_step(size: int, workers: int, replicas: int = 1):
+    """One bounded CPU sample of `replicas` steps (one per GPU of the other arm): every method at 3 and at 6 iterations, the jobs
+    spread over `workers` processes (the reference is single-threaded per pair).  Returns the measured sample and the time the
+    full step (the GPU arm's iteration caps) takes at the measured set-up and per-iteration costs."""
     import multiprocessing as mp
-    jobs = [(m, size, niter) for m in METHODS]
+    jobs = [(m, size, r) for r in range(replicas) for m in METHODS]
     t0 = time.perf_counter()
     if workers > 1:
         with mp.get_context("fork").Pool(workers) as pool:
-            res = pool.map(_cpu_one, jobs)
+            res = pool.map(_cpu_one, jobs, chunksize=1)
     else:
         res = [_cpu_one(j) for j in jobs]
     wall = time.perf_counter() - t0
-    pxit = sum(r[1] for r in res) * size * size
-    return {"wall_s": wall, "pixel_iters": pxit, "per_method": {r[0]: {"iterations": r[1], "seconds": r[2]} for r in res}, "kind": res[0][3]}
+    n = size * size
+    per, full_times = {}, []
+    for method, its, ts, kind in res:
+        per_iter = max((ts[1] - ts[0]) / max(its[1] - its[0], 1), 1e-9)
+        setup = max(ts[0] - its[0] * per_iter, 0.0)
+        full = setup + NITER[method] * per_iter
+        full_times.append(full)
+        d = per.setdefault(method, {"setup_s": 0.0, "per_iteration_s": 0.0, "full_step_s": 0.0, "sample_s": 0.0, "sample_iterations": 0, "n": 0})
+        d["setup_s"] += setup; d["per_iteration_s"] += per_iter; d["full_step_s"] += full; d["sample_s"] += sum(ts); d["sample_iterations"] += sum(its); d["n"] += 1
+    for d in per.values():
+        k = d.pop("n")
+        for key in ("setup_s", "per_iteration_s", "full_step_s"):
+            d[key] /= k
+    # wall time of the full step on `workers` processes: all jobs concurrent when they fit, else bounded below by the total work
+    full_wall = max(max(full_times), sum(full_times) / workers)
+    work_full = replicas * sum(NITER[m] for m in METHODS) * n
+    return {"wall_s": wall, "sample_pixel_iters": sum(sum(r[1]) for r in res) * n, "per_method": per, "kind": res[0][3],
+            "full_step_wall_s": full_wall, "full_step_pixel_iters": work_full}
 
 
 def run_reference_arm(args):
@@ -147,25 +179,29 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     ncpu = os.cpu_count() or 1
-    workers = max(1, min(len(METHODS), ncpu))
-    niter = 3
-    for _ in range(args.warmup if args.warmup < 2 else 1):   # one warm-up pass is enough to page the library in
-        cpu_reference_step(min(args.size, 512), niter, workers)
-    tot_t, tot_px, last = 0.0, 0, None
+    replicas = max(1, args.gpus)                                  # the other arm runs one step per GPU
+    workers = max(1, min(len(METHODS) * replicas, ncpu))
+    for _ in range(args.warmup if args.warmup < 2 else 1):        # one warm-up pass is enough to page the library in
+        cpu_reference_step(min(args.size, 512), workers, 1)
+    tot_full, tot_work, tot_wall, tot_sample, last = 0.0, 0, 0.0, 0, None
     for _ in range(args.steps):
-        last = cpu_reference_step(args.size, niter, workers)
-        tot_t += last["wall_s"]; tot_px += last["pixel_iters"]
-    value = tot_px / tot_t / 1e6
-    sample = f"{niter} iterations of each of the 6 methods at {args.size}^2 per step (reference always runs >= 3), {workers} processes"
+        last = cpu_reference_step(args.size, workers, replicas)
+        tot_full += last["full_step_wall_s"]; tot_work += last["full_step_pixel_iters"]
+        tot_wall += last["wall_s"]; tot_sample += last["sample_pixel_iters"]
+    value = tot_work / tot_full / 1e6
+    sample = (f"per step: each of the 6 methods at {CPU_SAMPLE_ITERS[0]} and {CPU_SAMPLE_ITERS[1]} iterations at {args.size}^2 ({replicas} replica(s), {workers} processes, "
+              f"{tot_wall / args.steps:.1f} s wall) -> set-up and per-iteration cost per method; value = work of the full step at the GPU arm's caps "
+              f"{NITER} / (set-up + cap x per-iteration), longest process")
     line = {
         "impl": "reference", "metric": "Mpixel*iter/s (6 registration methods, aggregate)", "value": value, "unit": "Mpixel*iter/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_full / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.size),
         "cpu_baseline": {"value": value, "unit": "Mpixel*iter/s", "cores": workers, "kind": "reference" if last["kind"] == "ref" else "port",
-                         "sample": sample, "curvature_dct": "stand-in O(N log N) DCT (fftw3 not installed offline)"},
+                         "sample": sample, "measured_sample_mpix_iter_s": tot_sample / tot_wall / 1e6, "measured_sample_wall_s_per_step": tot_wall / args.steps,
+                         "per_method": last["per_method"], "curvature_dct": "stand-in O(N log N) DCT (fftw3 not installed offline)"},
         "e2e": {"value": value, "unit": "Mpixel*iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "methods": {m: {"mpix_iter_s": args.size * args.size * v["iterations"] / v["seconds"] / 1e6} for m, v in last["per_method"].items()},
+        "methods": {m: {"mpix_iter_s": args.size * args.size * NITER[m] / v["full_step_s"] / 1e6} for m, v in last["per_method"].items()},
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -174,7 +210,8 @@ def run_reference_arm(args):
 def workload_config(size: int) -> dict:
     return {"workload": f"c4_all_methods_{size}x{size}_f32", "size": [size, size], "nscales": 0, "nrefine": 1,
             "niter_cap": NITER, "regparams": PARAMS, "input": "lattice sigma_b=8 (fluid: 6) + texture, shift (1.5,-0.75) px",
-            "l2": "six sessions (about 1 GB of fields) are cycled every step, so each method starts from HBM; no extra flush"}
+            "l2": "six sessions (about 1 GB of fields) are cycled every step, so each method starts from HBM; no extra flush",
+            "arithmetic": "level 2 (relaxed engine) unless OF2D_MATH says otherwise; parity against the compiled reference is reported in `parity`"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -183,8 +220,17 @@ def workload_config(size: int) -> dict:
 # algorithmic bytes per pixel per launch of the engine kernels, fp32 (DESIGN.md "Kernels")
 KERNEL_BYTES_PER_PX = {
     "hs_iter": 28, "hs_pair": 28, "conv": 16, "conv_logger": 24, "conv_maxabs": 16, "demons_force": 24, "compose": 24, "square": 16,
+    "force_conv": 24, "force_conv_maxabs": 24, "compose_conv_logger": 24,
     "sor_tile_elastic": 28, "sor_tile_fluid": 44, "fluid_integrate": 24,
     "curv_rows_fwd": 36, "curv_cols": 32, "curv_rows_inv": 32, "curv_rows_inv_fwd": 60, "regrid_compose": 24, "regrid_rewarp": 36, "final_compose": 24,
+}
+# SURVEY.md 8(d) budgets the Fluid sweep (its kernel K-a) at 36 B/px: the 8 more are the increment this build materialises
+KERNEL_BYTES_PER_PX_SURVEY = {"sor_tile_fluid": 36}
+# launches whose event time is not an HBM measurement: a single L2-resident closing launch / self-gated launches that are mostly empty
+KERNEL_NOTES = {
+    "hs_iter": "one closing launch per refine pass on L2-resident fields (the iterations run in hs_pair): not an HBM measurement",
+    "square": "enqueued nsq_cap times per iteration and self-gated: most launches return at once, the average mixes empty and real launches",
+    "regrid_compose": "self-gated: runs only after iterations that ask for a regrid", "regrid_rewarp": "self-gated: runs only after iterations that ask for a regrid",
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/), 2048^2 fp32
 NCU_TRAFFIC_BYTES = {}
@@ -228,6 +274,37 @@ def cpu_batch_sample(method: str, size: int, niter: int, workers: int):
     wall = time.perf_counter() - t0
     return {"pairs_per_s": workers / wall, "cores": workers, "mean_iterations": float(np.mean([r[0] for r in res])),
             "sample": f"{workers} pairs of {size}^2 ({method}, niter cap {niter}), one process per pair, {wall:.1f} s wall"}
+
+
+def parity_check(of, sessions, size):
+    """The state the timed steps left behind (every session holds the result of a full step) against the fixtures sampled from the
+    COMPILED REFERENCE at this size and these caps (tests/golden/full2048_<method>.npz, tests/golden/make_golden_full.py):
+    iteration count, regrid trace, max |du| on the 64 x 64 sample lattice.  `ok` = north-star bar (1e-3 px, identical control flow)."""
+    out = {"ok": True, "methods": {}}
+    for m, s in sessions.items():
+        path = os.path.join(ROOT, "tests", "golden", f"full{size}_{m}.npz")
+        if not os.path.exists(path):
+            out["methods"][m] = {"fixture": None}
+            continue
+        g = np.load(path)
+        if int(g["niter"]) != NITER[m]:
+            out["methods"][m] = {"fixture": "cap differs"}
+            continue
+        tr = s.trace()["levels"][0]
+        mo = s.motion()
+        st, off = int(g["stride"]), int(g["offset"])
+        d = np.abs(mo[off::st, off::st] - g["sample"].astype(np.float64)).max(axis=2)
+        pos = off + st * np.arange(d.shape[0])
+        inner = (pos >= 8) & (pos < size - 8)     # within 8 px of the border the reference's own fp32 / fp64 builds differ by up to O(1) px (tests/test_fullsize_gpu.py)
+        du, du_border = float(d[np.ix_(inner, inner)].max()), float(d.max())
+        same_it = tr["iterations"] == len(g["err"])
+        same_rg = bool(np.array_equal(np.asarray(tr["regrid_iter"], dtype=int), g["regrid_iter"].astype(int)))
+        ok = same_it and same_rg and du <= 1e-3
+        out["methods"][m] = {"iterations_match": bool(same_it), "regrid_trace_matches": same_rg, "regrids": int(len(g["regrid_iter"])), "max_du_sampled_px": du,
+                             "max_du_sampled_px_incl_border_zone": du_border, "ok": bool(ok)}
+        out["ok"] = out["ok"] and bool(ok)
+    out["against"] = "tests/golden/full%d_*.npz (compiled reference, fp32, same caps)" % size
+    return out
 
 
 def run_ours(args):
@@ -305,6 +382,7 @@ def run_ours(args):
         return iters, ms, wall, launches, clocks
 
     iters, ms, wall, launches, clocks = timed(False)
+    parity = parity_check(of, sessions, size) if (rank == 0 and not args.quick) else None
     if args.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "ms": ms, "iterations": iters, "gpu_launches": int(launches)}), flush=True)
@@ -325,8 +403,13 @@ def run_ours(args):
             bpp = KERNEL_BYTES_PER_PX.get(name)
             avg = tms / max(cnt, 1)
             kern[name] = {"launches": cnt, "avg_ms": avg, "share_of_step": tms / tot_ms, "bytes_per_px": bpp,
-                          "gbs": (bpp * n / (avg * 1e-3) / 1e9) if bpp else None}
-        dom = next((k for k in kern if kern[k]["bytes_per_px"]), None)
+                          "gbs": (bpp * n / (avg * 1e-3) / 1e9) if (bpp and name not in KERNEL_NOTES) else None}
+            if name in KERNEL_BYTES_PER_PX_SURVEY:
+                kern[name]["bytes_per_px_survey"] = KERNEL_BYTES_PER_PX_SURVEY[name]
+                kern[name]["gbs_survey_bytes"] = KERNEL_BYTES_PER_PX_SURVEY[name] * n / (avg * 1e-3) / 1e9
+            if name in KERNEL_NOTES:
+                kern[name]["note"] = KERNEL_NOTES[name]
+        dom = next((k for k in kern if kern[k]["gbs"]), None)
     for s in sessions.values():
         s.close()
     sessions.clear()
@@ -351,16 +434,20 @@ def run_ours(args):
             mp = n * it / (ts[-1] * 1e-3) / 1e6
             f64[m] = {"iterations": it, "ms": ts[-1], "mpix_iter_s": mp, "gbs_algorithmic": mp * 1e6 * 2 * BYTES_PER_PX_ITER[m] / 1e9}
 
-    # ---- batched slice registration (BASELINE.json configs[4]): BATCH pairs of 512^2 per GPU, no collective in the solve
+    # ---- batched slice registration (BASELINE.json configs[4]): --batch pairs of 512^2 IN TOTAL, sharded over the ranks in
+    # contiguous ranges (no collective in the solve).  A rank keeps at most 512 distinct pairs in pinned host memory and goes
+    # through its shard in chunks of that size (the inputs of chunk c are pairs lo + c*512 ... modulo the distinct ones).
     batch_res = {}
     if args.batch > 0:
-        B, bp = args.batch, BATCH_PX
-        lo, hi = of.shard_pairs(B * world, world, rank)
-        Rb, Tb = make_batch_inputs(lo, hi, bp)
+        bp = BATCH_PX
+        lo, hi = of.shard_pairs(args.batch, world, rank)
+        mine = hi - lo
+        B = max(1, min(mine, 512))                      # pairs per call (and distinct inputs held by this rank)
+        ncalls = max(1, -(-mine // B))
+        Rb, Tb = make_batch_inputs(lo, lo + B, bp)
         prb = torch.from_numpy(Rb).pin_memory(); ptb = torch.from_numpy(Tb).pin_memory()
         pob = torch.empty((B, 2, bp, bp), dtype=torch.float64).pin_memory()
         del Rb, Tb
-        bsteps = max(1, min(args.steps, 2))
         for m in BATCH_METHODS:
             bt = of.Batch((bp, bp), B, BATCH_NITER[m], REG[m], PARAMS[m], nrefine=1, wave=min(B, 256), bits=32)
             bt.set_images_raw(prb.data_ptr(), ptb.data_ptr())
@@ -369,31 +456,33 @@ def run_ours(args):
                 def bstep():
                     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                     e0.record()
-                    if leg == "e2e":
-                        bt.set_images_raw(prb.data_ptr(), ptb.data_ptr())
-                    bt.estimate()
-                    if leg == "e2e":
-                        bt.motion_raw(pob.data_ptr())
+                    for _ in range(ncalls):
+                        if leg == "e2e":
+                            bt.register_raw(prb.data_ptr(), ptb.data_ptr(), pob.data_ptr())   # streamed: copies of neighbouring waves under the solve
+                        else:
+                            bt.estimate()
                     e1.record()
                     return e0, e1
-                bstep()
+                bt.estimate() if leg == "resident" else bt.register_raw(prb.data_ptr(), ptb.data_ptr(), pob.data_ptr())   # warm-up of the leg
                 barrier()
-                evs = [bstep() for _ in range(bsteps)]
+                ev = bstep()
                 barrier()
-                sec = sum(a.elapsed_time(b) for a, b in evs) * 1e-3 / bsteps
+                sec = ev[0].elapsed_time(ev[1]) * 1e-3
                 its, rg = bt.iterations()
                 v = torch.tensor([sec], device="cuda", dtype=torch.float64)
-                w = torch.tensor([float(B), float(its.sum())], device="cuda", dtype=torch.float64)
+                w = torch.tensor([float(B * ncalls), float(its.sum()) * ncalls], device="cuda", dtype=torch.float64)
                 if world > 1:
                     dist.all_reduce(v, op=dist.ReduceOp.MAX)
                     dist.all_reduce(w, op=dist.ReduceOp.SUM)
                 res[leg] = {"pairs_per_s": float(w[0]) / float(v[0]), "seconds": float(v[0]),
                             "mpix_iter_s": float(w[1]) * bp * bp / float(v[0]) / 1e6}
                 res["mean_iterations"] = float(w[1]) / float(w[0])
+                res["pairs"] = int(w[0])
             bt.close()
             batch_res[m] = res
-        batch_res["config"] = {"workload": f"c5_batch_{bp}x{bp}", "pairs_per_gpu": B, "total_pairs": B * world, "niter_cap": BATCH_NITER,
-                               "wave": min(B, 256), "h2d_bytes_per_pair": 2 * bp * bp * 8, "d2h_bytes_per_pair": 2 * bp * bp * 8,
+        batch_res["config"] = {"workload": f"c5_batch_{bp}x{bp}", "total_pairs": args.batch, "n_gpus": world, "pairs_per_call": B, "calls_per_rank": ncalls,
+                               "niter_cap": BATCH_NITER, "wave": min(B, 256), "h2d_bytes_per_pair": 2 * bp * bp * 8, "d2h_bytes_per_pair": 2 * bp * bp * 8,
+                               "e2e": "of2d_batch_register: pinned host doubles in, planar doubles out, copies of wave k+1 / k-1 under the solve of wave k",
                                "sharding": "contiguous pair ranges per rank, no collective in the solve"}
         del prb, ptb, pob
 
@@ -426,14 +515,18 @@ def run_ours(args):
             mp = n * iters[m] / (ms[m] * 1e-3) / 1e6
             gbs = mp * 1e6 * BYTES_PER_PX_ITER[m] / 1e9
             methods[m] = {"iterations": iters[m], "ms": ms[m], "mpix_iter_s": mp, "gbs_algorithmic": gbs, "frac_of_hbm_peak": gbs / peak,
-                          "e2e_ms": ms_e[m]}
+                          "bytes_per_px_iter": BYTES_PER_PX_ITER[m], "bytes_per_px_iter_survey": BYTES_PER_PX_ITER_SURVEY[m],
+                          "frac_of_hbm_peak_survey_bytes": mp * 1e6 * BYTES_PER_PX_ITER_SURVEY[m] / 1e9 / peak, "e2e_ms": ms_e[m]}
         ncpu = os.cpu_count() or 1
         workers = max(1, min(len(METHODS), ncpu))
-        c = cpu_reference_step(size, 3, workers)
-        cpu = {"value": c["pixel_iters"] / c["wall_s"] / 1e6, "unit": "Mpixel*iter/s", "cores": workers,
+        c = cpu_reference_step(size, workers, 1)
+        cpu = {"value": c["full_step_pixel_iters"] / c["full_step_wall_s"] / 1e6, "unit": "Mpixel*iter/s", "cores": workers,
                "kind": "reference" if c["kind"] == "ref" else "port",
-               "sample": f"3 iterations of each of the 6 methods at {size}^2, {workers} processes, {c['wall_s']:.1f} s wall",
-               "per_method_mpix_iter_s": {m: n * v["iterations"] / v["seconds"] / 1e6 for m, v in c["per_method"].items()},
+               "sample": (f"each of the 6 methods at {CPU_SAMPLE_ITERS[0]} and {CPU_SAMPLE_ITERS[1]} iterations at {size}^2, {workers} processes, {c['wall_s']:.1f} s wall -> set-up and "
+                          f"per-iteration cost per method; value = work of the full step at the GPU arm's caps / (set-up + cap x per-iteration), longest process"),
+               "measured_sample_mpix_iter_s": c["sample_pixel_iters"] / c["wall_s"] / 1e6,
+               "per_method": c["per_method"],
+               "per_method_mpix_iter_s": {m: n * NITER[m] / v["full_step_s"] / 1e6 for m, v in c["per_method"].items()},
                "curvature_dct": "stand-in O(N log N) DCT (fftw3 not installed offline)"}
         if args.batch > 0:
             bw = max(1, min(ncpu, 16))
@@ -448,16 +541,20 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
                          "frac": kern[dom]["gbs"] / peak, "traffic": NCU_TRAFFIC_BYTES.get(dom), "peak_source": peak_src,
+                         "frac_survey_bytes": (kern[dom].get("gbs_survey_bytes") or kern[dom]["gbs"]) / peak,
                          "share_of_step": kern[dom]["share_of_step"], "avg_launch_ms": kern[dom]["avg_ms"],
                          "algorithmic_bytes_per_launch": kern[dom]["bytes_per_px"] * n,
                          "how": "CUDA events around every engine launch of one extra (untimed) step, on the launching stream"} if dom else None,
             "kernels": kern,
             "methods": methods,
             "methods_f64": {m: dict(v, frac_of_hbm_peak=v["gbs_algorithmic"] / peak) for m, v in f64.items()},
-            "batch": batch_res,
+            "parity": parity,
+            "math_level": {0: "strict", 1: "exact", 2: "relaxed"}.get(of.get_math(32)),
             "cpu_baseline": cpu,
             "wall_s_timed_region": wall,
             "loaded_libraries": [os.path.relpath(p, ROOT) for p in of.loaded_libraries()],
+            # LAST key (the driver keeps the tail of the line): BASELINE.json configs[4], pairs/s over all ranks
+            "batch": batch_res,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -473,7 +570,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--size", type=int, default=2048)
-    ap.add_argument("--batch", type=int, default=512, help="pairs of 512^2 per GPU in the batched leg (0 = skip); 8 GPUs x 512 = BASELINE's 4096")
+    ap.add_argument("--batch", type=int, default=4096, help="pairs of 512^2 in the batched leg IN TOTAL, sharded over the ranks (0 = skip); BASELINE configs[4]: 4096")
     ap.add_argument("--no-fp64", dest="fp64", action="store_false", help="skip the fp64-mode leg")
     ap.add_argument("--quick", action="store_true", help="timed region only (no e2e leg, kernel microbench or CPU baseline): for ncu launch lists")
     ap.add_argument("--methods", default=",".join(list(METHODS)), help="comma-separated subset (profiling only; the default is the benchmark)")

@@ -51,6 +51,11 @@ int of2d_ctx_set_stream(of2d_ctx *ctx, void *cuda_stream);
 int of2d_ctx_use_own_stream(of2d_ctx *ctx);
 void *of2d_ctx_get_stream(of2d_ctx *ctx);
 int of2d_ctx_sync(of2d_ctx *ctx);
+/* several contexts in one process (one per GPU and host thread, or extra copy streams on one GPU): make the context's
+   device current for the calling host thread; order the waiter's stream after everything enqueued on the signaller's so far */
+int of2d_ctx_make_current(of2d_ctx *ctx);
+int of2d_ctx_device(of2d_ctx *ctx);
+int of2d_ctx_wait_for(of2d_ctx *waiter, of2d_ctx *signaller);
 /* arithmetic level of the context (read when an engine is created / a driver loop starts):
      0  strict : the host classes run the reference's loop literally, one per-step kernel per call; every value is
                  the reference's expression in the reference's operation order, unfused (bit-exact parity pin);

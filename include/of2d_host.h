@@ -66,10 +66,20 @@ int of2d_session_get_motion(of2d_session *s, double *planar_out);      /* 2*N do
 int of2d_session_get_motion_aos(of2d_session *s, void *out_real);       /* N {x,y} pairs in the field precision */
 int of2d_session_warp(of2d_session *s, const double *img, double *out);
 
+/* the reference's public Image / Motion / Kernel methods that no driver calls, on host arrays:
+   op 0: Image::sum / max / min -> scalars[0..2] (src/Image.cpp:78-104); op 1: Image::normalize -> out (:107-116);
+   op 2: Image::convolute with Kernel::set_gaussian(sigma) when sigma > 0, else Kernel::set_average -> out (:184-187;
+   the reference leaves its float accumulator uninitialised there, src/Field.tpp:240 -- here it starts from zero).
+   Images: dimx*dimy column-major doubles; motions: dimx*dimy {x, y} double pairs. */
+int of2d_host_image_op(int op, int dimx, int dimy, const double *in, double *out, double *scalars, int kernel_w, double sigma);
+int of2d_host_motion_boundary(int kind, int dimx, int dimy, const double *aos_in, double *aos_out);   /* 0 Neumann, 1 Dirichlet (src/Motion.cpp:181-251) */
+int of2d_host_kernel(int kind, int w, double sigma, double *out);                                      /* 0 Gaussian, 1 average (src/Kernel.cpp:45-82) */
+
 /* extension: `batch` independent pairs of one size registered together on this process's GPU (BASELINE.json
    configs[4]; one level, cold start per pair = what a fresh ImageRegistration* object with nscales = 0 computes).
    Iref / Imov: batch images back to back; planar_out: per pair the x plane then the y plane.
-   wave: pairs resident in the engine at a time (0 = default); batch must be a multiple of it. */
+   wave: pairs resident in the engine at a time (0 = default 256); the waves are balanced and a partial last wave is
+   padded internally, so any batch size works. */
 typedef struct of2d_batch of2d_batch;
 int of2d_batch_create(int dimx, int dimy, int batch, int niter, int nrefine, int reg, const double *regparams, int nparams, int wave, of2d_batch **out);
 void of2d_batch_destroy(of2d_batch *b);
@@ -78,6 +88,20 @@ int of2d_batch_estimate(of2d_batch *b);
 int of2d_batch_get_motion(of2d_batch *b, double *planar_out);
 int of2d_batch_iterations(of2d_batch *b, int *iterations, int *regrids);
 int of2d_batch_wave(of2d_batch *b);
+/* streamed protocol: set_images + estimate + get_motion in one call, wave by wave, with the host -> device copy of wave
+   k + 1 and the device -> host copy of wave k - 1 under the solve of wave k (overlap needs pinned host buffers) */
+int of2d_batch_register(of2d_batch *b, const double *Iref, const double *Imov, double *planar_out);
+/* cine chains: `frames` consecutive frame pairs of batch / frames independent sequences, frame-major (pair f * S + s);
+   frame f starts from the motion (Fluid: and the velocity) frame f - 1 ended with -- what the reference does when
+   estimate_motion() is called again on one object (src/ImageRegistration.cpp:135-139, OpticalFlowFluid.cpp:50,128) */
+int of2d_batch_create_chain(int dimx, int dimy, int batch, int frames, int niter, int nrefine, int reg, const double *regparams, int nparams, of2d_batch **out);
+/* one process, several GPUs: the pairs are sharded in contiguous ranges over `devices`; every shard has its own
+   context, streams and host thread; there is no exchange between shards.  All of2d_batch_* calls work on the result. */
+int of2d_batch_create_multi(int dimx, int dimy, int batch, int niter, int nrefine, int reg, const double *regparams, int nparams, int wave,
+                            const int *devices, int ndevices, of2d_batch **out);
+int of2d_shard_range(int total, int world, int rank, int *lo, int *hi);   /* the partition (pure host arithmetic; 0 = ok) */
+int of2d_batch_num_shards(of2d_batch *b);
+int of2d_batch_shard_info(of2d_batch *b, int shard, int *device, int *lo, int *hi);
 
 /* trace of the last estimate_motion(); s == NULL addresses the MEX singleton */
 int of2d_trace_num_levels(of2d_session *s);

@@ -277,13 +277,42 @@ class Batch:
     """`batch` independent pairs registered together (extension, include/of2d_host.h of2d_batch_*).
     Images: (batch, dimy, dimx) float64; motion: (batch, dimy, dimx, 2)."""
 
-    def __init__(self, dims, batch: int, niter: int, reg: int, regparams, nrefine: int = 1, wave: int = 0, bits: int = 32):
+    def __init__(self, dims, batch: int, niter: int, reg: int, regparams, nrefine: int = 1, wave: int = 0, bits: int = 32, frames: int = 1, devices=None):
+        """frames > 1: cine chains (frame-major batch, frame f warm-starts from frame f - 1: of2d_batch_create_chain);
+        devices = [d0, d1, ...]: the pairs are sharded over these GPUs inside this process (of2d_batch_create_multi)."""
         self.lib = host(bits)
         dimx, dimy = dims
         self.shape = (batch, dimy, dimx)
         params = _f64(list(regparams) if len(regparams) else [0.0])
         self.handle = C.c_void_p()
-        _check(self.lib, self.lib.of2d_batch_create(dimx, dimy, batch, niter, nrefine, reg, _ptr(params), len(regparams), wave, C.byref(self.handle)))
+        if frames > 1:
+            assert devices is None, "cine chains run on one device"
+            _check(self.lib, self.lib.of2d_batch_create_chain(dimx, dimy, batch, frames, niter, nrefine, reg, _ptr(params), len(regparams), C.byref(self.handle)))
+        elif devices is not None:
+            dev = np.ascontiguousarray(np.asarray(devices, dtype=np.int32))
+            _check(self.lib, self.lib.of2d_batch_create_multi(dimx, dimy, batch, niter, nrefine, reg, _ptr(params), len(regparams), wave, _ptr(dev), len(dev), C.byref(self.handle)))
+        else:
+            _check(self.lib, self.lib.of2d_batch_create(dimx, dimy, batch, niter, nrefine, reg, _ptr(params), len(regparams), wave, C.byref(self.handle)))
+
+    def register(self, Iref, Imov) -> np.ndarray:
+        """Streamed protocol (of2d_batch_register): copies of the neighbouring waves run under the solve of the current one."""
+        Iref, Imov = _f64(Iref), _f64(Imov)
+        assert Iref.shape == self.shape and Imov.shape == self.shape
+        b, dimy, dimx = self.shape
+        planar = np.zeros((b, 2, dimy, dimx))
+        _check(self.lib, self.lib.of2d_batch_register(self.handle, _ptr(Iref), _ptr(Imov), _ptr(planar)))
+        return np.ascontiguousarray(np.moveaxis(planar, 1, -1))
+
+    def register_raw(self, Iref_ptr: int, Imov_ptr: int, out_ptr: int):
+        _check(self.lib, self.lib.of2d_batch_register(self.handle, C.c_void_p(Iref_ptr), C.c_void_p(Imov_ptr), C.c_void_p(out_ptr)))
+
+    def shards(self):
+        out = []
+        for k in range(int(self.lib.of2d_batch_num_shards(self.handle))):
+            d, lo, hi = C.c_int(), C.c_int(), C.c_int()
+            _check(self.lib, self.lib.of2d_batch_shard_info(self.handle, k, C.byref(d), C.byref(lo), C.byref(hi)))
+            out.append((d.value, lo.value, hi.value))
+        return out
 
     def set_images(self, Iref, Imov):
         Iref, Imov = _f64(Iref), _f64(Imov)

@@ -34,7 +34,7 @@ NVCC_FLAGS = [
 EXACT_FLAGS = ["-fmad=false"]
 # ... except *_relaxed.cu (the second build of the iteration engine, arithmetic level 2)
 RELAXED_FLAGS = ["-fmad=true", "-prec-div=false", "-prec-sqrt=false"]
-CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-Wno-unused-function", "-I" + os.path.join(ROOT, "include"), "-I" + HOST, "-I" + os.path.join(HOST, "mex")]
+CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-pthread", "-Wall", "-Wno-unused-function", "-I" + os.path.join(ROOT, "include"), "-I" + HOST, "-I" + os.path.join(HOST, "mex")]
 
 
 def _nvcc() -> str:

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -20,9 +21,14 @@ struct of2d_profiler {
 };
 
 int of2d_ensure_dynamic_smem(const void *kernel, size_t bytes) {
-    static std::map<const void *, size_t> configured;
+    // cudaFuncSetAttribute is per device: one record per (device, kernel), guarded for concurrent host threads
+    static std::map<std::pair<int, const void *>, size_t> configured;
+    static std::mutex mu;
     if (bytes <= 48 * 1024) return OF2D_SUCCESS;
-    size_t &cur = configured[kernel];
+    int dev = 0;
+    OF2D_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &cur = configured[std::make_pair(dev, kernel)];
     if (bytes > cur) {
         OF2D_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         cur = bytes;
@@ -117,6 +123,20 @@ int of2d_ctx_use_own_stream(of2d_ctx *c) {
 void *of2d_ctx_get_stream(of2d_ctx *c) { return (void *)c->stream; }
 int of2d_ctx_sync(of2d_ctx *c) {
     OF2D_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return OF2D_SUCCESS;
+}
+int of2d_ctx_make_current(of2d_ctx *c) {
+    OF2D_CUDA_TRY(cudaSetDevice(c->device));
+    return OF2D_SUCCESS;
+}
+int of2d_ctx_device(of2d_ctx *c) { return c->device; }
+int of2d_ctx_wait_for(of2d_ctx *waiter, of2d_ctx *signaller) {
+    // everything enqueued on the signaller's stream so far happens before whatever the waiter's stream is given next
+    cudaEvent_t ev;
+    OF2D_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    OF2D_CUDA_TRY(cudaEventRecord(ev, signaller->stream));
+    OF2D_CUDA_TRY(cudaStreamWaitEvent(waiter->stream, ev, 0));
+    OF2D_CUDA_TRY(cudaEventDestroy(ev));   // released once the recorded work completes
     return OF2D_SUCCESS;
 }
 int of2d_ctx_set_fast_math(of2d_ctx *c, int on) {

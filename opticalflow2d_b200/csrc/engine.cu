@@ -30,7 +30,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <new>
+#include <tuple>
 #include <vector>
 
 #include "device_math.cuh"
@@ -38,6 +41,7 @@
 #include "engine_internal.cuh"
 
 #include "engine_kernels.cuh"
+#include "engine_fused.cuh"
 #include "sor_tile.cuh"
 
 // =================================================================================================
@@ -95,11 +99,18 @@ inline int ctas_per_sm(const void *kernel, size_t smem) {
     static int forced = -1;
     if (forced < 0) { const char *e = getenv("OF2D_CTAS_PER_SM"); forced = e && atoi(e) > 0 ? atoi(e) : 0; }
     if (forced) return forced;
-    static std::vector<std::pair<std::pair<const void *, size_t>, int>> cache;
-    for (const auto &c : cache) if (c.first.first == kernel && c.first.second == smem) return c.second;
+    // occupancy depends on the kernel's attributes on the CURRENT device: keyed by (device, kernel, smem), guarded
+    static std::map<std::tuple<int, const void *, size_t>, int> cache;
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_tuple(dev, kernel, smem);
+    const auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TX * TY, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 4; }
-    cache.push_back({{kernel, smem}, occ});
+    cache[key] = occ;
     return occ;
 }
 template <class KernelT>
@@ -170,6 +181,80 @@ int launch_conv(of2d_engine *E, const EngK<R> &K, int src, int dst, int which) {
 }
 
 
+#if OF2D_RELAXED
+// Demons in two fused kernels (engine_fused.cuh): kernel widths 3 and 5 (the default) whose taps are separable (Gaussians are)
+// OF2D_FUSED: 0 off, 1 both kernels (default), 2 only the force + smoothing kernel, 3 only the compose + smoothing kernel;
+// OF2D_FUSED_NOFAST=1: every tile takes the general (border) path -- experiments only
+inline int fused_demons_mode() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("OF2D_FUSED"); on = e ? atoi(e) : 1; if (on < 0 || on > 3) on = 1; }
+    return on;
+}
+inline int fused_nofast() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("OF2D_FUSED_NOFAST"); v = e && atoi(e) != 0 ? 1 : 0; }
+    return v;
+}
+template <class R, int KW>
+int enqueue_fused_demons_kw(of2d_engine *E, const EngK<R> &K, const R *d_Iref, const ConvW<R> &Wf, const ConvW<R> &Wd) {
+    cudaStream_t s = E->ctx->stream;
+    const dim3 b(TX, TY);
+    const of2d_engine_desc &d = E->d;
+    const R si = (R)d.sigma_i, sx = (R)d.sigma_x;
+    const R sratio = (si * si) / (sx * sx);
+    const size_t sm1 = fused_smem_force<R, KW>(), sm2 = fused_smem_compose<R, KW>();
+    const int mode = fused_demons_mode(), nf = fused_nofast();
+    const R sxsq = sx * sx;
+    int ex = 0;
+    const R inv_sxsq = (sxsq > 0 && frexp((double)sxsq, &ex) == 0.5 && ex > -100 && ex < 100) ? (R)ldexp(1.0, 1 - ex) : (R)0;
+    if (mode == 3) {   // unfused first half: force -> C0, smoothing C0 -> C1
+        { ProfScope _ps(E->ctx, "demons_force"); pdl_launch(k_e_demons_force<R>, grid_tiles(E, k_e_demons_force<R>), b, 0, s, K, d_Iref, (const R *)E->aux, si * si, sxsq, inv_sxsq); }
+        OF2D_LAUNCH_CHECK(E->ctx);
+        if (d.method == 3) TRY((launch_conv<R, 0>(E, K, B_C0, B_C1, 0))); else TRY((launch_conv<R, 2>(E, K, B_C0, B_C1, 0)));
+    } else if (d.method == 3) {
+        TRY(of2d_ensure_dynamic_smem((const void *)k_rx_force_conv<R, 0, KW>, sm1));
+        { ProfScope _ps(E->ctx, "force_conv"); pdl_launch(k_rx_force_conv<R, 0, KW>, grid_tiles(E, k_rx_force_conv<R, 0, KW>, sm1), b, sm1, s, K, d_Iref, (const R *)E->aux, sratio, Wf, (int)B_C1, E->nsq_cap, nf); }
+        OF2D_LAUNCH_CHECK(E->ctx);
+    } else {
+        TRY(of2d_ensure_dynamic_smem((const void *)k_rx_force_conv<R, 2, KW>, sm1));
+        { ProfScope _ps(E->ctx, "force_conv_maxabs"); pdl_launch(k_rx_force_conv<R, 2, KW>, grid_tiles(E, k_rx_force_conv<R, 2, KW>, sm1), b, sm1, s, K, d_Iref, (const R *)E->aux, sratio, Wf, (int)B_C1, E->nsq_cap, nf); }
+        OF2D_LAUNCH_CHECK(E->ctx);
+    }
+    if (d.method == 4)
+        for (int q = 0; q < E->nsq_cap; q++) {
+            { ProfScope _ps(E->ctx, "square"); pdl_launch(k_e_square<R>, grid_tiles(E, k_e_square<R>), b, 0, s, K, q); }
+            OF2D_LAUNCH_CHECK(E->ctx);
+        }
+    if (mode == 2) {   // unfused second half
+        if (d.method == 3) {
+            { ProfScope _pc(E->ctx, "compose"); pdl_launch(k_e_compose<R, false>, grid_tiles(E, k_e_compose<R, false>), b, 0, s, K, G_ACTIVE, B_EST_CUR, B_C1, B_C0, d.accumulation == 1); }
+            OF2D_LAUNCH_CHECK(E->ctx);
+            TRY((launch_conv<R, 1>(E, K, B_C0, B_EST_NEXT, 1)));
+        } else {
+            { ProfScope _pc(E->ctx, "compose"); pdl_launch(k_e_compose<R, false>, grid_tiles(E, k_e_compose<R, false>), b, 0, s, K, G_ACTIVE, B_EST_CUR, B_CRES, B_CTMP, 0); }
+            OF2D_LAUNCH_CHECK(E->ctx);
+            TRY((launch_conv<R, 1>(E, K, B_CTMP, B_EST_NEXT, 1)));
+        }
+        return OF2D_SUCCESS;
+    }
+    TRY(of2d_ensure_dynamic_smem((const void *)k_rx_compose_conv<R, KW>, sm2));
+    { ProfScope _pc(E->ctx, "compose_conv_logger"); pdl_launch(k_rx_compose_conv<R, KW>, grid_tiles(E, k_rx_compose_conv<R, KW>, sm2), b, sm2, s, K, d.method == 3 ? (int)B_C1 : (int)B_CRES, d.method == 3 && d.accumulation == 1 ? 1 : 0, Wd, nf); }
+    OF2D_LAUNCH_CHECK(E->ctx);
+    return OF2D_SUCCESS;
+}
+// returns 1 when the iteration was enqueued, 0 when the unfused sequence has to run, < 0 on error
+template <class R>
+int enqueue_fused_demons(of2d_engine *E, const EngK<R> &K, const R *d_Iref) {
+    if (!fused_demons_mode()) return 0;
+    const int kw = E->d.kernel_w;
+    if ((kw != 3 && kw != 5) || E->n >= (size_t)0x7fff0000u) return 0;   // wider kernels / larger fields: the unfused sequence
+    const ConvW<R> Wf = conv_weights<R>(E, 0), Wd = conv_weights<R>(E, 1);
+    if (!Wf.separable || !Wd.separable) return 0;
+    int st = kw == 3 ? enqueue_fused_demons_kw<R, 3>(E, K, d_Iref, Wf, Wd) : enqueue_fused_demons_kw<R, 5>(E, K, d_Iref, Wf, Wd);
+    return st ? -st : 1;
+}
+#endif
+
 // one iteration of method `m`, enqueued on the context's stream
 template <class R>
 int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref, int curv_flags = 0) {
@@ -192,6 +277,9 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref, int cur
             break;
         case 3:
         case 4: {
+#if OF2D_RELAXED
+            { const int f = enqueue_fused_demons<R>(E, K, d_Iref); if (f < 0) return -f; if (f > 0) break; }
+#endif
             const R si = (R)d.sigma_i, sx = (R)d.sigma_x;
             const R sxsq = sx * sx;
             int ex = 0;
@@ -392,7 +480,7 @@ int ENG(create)(of2d_ctx *ctx, const of2d_engine_desc *desc, of2d_engine_head **
     int st = OF2D_SUCCESS;
     auto fail = [&](int code) { ENG(destroy)(&E->head); return code; };
     if (E->transposed) {
-        E->sor = sor_plan(nx, ny, B, desc->mu, desc->lambda, desc->omega, E->dbl, m == 5);
+        E->sor = sor_plan(nx, ny, B, desc->mu, desc->lambda, desc->omega, E->dbl, m == 5, ctx->sm_count);
         if (!E->sor.supported) {
             of2d_set_error("engine: SOR parameters (mu %g, lambda %g, omega %g) do not contract fast enough for the tiled sweep", desc->mu, desc->lambda, desc->omega);
             return fail(OF2D_ERR_UNSUPPORTED);

@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
 }  // namespace
 
 // halo widths from the contraction of the sweep; supported = 0 when the parameters do not contract
-static inline SorPlan sor_plan(int nx, int ny, int batch, double mu, double lambda, double omega, bool dbl, bool fluid) {
+static inline SorPlan sor_plan(int nx, int ny, int batch, double mu, double lambda, double omega, bool dbl, bool fluid, int sm_count = 148) {
     SorPlan S;
     memset(&S, 0, sizeof(S));
     S.nx = nx; S.ny = ny; S.batch = batch;
@@ -529,7 +529,7 @@ static inline SorPlan sor_plan(int nx, int ny, int batch, double mu, double lamb
         if (fit < per_sm) per_sm = fit < 1 ? 1 : fit;
     }
     { const char *e = getenv("OF2D_SOR_PER_SM"); if (e && atoi(e) > 0) per_sm = atoi(e); }
-    long want = 148L * per_sm / ((long)batch * S.nstrips);
+    long want = (long)sm_count * per_sm / ((long)batch * S.nstrips);
     if (want < 1) want = 1;
     S.BX = ceil_div(nx - 2, (int)want);
     if (S.BX < S.HW) S.BX = S.HW;

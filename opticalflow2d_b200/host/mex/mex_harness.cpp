@@ -6,7 +6,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <exception>
+#include <functional>
 #include <stdexcept>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -16,6 +19,7 @@
 #include <src/BatchRegistration.h>
 #include <src/DeviceRuntime.h>
 #include <src/Image.h>
+#include <src/Kernel.h>
 #include <src/ImageRegistrationDemons.h>
 #include <src/ImageRegistrationFluid.h>
 #include <src/ImageRegistrationOpticalFlow.h>
@@ -217,42 +221,174 @@ int of2d_session_warp(of2d_session* s, const double* img, double* out) {
     });
 }
 
+// ---- the public Image / Motion / Kernel methods that no driver calls, for callers without C++ ------------
+// Images cross as column-major doubles (Image::set_image / copy_image_to_input), motions as AoS doubles {x, y} per pixel.
+int of2d_host_image_op(int op, int dimx, int dimy, const double* in, double* out, double* scalars, int kernel_w, double sigma) {
+    return guarded([&] {
+        Image im(dim((unsigned int)dimx, (unsigned int)dimy));
+        im.set_image(in);
+        switch (op) {
+            case 0:   // Image::sum / max / min, src/Image.cpp:78-104
+                scalars[0] = (double)im.sum(); scalars[1] = (double)im.max(); scalars[2] = (double)im.min();
+                break;
+            case 1:   // Image::normalize, src/Image.cpp:107-116
+                im.normalize();
+                im.copy_image_to_input(out);
+                break;
+            case 2: {   // Image::convolute, src/Image.cpp:184-187, with Kernel::set_gaussian (sigma > 0) or Kernel::set_average
+                Kernel k((unsigned int)kernel_w);
+                if (sigma > 0) k.set_gaussian((of2d_real)sigma); else k.set_average();
+                im.convolute(k);
+                im.copy_image_to_input(out);
+                break;
+            }
+            default: throw std::invalid_argument("of2d_host_image_op: unknown operation");
+        }
+    });
+}
+int of2d_host_motion_boundary(int kind, int dimx, int dimy, const double* aos_in, double* aos_out) {
+    return guarded([&] {
+        Motion mo(dim((unsigned int)dimx, (unsigned int)dimy));
+        vector2d* u = mo.get_motion();
+        const size_t n = (size_t)dimx * (size_t)dimy;
+        for (size_t k = 0; k < n; k++) { u[k].x = (of2d_real)aos_in[2 * k]; u[k].y = (of2d_real)aos_in[2 * k + 1]; }
+        if (kind) mo.Dirichlet_boundaryconditions(); else mo.Neumann_boundaryconditions();   // src/Motion.cpp:181-251
+        u = mo.get_motion();
+        for (size_t k = 0; k < n; k++) { aos_out[2 * k] = (double)u[k].x; aos_out[2 * k + 1] = (double)u[k].y; }
+    });
+}
+int of2d_host_kernel(int kind, int w, double sigma, double* out) {
+    return guarded([&] {
+        Kernel k((unsigned int)w);
+        if (kind == 0) k.set_gaussian((of2d_real)sigma); else k.set_average();   // src/Kernel.cpp:45-82
+        memcpy(out, k.get_kernel(), sizeof(double) * k.get_size());
+    });
+}
+
 // ---- batch API (extension): independent pairs registered together ----------------------------------
+// A batch is one or more SHARDS: contiguous pair ranges, each on its own device behind its own context and driven by its
+// own host thread (one host thread, one CUDA context, compute + copy streams per GPU; no collective in the
+// solve).  The default is a single shard on the process context, run inline in the calling thread.
 struct of2d_batch {
-    std::unique_ptr<BatchRegistration> reg;
+    struct Shard {
+        of2d_ctx* ctx = nullptr;                 // nullptr: the process context (of2d::context())
+        std::unique_ptr<BatchRegistration> reg;
+        int lo = 0, hi = 0;                      // pair range [lo, hi)
+    };
+    std::vector<Shard> shards;
+    size_t npix = 0;
+    int batch = 0;
+
+    // fn(shard) on every shard, each in its own thread with its context current; the first exception is rethrown here
+    void each(const std::function<void(Shard&)>& fn) {
+        if (shards.size() == 1 && !shards[0].ctx) { fn(shards[0]); return; }
+        std::vector<std::thread> th;
+        std::vector<std::exception_ptr> err(shards.size());
+        for (size_t k = 0; k < shards.size(); k++)
+            th.emplace_back([&, k] {
+                try {
+                    of2d::set_thread_context(shards[k].ctx);
+                    fn(shards[k]);
+                } catch (...) { err[k] = std::current_exception(); }
+                try { of2d::set_thread_context(nullptr); } catch (...) {}
+            });
+        for (auto& t : th) t.join();
+        for (auto& e : err) if (e) std::rethrow_exception(e);
+    }
+    ~of2d_batch() {
+        try { each([](Shard& s) { s.reg.reset(); }); } catch (...) {}
+        for (auto& s : shards) if (s.ctx) of2d_ctx_destroy(s.ctx);
+    }
 };
 
-int of2d_batch_create(int dimx, int dimy, int batch, int niter, int nrefine, int reg, const double* regparams, int nparams, int wave, of2d_batch** out) {
+// contiguous shard [lo, hi) of `total` pairs for `rank` of `world` devices (needs no GPU): the whole multi-GPU protocol of the path
+int of2d_shard_range(int total, int world, int rank, int* lo, int* hi) {
+    if (total < 0 || world < 1 || rank < 0 || rank >= world) return 2;
+    const int base = total / world, rem = total % world;
+    const int l = rank * base + (rank < rem ? rank : rem);
+    if (lo) *lo = l;
+    if (hi) *hi = l + base + (rank < rem ? 1 : 0);
+    return 0;
+}
+
+static int batch_create(int dimx, int dimy, int batch, int frames, int niter, int nrefine, int reg, const double* regparams, int nparams, int wave,
+                        const int* devices, int ndevices, of2d_batch** out) {
     *out = nullptr;
     return guarded([&] {
         std::vector<of2d_real> p((size_t)(nparams > 0 ? nparams : 1));
         for (int k = 0; k < nparams; k++) p[(size_t)k] = (of2d_real)regparams[k];
         if (reg < 0 || reg > 5) mexErrMsgTxt("Error: invalid regularisation given\n");
+        if (batch <= 0 || dimx <= 0 || dimy <= 0) throw std::invalid_argument("of2d_batch_create: bad batch / dimensions");
+        if (ndevices < 0 || (ndevices > 0 && !devices)) throw std::invalid_argument("of2d_batch_create_multi: bad device list");
+        if (frames > 1 && batch % frames != 0) throw std::invalid_argument("of2d_batch_create_chain: the batch must be a multiple of the number of frames");
         std::unique_ptr<of2d_batch> b(new of2d_batch());
-        b->reg.reset(new BatchRegistration(dim((unsigned int)dimx, (unsigned int)dimy), batch, niter, nrefine, static_cast<Regularisation>(reg), p.data(),
-                                           (unsigned)nparams, wave));
+        b->npix = (size_t)dimx * (size_t)dimy;
+        b->batch = batch;
+        const int nsh = ndevices > 0 ? (ndevices < batch ? ndevices : batch) : 1;
+        b->shards.resize((size_t)nsh);
+        const int level = ndevices > 0 ? of2d_ctx_get_fast_math(of2d::context()) : 0;
+        for (int k = 0; k < nsh; k++) {   // contiguous ranges, the same partition as one process per GPU uses
+            of2d_shard_range(batch, nsh, k, &b->shards[(size_t)k].lo, &b->shards[(size_t)k].hi);
+            if (ndevices > 0) {
+                of2d::check(of2d_ctx_create(devices[k], &b->shards[(size_t)k].ctx));
+                of2d::check(of2d_ctx_set_fast_math(b->shards[(size_t)k].ctx, level));
+            }
+        }
+        if (ndevices > 0) of2d::check(of2d_ctx_make_current(of2d::context()));
+        b->each([&](of2d_batch::Shard& s) {
+            s.reg.reset(new BatchRegistration(dim((unsigned int)dimx, (unsigned int)dimy), s.hi - s.lo, niter, nrefine, static_cast<Regularisation>(reg), p.data(),
+                                              (unsigned)nparams, wave, frames));
+        });
         *out = b.release();
     });
 }
+
+int of2d_batch_create(int dimx, int dimy, int batch, int niter, int nrefine, int reg, const double* regparams, int nparams, int wave, of2d_batch** out) {
+    return batch_create(dimx, dimy, batch, 1, niter, nrefine, reg, regparams, nparams, wave, nullptr, 0, out);
+}
+int of2d_batch_create_chain(int dimx, int dimy, int batch, int frames, int niter, int nrefine, int reg, const double* regparams, int nparams, of2d_batch** out) {
+    return batch_create(dimx, dimy, batch, frames, niter, nrefine, reg, regparams, nparams, 0, nullptr, 0, out);
+}
+int of2d_batch_create_multi(int dimx, int dimy, int batch, int niter, int nrefine, int reg, const double* regparams, int nparams, int wave, const int* devices,
+                            int ndevices, of2d_batch** out) {
+    if (ndevices <= 0) { *out = nullptr; return guarded([] { throw std::invalid_argument("of2d_batch_create_multi: no devices given"); }); }
+    return batch_create(dimx, dimy, batch, 1, niter, nrefine, reg, regparams, nparams, wave, devices, ndevices, out);
+}
 void of2d_batch_destroy(of2d_batch* b) { delete b; }
 int of2d_batch_set_images(of2d_batch* b, const double* Iref, const double* Imov) {
-    return guarded([&] { b->reg->set_images(Iref, Imov); });
+    return guarded([&] { b->each([&](of2d_batch::Shard& s) { s.reg->set_images(Iref + b->npix * (size_t)s.lo, Imov + b->npix * (size_t)s.lo); }); });
 }
 int of2d_batch_estimate(of2d_batch* b) {
-    return guarded([&] { b->reg->estimate_motion(); });
+    return guarded([&] { b->each([&](of2d_batch::Shard& s) { s.reg->estimate_motion(); }); });
 }
 int of2d_batch_get_motion(of2d_batch* b, double* planar_out) {
-    return guarded([&] { b->reg->copy_estimated_motion(planar_out); });
+    return guarded([&] { b->each([&](of2d_batch::Shard& s) { s.reg->copy_estimated_motion(planar_out + 2 * b->npix * (size_t)s.lo); }); });
+}
+int of2d_batch_register(of2d_batch* b, const double* Iref, const double* Imov, double* planar_out) {
+    return guarded([&] {
+        b->each([&](of2d_batch::Shard& s) { s.reg->register_pairs(Iref + b->npix * (size_t)s.lo, Imov + b->npix * (size_t)s.lo, planar_out + 2 * b->npix * (size_t)s.lo); });
+    });
 }
 int of2d_batch_iterations(of2d_batch* b, int* iterations, int* regrids) {
     return guarded([&] {
-        for (int k = 0; k < b->reg->size(); k++) {
-            if (iterations) iterations[k] = b->reg->iterations()[(size_t)k];
-            if (regrids) regrids[k] = b->reg->regrids()[(size_t)k];
-        }
+        for (const auto& s : b->shards)
+            for (int k = 0; k < s.reg->size(); k++) {
+                if (iterations) iterations[s.lo + k] = s.reg->iterations()[(size_t)k];
+                if (regrids) regrids[s.lo + k] = s.reg->regrids()[(size_t)k];
+            }
     });
 }
-int of2d_batch_wave(of2d_batch* b) { return b->reg->wave_size(); }
+int of2d_batch_wave(of2d_batch* b) { return b->shards[0].reg->wave_size(); }
+int of2d_batch_num_shards(of2d_batch* b) { return (int)b->shards.size(); }
+int of2d_batch_shard_info(of2d_batch* b, int shard, int* device, int* lo, int* hi) {
+    return guarded([&] {
+        if (shard < 0 || shard >= (int)b->shards.size()) throw std::invalid_argument("of2d_batch_shard_info: shard out of range");
+        const auto& s = b->shards[(size_t)shard];
+        if (device) *device = of2d_ctx_device(s.ctx ? s.ctx : of2d::context());
+        if (lo) *lo = s.lo;
+        if (hi) *hi = s.hi;
+    });
+}
 
 // ---- trace access: `s` may be NULL to address the MEX singleton -------------------------------------
 static const RegistrationTrace* pick_trace(of2d_session* s) { return trace_of(s ? s->reg.get() : of2d_wrapper_registration()); }

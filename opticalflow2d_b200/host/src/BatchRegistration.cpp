@@ -20,16 +20,25 @@ bool valid_params(const Regularisation reg, const unsigned int n) {   // arities
 }  // namespace
 
 BatchRegistration::BatchRegistration(const dim dimin, const int batch_, const int niter_, const int nrefine_, const Regularisation reg, const of2d_real* p,
-                                     const unsigned int nparams, const int wave_)
-    : grid(dimin), batch(batch_), niter(niter_), nrefine(nrefine_), wave(wave_), npix((size_t)dimin.x * dimin.y), engine(nullptr), Iref(nullptr),
-      Imov(nullptr), motion(nullptr), staging(nullptr) {
+                                     const unsigned int nparams, const int wave_, const int frames_)
+    : grid(dimin), batch(batch_), niter(niter_), nrefine(nrefine_), wave(wave_), nwaves(1), frames(frames_ < 1 ? 1 : frames_), npix((size_t)dimin.x * dimin.y),
+      engine(nullptr), Iref(nullptr), Imov(nullptr), motion(nullptr), staging(nullptr), ctx_in(nullptr), ctx_out(nullptr) {
+    for (int k = 0; k < 2; k++) s_in[k] = s_ref[k] = s_mov[k] = s_mot[k] = s_out[k] = nullptr;
     if (batch <= 0 || niter < 0 || nrefine < 1) throw std::invalid_argument("BatchRegistration: bad batch / niter / nrefine");
     if (!valid_params(reg, nparams)) throw std::invalid_argument("Invalid number of regularisation parameters for given regularisation method.\n");
-    if (wave <= 0) {
-        const char* e = std::getenv("OF2D_BATCH_WAVE");
-        wave = e && std::atoi(e) > 0 ? std::atoi(e) : 256;
+    if (frames > 1) {   // cine chains: one wave per frame
+        if (batch % frames != 0) throw std::invalid_argument("BatchRegistration: the batch must be a multiple of the number of frames");
+        wave = batch / frames;
+        nwaves = frames;
+    } else {
+        if (wave <= 0) {
+            const char* e = std::getenv("OF2D_BATCH_WAVE");
+            wave = e && std::atoi(e) > 0 ? std::atoi(e) : 256;
+        }
+        if (wave > batch) wave = batch;
+        nwaves = (batch + wave - 1) / wave;
+        wave = (batch + nwaves - 1) / nwaves;   // balanced: the last wave is short by less than nwaves pairs (padded with copies)
     }
-    if (wave > batch) wave = batch;
 
     of2d_engine_desc d;
     std::memset(&d, 0, sizeof(d));
@@ -60,11 +69,6 @@ BatchRegistration::BatchRegistration(const dim dimin, const int batch_, const in
         }
     }
     of2d::check(of2d_engine_create(of2d::context(), &d, &engine));
-    const size_t rb = sizeof(of2d_real);
-    Iref = new of2d::Buffer(rb * npix * (size_t)batch);
-    Imov = new of2d::Buffer(rb * npix * (size_t)batch);
-    motion = new of2d::Buffer(2 * rb * npix * (size_t)batch);
-    staging = new of2d::Buffer(sizeof(double) * 2 * npix * (size_t)wave);
     iters.assign((size_t)batch, 0);
     nregrid.assign((size_t)batch, 0);
 }
@@ -75,57 +79,145 @@ BatchRegistration::~BatchRegistration() {
     delete Imov;
     delete motion;
     delete staging;
+    for (int k = 0; k < 2; k++) { delete s_in[k]; delete s_ref[k]; delete s_mov[k]; delete s_mot[k]; delete s_out[k]; }
+    if (ctx_in) of2d_ctx_destroy(ctx_in);
+    if (ctx_out) of2d_ctx_destroy(ctx_out);
+}
+
+// a partial last wave is filled up with copies of its first pair (valid images: no spurious divide-by-zero); their results are dropped
+void BatchRegistration::pad_wave(of2d_ctx* ctx, of2d_real* img, int m) const {
+    for (int k = m; k < wave; k++) of2d::check(of2d_d2d(ctx, img + npix * (size_t)k, img, sizeof(of2d_real) * npix));
 }
 
 // Image::set_image for every pair: doubles cross the bus, the cast to `real` happens on the device
 void BatchRegistration::set_images(const double* ref, const double* mov) {
     of2d_ctx* ctx = of2d::context();
+    const size_t rb = sizeof(of2d_real), cap = npix * (size_t)wave * (size_t)nwaves;
+    if (!Iref) {
+        Iref = new of2d::Buffer(rb * cap);
+        Imov = new of2d::Buffer(rb * cap);
+        motion = new of2d::Buffer(2 * rb * cap);
+        staging = new of2d::Buffer(sizeof(double) * 2 * npix * (size_t)wave);
+    }
     double* st = (double*)staging->device_discard();
     of2d_real* dr = (of2d_real*)Iref->device_discard();
     of2d_real* dm = (of2d_real*)Imov->device_discard();
-    for (int p0 = 0; p0 < batch; p0 += wave) {
-        const int m = batch - p0 < wave ? batch - p0 : wave;
+    for (int w = 0; w < nwaves; w++) {
+        const int p0 = w * wave, m = batch - p0 < wave ? batch - p0 : wave;
         const size_t cnt = npix * (size_t)m, off = npix * (size_t)p0;
         of2d::check(of2d_h2d(ctx, st, ref + off, sizeof(double) * cnt));
         of2d::check(of2d::image_from_double(cnt, st, dr + off));
         of2d::check(of2d_h2d(ctx, st + cnt, mov + off, sizeof(double) * cnt));
         of2d::check(of2d::image_from_double(cnt, st + cnt, dm + off));
+        if (m < wave) { pad_wave(ctx, dr + off, m); pad_wave(ctx, dm + off, m); }
     }
+    of2d::check(of2d_ctx_sync(ctx));   // the copies read the caller's buffers: complete before returning (as Image::set_image)
 }
 
-void BatchRegistration::estimate_motion() {
-    motion->zero();
-    of2d_real* mo = (of2d_real*)motion->device_rw();
-    const of2d_real* dr = (const of2d_real*)Iref->device_ro();
-    const of2d_real* dm = (const of2d_real*)Imov->device_ro();
-    for (int p0 = 0; p0 < batch; p0 += wave) {
-        const int m = batch - p0 < wave ? batch - p0 : wave;
-        if (m != wave) throw std::invalid_argument("BatchRegistration: the batch must be a multiple of the wave size");
-        of2d::check(of2d_engine_reset_state(engine));   // fresh solver state per pair
-        const size_t off = npix * (size_t)p0;
-        for (int refine = 0; refine < nrefine; refine++) {
-            const int st = sizeof(of2d_real) == 8 ? of2d_engine_refine_f64(engine, (const double*)(dr + off), (const double*)(dm + off), (double*)(mo + 2 * off), niter)
-                                                  : of2d_engine_refine_f32(engine, (const float*)(dr + off), (const float*)(dm + off), (float*)(mo + 2 * off), niter);
-            of2d::check(st);
-            for (int k = 0; k < m; k++) {
-                int it = 0, rg = 0;
-                of2d::check(of2d_engine_pair_result(engine, k, &it, &rg, nullptr));
-                if (refine == 0) { iters[(size_t)(p0 + k)] = 0; nregrid[(size_t)(p0 + k)] = 0; }
-                iters[(size_t)(p0 + k)] += it;
-                nregrid[(size_t)(p0 + k)] += rg;
-            }
+// one wave on the engine: cold start per pair (or the previous frame's state in a cine chain), nrefine passes
+void BatchRegistration::solve_wave(int w, const of2d_real* dr, const of2d_real* dm, of2d_real* mo, int m) {
+    if (frames == 1 || w == 0) of2d::check(of2d_engine_reset_state(engine));   // fresh solver state per pair; chains keep it
+    const int p0 = w * wave;
+    for (int refine = 0; refine < nrefine; refine++) {
+        const int st = sizeof(of2d_real) == 8 ? of2d_engine_refine_f64(engine, (const double*)dr, (const double*)dm, (double*)mo, niter)
+                                              : of2d_engine_refine_f32(engine, (const float*)dr, (const float*)dm, (float*)mo, niter);
+        of2d::check(st);
+        for (int k = 0; k < m; k++) {
+            int it = 0, rg = 0;
+            of2d::check(of2d_engine_pair_result(engine, k, &it, &rg, nullptr));
+            if (refine == 0) { iters[(size_t)(p0 + k)] = 0; nregrid[(size_t)(p0 + k)] = 0; }
+            iters[(size_t)(p0 + k)] += it;
+            nregrid[(size_t)(p0 + k)] += rg;
         }
     }
 }
 
+void BatchRegistration::estimate_motion() {
+    if (!Iref) throw std::invalid_argument("BatchRegistration: set_images() first");
+    of2d_ctx* ctx = of2d::context();
+    motion->zero();
+    of2d_real* mo = (of2d_real*)motion->device_rw();
+    const of2d_real* dr = (const of2d_real*)Iref->device_ro();
+    const of2d_real* dm = (const of2d_real*)Imov->device_ro();
+    for (int w = 0; w < nwaves; w++) {
+        const int p0 = w * wave, m = batch - p0 < wave ? batch - p0 : wave;
+        const size_t off = npix * (size_t)p0;
+        if (frames > 1 && w > 0)   // cine chain: frame w starts from the motion frame w - 1 ended with
+            of2d::check(of2d_d2d(ctx, mo + 2 * off, mo + 2 * (off - npix * (size_t)wave), 2 * sizeof(of2d_real) * npix * (size_t)wave));
+        solve_wave(w, dr + off, dm + off, mo + 2 * off, m);
+    }
+}
+
 void BatchRegistration::copy_estimated_motion(double* out) const {
+    if (!motion) throw std::invalid_argument("BatchRegistration: nothing estimated yet");
     of2d_ctx* ctx = of2d::context();
     const of2d_real* mo = (const of2d_real*)motion->device_ro();
     double* st = (double*)staging->device_discard();
-    for (int p0 = 0; p0 < batch; p0 += wave) {
-        const int m = batch - p0 < wave ? batch - p0 : wave;
+    for (int w = 0; w < nwaves; w++) {
+        const int p0 = w * wave, m = batch - p0 < wave ? batch - p0 : wave;
         for (int k = 0; k < m; k++)
             of2d::check(of2d::motion_to_planar(npix, mo + 2 * npix * (size_t)(p0 + k), st + 2 * npix * (size_t)k));
         of2d::check(of2d_d2h(ctx, out + 2 * npix * (size_t)p0, st, sizeof(double) * 2 * npix * (size_t)m));
     }
+}
+
+// Streamed protocol.  Three streams: `in` (host -> device copies and the double -> real casts of the NEXT wave), the
+// context's compute stream (the engine), `out` (real -> planar double and the device -> host copy of the PREVIOUS wave).
+// of2d_engine_refine returns when its wave is complete, so the host enqueues the neighbours' copies just before it calls the
+// solve of wave k; the streams are ordered by of2d_ctx_wait_for at the buffer hand-overs.
+void BatchRegistration::register_pairs(const double* ref, const double* mov, double* out) {
+    of2d_ctx* ctx = of2d::context();
+    const size_t rb = sizeof(of2d_real), wn = npix * (size_t)wave;
+    if (!ctx_in) {
+        of2d::check(of2d_ctx_create(of2d_ctx_device(ctx), &ctx_in));
+        of2d::check(of2d_ctx_create(of2d_ctx_device(ctx), &ctx_out));
+        of2d::check(of2d_ctx_make_current(ctx));
+        for (int k = 0; k < 2; k++) {
+            s_in[k] = new of2d::Buffer(sizeof(double) * 2 * wn);
+            s_ref[k] = new of2d::Buffer(rb * wn);
+            s_mov[k] = new of2d::Buffer(rb * wn);
+            s_mot[k] = new of2d::Buffer(2 * rb * wn);
+            s_out[k] = new of2d::Buffer(sizeof(double) * 2 * wn);
+        }
+        of2d::check(of2d_ctx_sync(ctx));   // allocations and clears are ordered on the compute stream: visible to the copy streams from here on
+    }
+    auto count = [&](int w) { const int p0 = w * wave; return batch - p0 < wave ? batch - p0 : wave; };
+    auto issue_in = [&](int w) {   // `in` stream: images of wave w -> buffer set w & 1
+        const int b = w & 1, m = count(w);
+        const size_t cnt = npix * (size_t)m, off = npix * (size_t)(w * wave);
+        double* st = (double*)s_in[b]->device_discard();
+        of2d_real* dr = (of2d_real*)s_ref[b]->device_discard();
+        of2d_real* dm = (of2d_real*)s_mov[b]->device_discard();
+        of2d::check(of2d_h2d(ctx_in, st, ref + off, sizeof(double) * cnt));
+        of2d::check(of2d_h2d(ctx_in, st + wn, mov + off, sizeof(double) * cnt));
+        of2d::check(sizeof(of2d_real) == 8 ? of2d_image_from_double_f64(ctx_in, cnt, st, (double*)dr) : of2d_image_from_double_f32(ctx_in, cnt, st, (float*)dr));
+        of2d::check(sizeof(of2d_real) == 8 ? of2d_image_from_double_f64(ctx_in, cnt, st + wn, (double*)dm) : of2d_image_from_double_f32(ctx_in, cnt, st + wn, (float*)dm));
+        if (m < wave) { pad_wave(ctx_in, dr, m); pad_wave(ctx_in, dm, m); }
+    };
+    auto issue_out = [&](int w) {   // `out` stream: motion of wave w (solved: the engine call has returned) -> caller
+        const int b = w & 1, m = count(w);
+        const of2d_real* mo = (const of2d_real*)s_mot[b]->device_ro();
+        double* st = (double*)s_out[b]->device_discard();
+        for (int k = 0; k < m; k++)
+            of2d::check(sizeof(of2d_real) == 8 ? of2d_motion_to_planar_double_f64(ctx_out, npix, (const double*)(mo + 2 * npix * (size_t)k), st + 2 * npix * (size_t)k)
+                                               : of2d_motion_to_planar_double_f32(ctx_out, npix, (const float*)(mo + 2 * npix * (size_t)k), st + 2 * npix * (size_t)k));
+        of2d::check(of2d_d2h_async(ctx_out, out + 2 * npix * (size_t)(w * wave), st, sizeof(double) * 2 * npix * (size_t)m));
+    };
+    issue_in(0);
+    for (int w = 0; w < nwaves; w++) {
+        const int b = w & 1;
+        // the compute stream takes over buffer set b: after the copies of wave w (in) and after wave w - 2 has left it (out)
+        of2d::check(of2d_ctx_wait_for(ctx, ctx_in));
+        of2d::check(of2d_ctx_wait_for(ctx, ctx_out));
+        of2d_real* mo = (of2d_real*)s_mot[b]->device_discard();
+        if (frames > 1 && w > 0) of2d::check(of2d_d2d(ctx, mo, s_mot[b ^ 1]->device_ro(), 2 * rb * wn));   // cine chain
+        else of2d::check(of2d_memset(ctx, mo, 0, 2 * rb * wn));
+        // neighbours' copies go under this wave's solve: set b ^ 1 is free (wave w - 1 is solved, wave w + 1 not started)
+        if (w + 1 < nwaves) issue_in(w + 1);
+        if (w >= 1) issue_out(w - 1);
+        solve_wave(w, (const of2d_real*)s_ref[b]->device_ro(), (const of2d_real*)s_mov[b]->device_ro(), mo, count(w));
+    }
+    issue_out(nwaves - 1);
+    of2d::check(of2d_ctx_sync(ctx_out));
+    of2d::check(of2d_ctx_sync(ctx_in));
 }

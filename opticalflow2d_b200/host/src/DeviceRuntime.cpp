@@ -9,6 +9,7 @@ namespace of2d {
 namespace {
 of2d_ctx* g_ctx = nullptr;
 std::mutex g_mutex;
+thread_local of2d_ctx* tl_ctx = nullptr;   // per-thread override (multi-GPU batches: one host thread and one context per device)
 
 int pick_device() {
     const char* names[] = {"OF2D_DEVICE", "LOCAL_RANK"};
@@ -20,7 +21,13 @@ int pick_device() {
 }
 }  // namespace
 
+void set_thread_context(of2d_ctx* ctx) {
+    tl_ctx = ctx;
+    if (ctx) check(of2d_ctx_make_current(ctx));
+}
+
 of2d_ctx* context() {
+    if (tl_ctx) return tl_ctx;
     if (g_ctx) return g_ctx;
     std::lock_guard<std::mutex> lock(g_mutex);
     if (!g_ctx) {
@@ -94,6 +101,7 @@ void* Buffer::device_discard() {
 
 void* Buffer::host() const {
     if (!hptr_) check(of2d_host_alloc(bytes_, &hptr_));
+    else if (host_valid_ && device_valid_) check(of2d_ctx_sync(context()));   // an upload from this mirror may still be in flight: the caller may write
     if (!host_valid_) {
         check(of2d_d2h(context(), hptr_, dptr_, bytes_));
         host_valid_ = true;

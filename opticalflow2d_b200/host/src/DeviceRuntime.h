@@ -20,6 +20,9 @@ namespace of2d {
 
 of2d_ctx* context();            // created on first use on device $OF2D_DEVICE (else $LOCAL_RANK, else 0)
 void release_context();         // tears the context down (tests)
+// per-thread override of context(): the calling host thread works on `ctx` (and its device) until reset with nullptr;
+// used by multi-GPU batches (one host thread + one context per device)
+void set_thread_context(of2d_ctx* ctx);
 void check(int status);         // throws per the table above
 void poll_divzero();            // throws if a kernel raised the divide-by-zero flag since the last poll
 

@@ -750,6 +750,89 @@ int of2d_oracle_convolute_motion(int dimx, int dimy, real *u, int w, real sigma)
     free(k);
     return g_status;
 }
+/* ---- the rest of the public Image / Motion / Kernel surface ---- */
+/* src/Image.cpp:78-104: sequential accumulation in `real`; max starts from 0, min from the first element */
+int of2d_oracle_image_stats(int dimx, int dimy, const real *img, real *sum, real *mx, real *mn) {
+    BEGIN();
+    const size_t n = (size_t)dimx * dimy;
+    real s = 0.0f, hi = 0.0f;
+    for (size_t k = 0; k < n; k++) s += img[k];
+    for (size_t k = 0; k < n; k++) if (img[k] > hi) hi = img[k];
+    *sum = s; *mx = hi; *mn = image_min(img, n);
+    return g_status;
+}
+/* src/Image.cpp:107-116 */
+int of2d_oracle_image_normalize(int dimx, int dimy, real *img) {
+    BEGIN();
+    const size_t n = (size_t)dimx * dimy;
+    real hi = 0.0f;
+    for (size_t k = 0; k < n; k++) if (img[k] > hi) hi = img[k];
+    const real lo = image_min(img, n);
+    for (size_t k = 0; k < n; k++) img[k] = (img[k] - lo) / (hi - lo);
+    return g_status;
+}
+/* src/Motion.cpp:181-251; step = (1, dimx).  kind 0: Neumann, 1: Dirichlet.  The assignments are sequential; the
+   (dimx-1, 0) corner of the Neumann variant reads u[(dimy-2) + dimx] (src/Motion.cpp:213 uses the y extent for an x index). */
+int of2d_oracle_boundary_conditions(int dimx, int dimy, int kind, real *uu) {
+    BEGIN();
+    vec2 *u = (vec2 *)uu;
+    const unsigned nx = (unsigned)dimx, ny = (unsigned)dimy;
+    const vec2 zero = v2(0, 0);
+    for (unsigned i = 1; i + 1 < nx; i++) {
+        unsigned idx = i;
+        u[idx] = kind ? zero : u[idx + nx];
+        idx += (ny - 1) * nx;
+        u[idx] = kind ? zero : u[idx - nx];
+    }
+    for (unsigned j = 1; j + 1 < ny; j++) {
+        unsigned idx = j * nx;
+        u[idx] = kind ? zero : u[idx + 1];
+        idx += nx - 1;
+        u[idx] = kind ? zero : u[idx - 1];
+    }
+    u[0] = kind ? zero : u[1 + nx];
+    u[(ny - 1) * nx] = kind ? zero : u[1 + (ny - 2) * nx];
+    u[nx - 1] = kind ? zero : u[(ny - 2) + nx];
+    u[(nx - 1) + (ny - 1) * nx] = kind ? zero : u[(nx - 2) + (ny - 2) * nx];
+    return g_status;
+}
+/* src/Kernel.cpp:75-82: 1.0f / (float)size, stored as double */
+int of2d_oracle_average_kernel(int w, double *out) {
+    BEGIN();
+    const unsigned n = (unsigned)w * (unsigned)w;
+    for (unsigned t = 0; t < n; t++) out[t] = 1.0f / (real)n;
+    return g_status;
+}
+/* src/Field.tpp:210-269 instantiated on float (Image::convolute, src/Image.cpp:184-187).  The reference leaves the accumulator
+   `val` uninitialised there (src/Field.tpp:240, undefined behaviour): this restatement takes the evident intent, val = 0. */
+int of2d_oracle_convolute_image(int dimx, int dimy, real *img, int w, real sigma) {
+    BEGIN();
+    const size_t n = (size_t)dimx * dimy;
+    double *k = (double *)calloc((size_t)w * w + 1, sizeof(double));
+    if (sigma > 0) gaussian_kernel(k, (unsigned)w, sigma); else of2d_oracle_average_kernel(w, k);
+    const int cx = (w - 1) / 2, cy = cx;
+    real *tmp = (real *)malloc(n * sizeof(real));
+    memcpy(tmp, img, n * sizeof(real));
+    for (int i = 0; i < dimx; i++) {
+        for (int j = 0; j < dimy; j++) {
+            const int idx = i + j * dimx;
+            real val = 0;
+            double weight = 0.0f;
+            for (int ii = -cx; ii <= cx; ii++) {
+                for (int jj = -cy; jj <= cy; jj++) {
+                    const long lin = (long)(i + ii) + (long)(j + jj) * (long)dimx;
+                    if (lin < 0 || lin >= (long)n) continue;
+                    const int ik = (ii + cx) + (jj + cy) * w;
+                    val += tmp[lin] * k[ik];     /* float * double: promoted, as in the reference's `fieldtmp[...] * k[...]` */
+                    weight += k[ik];
+                }
+            }
+            if (weight != 0) img[idx] = val / weight;
+        }
+    }
+    free(tmp); free(k);
+    return g_status;
+}
 int of2d_oracle_exp(int dimx, int dimy, real *u) {
     BEGIN(); motion_exp((vec2 *)u, (unsigned)dimx, (unsigned)dimy); return g_status;
 }

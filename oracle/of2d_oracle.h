@@ -52,6 +52,11 @@ int of2d_oracle_warp2d(int dimx, int dimy, real *img, const real *u);
 int of2d_oracle_accumulate(int dimx, int dimy, real *u, const real *v);
 int of2d_oracle_gaussian_kernel(int w, real sigma, double *out);
 int of2d_oracle_convolute_motion(int dimx, int dimy, real *u, int w, real sigma);
+int of2d_oracle_image_stats(int dimx, int dimy, const real *img, real *sum, real *mx, real *mn);
+int of2d_oracle_image_normalize(int dimx, int dimy, real *img);
+int of2d_oracle_boundary_conditions(int dimx, int dimy, int kind, real *u);
+int of2d_oracle_average_kernel(int w, double *out);
+int of2d_oracle_convolute_image(int dimx, int dimy, real *img, int w, real sigma);
 int of2d_oracle_exp(int dimx, int dimy, real *u);
 int of2d_oracle_norm_maxabs(int dimx, int dimy, const real *u, real *norm, real *maxabs);
 int of2d_oracle_jacobian(int dimx, int dimy, const real *u, real *jac, real *minjac);

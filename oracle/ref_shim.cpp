@@ -251,6 +251,36 @@ int of2d_ref_motion_resample(int inx, int iny, const real *in, int outx, int out
         read_motion(b, out);
     });
 }
+/* ---- the rest of the public Image / Motion / Kernel surface ---- */
+int of2d_ref_image_stats(int dimx, int dimy, const real *img, real *sum, real *mx, real *mn) {
+    return guarded([&] { Image a(dim(dimx, dimy)); fill_image(a, img); *sum = a.sum(); *mx = a.max(); *mn = a.min(); });
+}
+int of2d_ref_image_normalize(int dimx, int dimy, real *img) {
+    return guarded([&] { Image a(dim(dimx, dimy)); fill_image(a, img); a.normalize(); read_image(a, img); });
+}
+int of2d_ref_boundary_conditions(int dimx, int dimy, int kind, real *u) {
+    return guarded([&] {
+        Motion a(dim(dimx, dimy));
+        fill_motion(a, u);
+        if (kind) a.Dirichlet_boundaryconditions(); else a.Neumann_boundaryconditions();
+        read_motion(a, u);
+    });
+}
+int of2d_ref_average_kernel(int w, double *out) {
+    return guarded([&] { Kernel k((unsigned int)w); k.set_average(); memcpy(out, k.get_kernel(), sizeof(double) * k.get_size()); });
+}
+/* Image::convolute with a Gaussian (sigma > 0) or the average kernel (sigma <= 0).  Field<float>::convolute leaves its
+   accumulator `val` uninitialised (src/Field.tpp:240): what this returns is whatever the compiled code does with it. */
+int of2d_ref_convolute_image(int dimx, int dimy, real *img, int w, real sigma) {
+    return guarded([&] {
+        Image a(dim(dimx, dimy));
+        fill_image(a, img);
+        Kernel k((unsigned int)w);
+        if (sigma > 0) k.set_gaussian(sigma); else k.set_average();
+        a.convolute(k);
+        read_image(a, img);
+    });
+}
 /* Logger::update_error over a sequence of nseq fields (each 2*N reals); err has nseq entries */
 int of2d_ref_logger(int dimx, int dimy, const real *useq, int nseq, real *err) {
     return guarded([&] {

@@ -155,6 +155,38 @@ class RefLib:
         self._check(self._f("convolute_motion")(dimx, dimy, self._p(u), C.c_int(w), self.creal(sigma)))
         return u
 
+    # -- the rest of the public Image / Motion / Kernel surface --
+    def image_stats(self, img):
+        img = self._r(img)
+        dimy, dimx = img.shape
+        s, hi, lo = self.creal(0), self.creal(0), self.creal(0)
+        self._check(self._f("image_stats")(dimx, dimy, self._p(img), C.byref(s), C.byref(hi), C.byref(lo)))
+        return s.value, hi.value, lo.value
+
+    def image_normalize(self, img):
+        img = self._r(img).copy()
+        dimy, dimx = img.shape
+        self._check(self._f("image_normalize")(dimx, dimy, self._p(img)))
+        return img
+
+    def boundary_conditions(self, u, kind: int):
+        u = self._r(u).copy()
+        dimy, dimx, _ = u.shape
+        self._check(self._f("boundary_conditions")(dimx, dimy, C.c_int(kind), self._p(u)))
+        return u
+
+    def average_kernel(self, w: int):
+        out = np.zeros((w, w), dtype=np.float64)
+        self._check(self._f("average_kernel")(C.c_int(w), self._p(out)))
+        return out
+
+    def convolute_image(self, img, w: int, sigma: float):
+        """sigma > 0: Gaussian kernel; sigma <= 0: Kernel::set_average"""
+        img = self._r(img).copy()
+        dimy, dimx = img.shape
+        self._check(self._f("convolute_image")(dimx, dimy, self._p(img), C.c_int(w), self.creal(sigma)))
+        return img
+
     def exp(self, u):
         u = self._r(u).copy()
         dimy, dimx, _ = u.shape

@@ -45,12 +45,17 @@ CASES = [
     (of.THIRION, [1.0, 0.25, 1.5, 1.5, 5, 1], [12]),          # addition instead of composition
     (of.THIRION, [1.0, 0.5, 2.0, 1.0, 7, 0], [10]),           # 7 x 7 kernels
     (of.THIRION, [1.0, 0.5, 2.0, 1.0, 4, 0], [8]),            # even width: generic convolution path
+    (of.THIRION, [1.0, 0.5, 1.0, 0.8, 3, 0], [10]),           # 3 x 3 kernels
+    (of.THIRION, [0.5, 6.0, 1.5, 1.5, 5, 0], [6]),            # correspondences of several pixels: taps outside the staged window
+    (of.DIFFEOMORPHIC, [1.0, 6.0, 1.5, 1.5, 5], [6]),         # the same after scaling and squaring
     (of.DIFFEOMORPHIC, [1.0, 2.0, 1.5, 1.5, 5], [15]),        # sigma_x = 2: squarings are active
     (of.FLUID, [0.1, 0.0], [30]),
     (of.FLUID, [0.2, 0.1, 0.8], [20]),
 ]
-# achieved on these cases (px): contractions stay at the rounding level; Fluid amplifies ~10x per 10 iterations
+# achieved on these cases (px): contractions stay at the rounding level; Fluid amplifies ~10x per 10 iterations, and so do
+# Demons steps of several pixels (sigma_x = 6)
 ACHIEVED = {32: {of.FLUID: 5e-4}, 64: {}}
+BIG_STEPS = 5e-4
 
 
 @pytest.mark.parametrize("bits", [32, 64])
@@ -65,7 +70,8 @@ def test_relaxed_engine_within_north_star_of_strict(bits, reg, params, niter, di
     assert np.allclose(series(tr, "err"), series(ts, "err"), rtol=1e-3, atol=1e-10)
     du = maxdiff(mr, ms)
     assert du <= (1e-3 if bits == 32 else 1e-6), du
-    assert du <= ACHIEVED[bits].get(reg, 5e-5 if bits == 32 else 1e-9), du
+    big = reg in (of.THIRION, of.DIFFEOMORPHIC) and params[1] >= 4.0
+    assert du <= (BIG_STEPS if big and bits == 32 else ACHIEVED[bits].get(reg, 5e-5 if bits == 32 else 1e-9)), du
     ssd_r, ssd_s = float(((wr - R) ** 2).sum()), float(((ws - R) ** 2).sum())
     assert abs(ssd_r - ssd_s) <= 1e-4 * ssd_s
 
@@ -85,7 +91,7 @@ def test_relaxed_multiscale_and_refine_matches_oracle(reg, params, niter):
         # north-star tolerance the engine is held to the reference's OWN fp32 <-> fp64 spread on the same case
         want64 = oracle(64).register(R, T, reg, params, niter, nscales=2, nrefine=2, verbose=1)
         if len(want64["err"]) == len(want["err"]):
-            tol = max(tol, 4.0 * maxdiff(want["motion"], want64["motion"]))
+            tol = max(tol, 8.0 * maxdiff(want["motion"], want64["motion"]))
     assert maxdiff(mr, want["motion"]) <= tol
 
 

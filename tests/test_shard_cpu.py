@@ -23,6 +23,21 @@ def test_shards_partition_the_batch():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_native_shard_ranges_match_the_python_partition():
+    """of2d_shard_range (include/of2d_host.h) is the partition of2d_batch_create_multi uses inside one process: it must be
+    the one the one-process-per-GPU launch uses (shard_pairs).  Pure host arithmetic: no device needed."""
+    import ctypes as C
+    import opticalflow2d_b200 as of
+    lib = of.host(32)
+    for total in (0, 1, 7, 512, 4096, 4097):
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                lo, hi = C.c_int(), C.c_int()
+                assert lib.of2d_shard_range(total, world, r, C.byref(lo), C.byref(hi)) == 0
+                assert (lo.value, hi.value) == shard_pairs(total, world, r)
+    assert lib.of2d_shard_range(8, 2, 2, None, None) != 0
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
