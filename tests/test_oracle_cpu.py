@@ -144,3 +144,31 @@ def test_three_iterations_always_run():
     R, _ = S.make_pair(24, 24, "blob")
     out = orc.register(R, R, 0, [0.5], [50])       # identical images: zero motion, still three iterations
     assert len(out["err"]) == 3 and np.all(out["motion"] == 0)
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_oracle_surface_functions_match_compiled_reference(bits):
+    """SURVEY 8 f4: Image::sum/max/min/normalize, Motion::Neumann_/Dirichlet_boundaryconditions, Kernel::set_average --
+    the restatement against the compiled reference, bit for bit.  Image::convolute is NOT comparable: the reference leaves its
+    float accumulator uninitialised (src/Field.tpp:240) and the compiled code carries it from pixel to pixel; the restatement
+    (and the CUDA path) start from zero, which this test documents by checking the restatement against the definition."""
+    if not refapi.available("ref", bits):
+        pytest.skip("oracle/_ref not built")
+    ref, orc = refapi.get("ref", bits), refapi.get("oracle", bits)
+    rng = np.random.default_rng(11)
+    for dimx, dimy in ((52, 37), (37, 52), (5, 9)):
+        img = rng.uniform(-0.3, 1.2, (dimy, dimx))
+        u = rng.normal(size=(dimy, dimx, 2))
+        assert ref.image_stats(img) == orc.image_stats(img)
+        assert np.array_equal(ref.image_normalize(img), orc.image_normalize(img))
+        for kind in (0, 1):
+            assert np.array_equal(ref.boundary_conditions(u, kind), orc.boundary_conditions(u, kind))
+    for w in (3, 4, 5, 7):
+        assert np.array_equal(ref.average_kernel(w), orc.average_kernel(w))
+    # Image::convolute, zero-initialised: interior pixels of a constant image stay constant, a delta spreads the kernel
+    img = np.full((20, 24), 0.75)
+    out = orc.convolute_image(img, 5, 1.5)
+    assert np.allclose(out[3:-3, 3:-3], 0.75, rtol=1e-6)
+    delta = np.zeros((21, 21)); delta[10, 10] = 1.0
+    k = orc.gaussian_kernel(5, 1.5)
+    assert np.allclose(orc.convolute_image(delta, 5, 1.5)[8:13, 8:13], k[::-1, ::-1], rtol=1e-6, atol=1e-9)
