@@ -19,10 +19,17 @@
 //   P1 rows    : rhs = u - tau f (f = L-SSD force, fused)  -> DCT-II along x  -> spectrum
 //   P2 columns : DCT-II along y -> x 1/(1 + tau alpha lap^2) -> DCT-III along y (spectrum stays in smem)
 //   P3 rows    : DCT-III along x -> u' = rhs / (4 N)
-// Non-power-of-two lengths take a direct O(n^2) path (correct, not fast).
+// Non-power-of-two lengths (fftw takes any n; the reference's demo pads to 278 = 2 x 139) use Bluestein's algorithm: the
+// n-point DFT inside Makhoul's DCT is a chirp-modulated circular convolution of length M = 2^k >= 2n - 1, evaluated with the
+// same radix-2 kernels (DIF forward -> pointwise product with the transformed chirp, stored bit-reversed -> DIT inverse), so
+// a line costs two M-point FFTs: O(n log n) for every n.  Lines too long for shared memory (n > 4096) fall back to the direct
+// O(n^2) sum.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+
+#include <complex>
+#include <vector>
 
 #include "device_math.cuh"
 #include "engine_internal.cuh"
@@ -56,7 +63,12 @@ struct LineTables {
     const double *costab;  // cos(pi m / (2n)), m < 4n (direct path only)
     const void *tw16a;     // [4][n/16]:  e^{-2 pi i k 2^i / n}       (register path, dct_reg.cuh; 512 <= n <= 4096)
     const void *tw16b;     // [4][n/256]: e^{-2 pi i k 2^i / (n/16)}
+    // Bluestein (non-power-of-two n): M = 2^log2M >= 2n - 1
+    const void *twM;       // e^{-2 pi i k / M}, k < M/2
+    const void *chirp;     // w_j = e^{-i pi j^2 / n}, j < n
+    const void *bhat;      // FFT_M(b) / M in BIT-REVERSED order, b_j = conj(w_|j|) wrapped to length M
     int n, log2n, pow2;
+    int M, log2M, bluestein;
 };
 
 // in-place radix-2 DIT, input in bit-reversed order, output natural. sign<0: forward.
@@ -100,6 +112,16 @@ __device__ __forceinline__ int bitrev(int i, int log2n) { return (int)(__brev((u
 // Makhoul reordering: natural position m -> FFT input position
 __device__ __forceinline__ int makhoul_pos(int m, int n) { return (m & 1) ? n - 1 - (m >> 1) : (m >> 1); }
 
+// n-point DFT by Bluestein: on entry y[j] = v_j w_j (j < n), 0 for n <= j < M; on return DFT_n(v)_k = w_k y[k], k < n
+template <class S>
+__device__ void bluestein_core(cplx_t<S> *y, const LineTables &T) {
+    fft_dif<S>(y, T.M, T.log2M, (const cplx_t<S> *)T.twM, -1);          // natural -> bit-reversed
+    const cplx_t<S> *bh = (const cplx_t<S> *)T.bhat;
+    for (int k = threadIdx.x; k < T.M; k += blockDim.x) y[k] = cmul<S>(y[k], bh[k]);
+    __syncthreads();
+    fft_dit<S>(y, T.M, T.log2M, (const cplx_t<S> *)T.twM, +1);          // bit-reversed -> natural (1 / M is folded into bhat)
+}
+
 // smem slot where sample m of a line must be placed before dct2_line()
 template <class S>
 __device__ __forceinline__ int dct2_load_slot(int m, const LineTables &T) {
@@ -137,6 +159,35 @@ __device__ void dct2_line(cplx_t<S> *x, cplx_t<S> *tmp, const LineTables &T) {
                 cplx_t<S> o; o.x = (S)2 * (var * w.x - vai * w.y); o.y = (S)2 * (vbr * w.x - vbi * w.y);
                 x[nk] = o;
             }
+        }
+        __syncthreads();
+    } else if (T.bluestein) {
+        // x[m]: samples in natural order; tmp[M]: Makhoul-permuted, chirp-modulated, zero-padded
+        const cplx_t<S> *w = (const cplx_t<S> *)T.chirp, *q = (const cplx_t<S> *)T.q;
+        for (int j = n + threadIdx.x; j < T.M; j += blockDim.x) { cplx_t<S> z; z.x = (S)0; z.y = (S)0; tmp[j] = z; }
+        for (int m = threadIdx.x; m < n; m += blockDim.x) { const int pos = makhoul_pos(m, n); tmp[pos] = cmul<S>(x[m], w[pos]); }
+        __syncthreads();
+        bluestein_core<S>(tmp, T);
+        for (int k = threadIdx.x; k < n; k += blockDim.x) x[k] = cmul<S>(tmp[k], w[k]);   // Z_k = FFT(v_a + i v_b)_k
+        __syncthreads();
+        for (int k = threadIdx.x; k <= (n >> 1); k += blockDim.x) {
+            const int nk = k == 0 ? 0 : n - k;
+            const cplx_t<S> zk = x[k], zn = x[nk];
+            cplx_t<S> ok, on;
+            {
+                const S var = (S)0.5 * (zk.x + zn.x), vai = (S)0.5 * (zk.y - zn.y);
+                const S vbr = (S)0.5 * (zk.y + zn.y), vbi = (S)-0.5 * (zk.x - zn.x);
+                const cplx_t<S> ww = q[k];
+                ok.x = (S)2 * (var * ww.x - vai * ww.y); ok.y = (S)2 * (vbr * ww.x - vbi * ww.y);
+            }
+            {
+                const S var = (S)0.5 * (zn.x + zk.x), vai = (S)0.5 * (zn.y - zk.y);
+                const S vbr = (S)0.5 * (zn.y + zk.y), vbi = (S)-0.5 * (zn.x - zk.x);
+                const cplx_t<S> ww = q[nk];
+                on.x = (S)2 * (var * ww.x - vai * ww.y); on.y = (S)2 * (vbr * ww.x - vbi * ww.y);
+            }
+            x[k] = ok;
+            if (nk != k) x[nk] = on;
         }
         __syncthreads();
     } else {
@@ -186,6 +237,34 @@ __device__ void dct3_line(cplx_t<S> *x, cplx_t<S> *tmp, const LineTables &T) {
         }
         __syncthreads();
         fft_dif<S>(x, n, T.log2n, (const cplx_t<S> *)T.tw, +1);
+    } else if (T.bluestein) {
+        const cplx_t<S> *w = (const cplx_t<S> *)T.chirp, *q = (const cplx_t<S> *)T.q;
+        // h_j = (X_j - i X_{n-j}) e^{+i pi j / 2n} for both sequences, packed z_j = h_a + i h_b; the unnormalised inverse DFT
+        // t = n IFFT(z) is conj(DFT(conj z)): tmp_j = conj(z_j) w_j
+        for (int j = n + threadIdx.x; j < T.M; j += blockDim.x) { cplx_t<S> z; z.x = (S)0; z.y = (S)0; tmp[j] = z; }
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            cplx_t<S> z;
+            if (j == 0) z = x[0];
+            else {
+                const cplx_t<S> Xj = x[j], Xn = x[n - j];
+                const S cr = q[j].x, ci = -q[j].y;
+                const S har = Xj.x * cr + Xn.x * ci, hai = Xj.x * ci - Xn.x * cr;
+                const S hbr = Xj.y * cr + Xn.y * ci, hbi = Xj.y * ci - Xn.y * cr;
+                z.x = har - hbi; z.y = hai + hbr;
+            }
+            z.y = -z.y;
+            tmp[j] = cmul<S>(z, w[j]);
+        }
+        __syncthreads();
+        bluestein_core<S>(tmp, T);
+        // sample m of the output is t[makhoul_pos(m)] (a[2m'] = Re t[m'], a[2m'+1] = Re t[n-1-m'])
+        for (int m = threadIdx.x; m < n; m += blockDim.x) {
+            const int pos = makhoul_pos(m, n);
+            cplx_t<S> t = cmul<S>(tmp[pos], w[pos]);
+            t.y = -t.y;
+            x[m] = t;
+        }
+        __syncthreads();
     } else {
         for (int k = threadIdx.x; k < n; k += blockDim.x) {
             double sa = 0.0, sb = 0.0;
@@ -369,6 +448,46 @@ int build_tables(int n, LineTables *T, void **d_blob) {
         T->tw = *d_blob;
         T->q = (const cplx_t<S> *)*d_blob + ntw;
         if (reg) { T->tw16a = (const cplx_t<S> *)*d_blob + ntw + nq; T->tw16b = (const cplx_t<S> *)*d_blob + ntw + nq + 4 * s1; }
+    } else if (n >= 2 && n <= 4096) {
+        // Bluestein tables: [twM (M/2)] [q (n)] [chirp (n)] [bhat (M, bit-reversed, / M)]
+        int l = 0;
+        while ((1 << l) < 2 * n - 1) l++;
+        const int M = 1 << l;
+        T->M = M; T->log2M = l; T->bluestein = 1;
+        const size_t tot = (size_t)M / 2 + 2 * (size_t)n + (size_t)M;
+        cplx_t<S> *h = (cplx_t<S> *)malloc(sizeof(cplx_t<S>) * tot);
+        cplx_t<S> *twM = h, *q = h + M / 2, *chirp = q + n, *bhat = chirp + n;
+        for (int k = 0; k < M / 2; k++) { twM[k].x = (S)cos(-2.0 * kPi * k / M); twM[k].y = (S)sin(-2.0 * kPi * k / M); }
+        for (int k = 0; k < n; k++) { q[k].x = (S)cos(-kPi * k / (2.0 * n)); q[k].y = (S)sin(-kPi * k / (2.0 * n)); }
+        std::vector<std::complex<double>> b((size_t)M, std::complex<double>(0.0, 0.0));
+        for (int j = 0; j < n; j++) {
+            const long r = ((long)j * j) % (2L * n);                 // j^2 mod 2n keeps the angle exact
+            const double a = kPi * (double)r / n;
+            chirp[j].x = (S)cos(a); chirp[j].y = (S)-sin(a);         // w_j = e^{-i pi j^2 / n}
+            const std::complex<double> bj(cos(a), sin(a));
+            b[(size_t)j] = bj;
+            if (j) b[(size_t)(M - j)] = bj;
+        }
+        // in-place radix-2 DIF on the host: natural in, bit-reversed out -- the order the device multiplies in
+        for (int s = l - 1; s >= 0; s--) {
+            const int half = 1 << s;
+            for (int blk = 0; blk < M; blk += 2 * half)
+                for (int k = 0; k < half; k++) {
+                    const double a = -2.0 * kPi * (double)((long)k << (l - 1 - s)) / M;
+                    const std::complex<double> wv(cos(a), sin(a)), p = b[(size_t)(blk + k)], m2 = b[(size_t)(blk + k + half)];
+                    b[(size_t)(blk + k)] = p + m2;
+                    b[(size_t)(blk + k + half)] = (p - m2) * wv;
+                }
+        }
+        for (int k = 0; k < M; k++) { bhat[k].x = (S)(b[(size_t)k].real() / M); bhat[k].y = (S)(b[(size_t)k].imag() / M); }
+        cudaError_t e = cudaMalloc(d_blob, sizeof(cplx_t<S>) * tot);
+        if (e == cudaSuccess) e = cudaMemcpy(*d_blob, h, sizeof(cplx_t<S>) * tot, cudaMemcpyHostToDevice);
+        free(h);
+        if (e != cudaSuccess) { of2d_set_error("dct tables: %s", cudaGetErrorString(e)); return OF2D_ERR_CUDA; }
+        T->twM = *d_blob;
+        T->q = (const cplx_t<S> *)*d_blob + M / 2;
+        T->chirp = (const cplx_t<S> *)*d_blob + M / 2 + n;
+        T->bhat = (const cplx_t<S> *)*d_blob + M / 2 + 2 * n;
     } else {
         double *h = (double *)malloc(sizeof(double) * 4 * (size_t)n);
         for (int m = 0; m < 4 * n; m++) h[m] = cos(kPi * m / (2.0 * n));
@@ -548,8 +667,10 @@ int of2d_curvature_plan_create(of2d_ctx *ctx, int nx, int ny, double alpha, doub
         return OF2D_ERR_CUDA;
     }
     const size_t cs = sizeof(double2);
-    P->smem_rows = cs * (size_t)nx * (P->Tx.pow2 ? 1 : 2);
-    const size_t per_col = cs * (size_t)ny, extra = P->Ty.pow2 ? 0 : per_col;
+    // scratch next to the line: none (power of two), the M-point convolution buffer (Bluestein), a second line (direct sum)
+    auto scratch = [&](const LineTables &T) -> size_t { return T.pow2 ? 0 : T.bluestein ? cs * (size_t)T.M : cs * (size_t)T.n; };
+    P->smem_rows = cs * (size_t)nx + scratch(P->Tx);
+    const size_t per_col = cs * (size_t)ny, extra = scratch(P->Ty);
     int C = 4;
     while (C > 1 && per_col * C + extra > kMaxSmem) C >>= 1;
     P->cols_per_cta = C;
@@ -625,7 +746,8 @@ int of2d_dct2d_f64(of2d_ctx *ctx, int n0, int n1, int kind, double *d) {
     int st = build_tables<double>(n0, &T0, &b0);
     if (st == OF2D_SUCCESS) st = build_tables<double>(n1, &T1, &b1);
     if (st == OF2D_SUCCESS) {
-        const size_t s1 = sizeof(double2) * (size_t)n1 * 2, s0 = sizeof(double2) * (size_t)n0 * 2;
+        auto need = [&](const LineTables &T) -> size_t { return sizeof(double2) * ((size_t)T.n + (T.pow2 ? 0 : T.bluestein ? (size_t)T.M : (size_t)T.n)); };
+        const size_t s1 = need(T1), s0 = need(T0);
         if (s0 > kMaxSmem || s1 > kMaxSmem) { of2d_set_error("of2d_dct2d_f64: line too long for shared memory"); st = OF2D_ERR_UNSUPPORTED; }
         else {
             of2d_ensure_dynamic_smem((const void *)k_dct_lines<double>, s1 > s0 ? s1 : s0);

@@ -95,6 +95,18 @@ def test_relaxed_multiscale_and_refine_matches_oracle(reg, params, niter):
     assert maxdiff(mr, want["motion"]) <= tol
 
 
+@pytest.mark.parametrize("bits", [32, 64])
+@pytest.mark.parametrize("dimx,dimy", [(278, 256), (150, 203)])
+def test_curvature_on_non_power_of_two_sizes_matches_oracle(bits, dimx, dimy):
+    """fftw takes any n (OpticalFlowCurvature.cpp:52-55) and the reference's demo pads its slices to 278 x 256
+    (test_opticalflow2d.m:14-20): those sizes run Bluestein's algorithm inside the same DCT kernels."""
+    R, T = S.make_pair(dimx, dimy, "lattice", shift=(1.5, -0.75), smooth=True)
+    mr, tr, _ = run(bits, "relaxed", (dimx, dimy), R, T, of.CURVATURE, [0.25, 1.0], [15])
+    want = oracle(bits).register(R, T, of.CURVATURE, [0.25, 1.0], [15], nscales=0, nrefine=1, verbose=1)
+    assert tr["total_iterations"] == len(want["err"])
+    assert maxdiff(mr, want["motion"]) <= (1e-5 if bits == 32 else 1e-10)
+
+
 BREAKS = [("blob", (0.3, -0.2), 0.02, 145), ("lattice", (0.4, 0.1), 0.02, 147), ("lattice", (0.4, 0.1), 0.05, 188), ("blob", (1.0, 0.5), 0.02, 192)]
 
 

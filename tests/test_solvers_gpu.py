@@ -158,7 +158,8 @@ def test_demons_get_update_chain(bits, reg, params):
     assert np.array_equal(u.cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("n0,n1", [(8, 8), (64, 32), (256, 128), (12, 20), (2048, 4)])
+# non-powers of two: Bluestein (any n up to 4096, incl. primes and the demo's padded 278 = 2 x 139); 5000: direct sum
+@pytest.mark.parametrize("n0,n1", [(8, 8), (64, 32), (256, 128), (12, 20), (2048, 4), (278, 256), (139, 97), (3, 5), (1000, 6), (7, 3000), (4, 4095), (3, 5000)])
 @pytest.mark.parametrize("kind", [2, 3])
 def test_dct2d_matches_fftw_definition(n0, n1, kind):
     """The device transform against scipy's DCT-II/III (norm=None), i.e. FFTW's REDFT10/REDFT01."""
@@ -175,7 +176,8 @@ def test_dct2d_matches_fftw_definition(n0, n1, kind):
 
 @pytest.mark.parametrize("bits", BITS)
 @pytest.mark.parametrize("dimx,dimy", [(64, 32), (128, 128), (48, 40), (64, 64), (256, 128), (64, 512), (1024, 64), (2048, 256), (128, 4096),
-                                       (512, 512), (1024, 512), (512, 2048), (4096, 512), (2048, 1024)])   # >= 512 both ways: register path (dct_reg.cuh)
+                                       (512, 512), (1024, 512), (512, 2048), (4096, 512), (2048, 1024),   # >= 512 both ways: register path (dct_reg.cuh)
+                                       (278, 256), (256, 278), (139, 97), (600, 360)])                      # non-powers of two: Bluestein (test_opticalflow2d.m:14-20 pads to 278 x 256)
 def test_curvature_steps(bits, dimx, dimy):
     dev = device()
     orc, R, T, g, it, _ = _setup(bits, dimx, dimy)

@@ -69,7 +69,8 @@ def test_convolute_image(bits, dimx, dimy, w, sigma):
     d_in = to_dev(img)
     d_out = torch.empty_like(d_in)
     dev.call("convolute_image", TD[bits], dimx, dimy, 1, d_in, d_out, np.ascontiguousarray(k), w, w)
-    assert maxdiff(d_out.cpu().numpy(), want) <= (2e-7 if bits == 32 else 4e-16) * max(1.0, float(np.abs(want).max()))
+    # the reference promotes every tap product to double (float field x double weight); the kernel multiplies by the weight rounded to `real`: a few ulp
+    assert maxdiff(d_out.cpu().numpy(), want) <= (5e-7 if bits == 32 else 9e-16) * max(1.0, float(np.abs(want).max()))
 
 
 @pytest.mark.parametrize("bits", BITS)
@@ -89,7 +90,7 @@ def test_host_classes_image_motion_kernel_surface(bits):
     for w, sigma in ((5, 1.5), (3, -1.0)):
         assert lib.of2d_host_image_op(2, dimx, dimy, p(img), p(out), None, w, C.c_double(sigma)) == 0
         want = orc.convolute_image(img, w, sigma)
-        assert maxdiff(out, want) <= (2e-7 if bits == 32 else 4e-16) * max(1.0, float(np.abs(want).max()))
+        assert maxdiff(out, want) <= (5e-7 if bits == 32 else 9e-16) * max(1.0, float(np.abs(want).max()))
     u = S.random_motion(dimx, dimy, 2.0, 7, False).astype(NP[bits]).astype(np.float64)
     uo = np.zeros_like(u)
     for kind in (0, 1):
