@@ -241,6 +241,11 @@ except (OSError, ValueError):
 
 BATCH_METHODS = ["thirion", "fluid"]
 BATCH_PX = 512
+# pairs resident in the engine at a time (measured, 1 GPU, resident / e2e pairs/s -- Thirion: 64: 1025 / 950, 128: 1039 / 961, 256: 1178 / 1076;
+# Fluid, whose pairs stop after different iteration counts so that a wave lasts as long as its slowest pair: 64: 1621 / 1525, 128: 1564 / 1440, 256: 1459 / 1310)
+BATCH_WAVE = {"thirion": 256, "fluid": 64}
+if os.environ.get("OF2D_BENCH_WAVE"):
+    BATCH_WAVE = {m: int(os.environ["OF2D_BENCH_WAVE"]) for m in BATCH_WAVE}
 BATCH_NITER = {"thirion": 100, "fluid": 60}   # Fluid: the cap at which all sampled pairs are pinned to 1e-3 px (tests/test_configs_gpu.py)
 
 
@@ -449,7 +454,7 @@ def run_ours(args):
         pob = torch.empty((B, 2, bp, bp), dtype=torch.float64).pin_memory()
         del Rb, Tb
         for m in BATCH_METHODS:
-            bt = of.Batch((bp, bp), B, BATCH_NITER[m], REG[m], PARAMS[m], nrefine=1, wave=min(B, 256), bits=32)
+            bt = of.Batch((bp, bp), B, BATCH_NITER[m], REG[m], PARAMS[m], nrefine=1, wave=min(B, BATCH_WAVE[m]), bits=32)
             bt.set_images_raw(prb.data_ptr(), ptb.data_ptr())
             res = {}
             for leg in ("resident", "e2e"):
@@ -481,7 +486,7 @@ def run_ours(args):
             bt.close()
             batch_res[m] = res
         batch_res["config"] = {"workload": f"c5_batch_{bp}x{bp}", "total_pairs": args.batch, "n_gpus": world, "pairs_per_call": B, "calls_per_rank": ncalls,
-                               "niter_cap": BATCH_NITER, "wave": min(B, 256), "h2d_bytes_per_pair": 2 * bp * bp * 8, "d2h_bytes_per_pair": 2 * bp * bp * 8,
+                               "niter_cap": BATCH_NITER, "wave": {m: min(B, BATCH_WAVE[m]) for m in BATCH_METHODS}, "h2d_bytes_per_pair": 2 * bp * bp * 8, "d2h_bytes_per_pair": 2 * bp * bp * 8,
                                "e2e": "of2d_batch_register: pinned host doubles in, planar doubles out, copies of wave k+1 / k-1 under the solve of wave k",
                                "sharding": "contiguous pair ranges per rank, no collective in the solve"}
         del prb, ptb, pob

@@ -112,11 +112,31 @@ __device__ __forceinline__ int bitrev(int i, int log2n) { return (int)(__brev((u
 // Makhoul reordering: natural position m -> FFT input position
 __device__ __forceinline__ int makhoul_pos(int m, int n) { return (m & 1) ? n - 1 - (m >> 1) : (m >> 1); }
 
-// n-point DFT by Bluestein: on entry y[j] = v_j w_j (j < n), 0 for n <= j < M; on return DFT_n(v)_k = w_k y[k], k < n
+// dct_fast.cuh (included below): radix-8 / radix-4 FFTs on swizzled shared memory, M >= 64
+__device__ __forceinline__ int swz(int i);
+__device__ void fft_dit_fast(double2 *x, int n, int L, int nlines, const double2 *__restrict__ tw);
+__device__ void fft_dif_fast(double2 *x, int n, int L, int nlines, const double2 *__restrict__ tw);
+
+// n-point DFT by Bluestein's algorithm in the M-point buffer y.  Element j of the input sequence a_j = v_j w_j (j < n; the
+// caller zero-fills the rest) goes to y[bs_in(j)]; after bluestein_core(), DFT_n(v)_k = w_k y[bs_out(k)], k < n.
+//   M >= 64 (fast): forward DIT (bit-reversed in -> natural out), product with FFT_M(b) / M in natural order, inverse DIF
+//                   (natural in -> bit-reversed out), all through the bank swizzle of dct_fast.cuh;
+//   M <  64       : radix-2 DIF forward (natural -> bit-reversed), product with the bit-reversed table, DIT inverse.
+__device__ __forceinline__ int bs_in(int j, const LineTables &T) { return T.log2M >= 6 ? swz(bitrev(j, T.log2M)) : j; }
+__device__ __forceinline__ int bs_out(int k, const LineTables &T) { return T.log2M >= 6 ? swz(bitrev(k, T.log2M)) : k; }
 template <class S>
 __device__ void bluestein_core(cplx_t<S> *y, const LineTables &T) {
-    fft_dif<S>(y, T.M, T.log2M, (const cplx_t<S> *)T.twM, -1);          // natural -> bit-reversed
     const cplx_t<S> *bh = (const cplx_t<S> *)T.bhat;
+    if constexpr (sizeof(S) == 8) {
+        if (T.log2M >= 6) {
+            fft_dit_fast(y, T.M, T.log2M, 1, (const double2 *)T.twM);
+            for (int k = threadIdx.x; k < T.M; k += blockDim.x) { const int s = swz(k); y[s] = cmul<S>(y[s], bh[k]); }
+            __syncthreads();
+            fft_dif_fast(y, T.M, T.log2M, 1, (const double2 *)T.twM);
+            return;
+        }
+    }
+    fft_dif<S>(y, T.M, T.log2M, (const cplx_t<S> *)T.twM, -1);          // natural -> bit-reversed
     for (int k = threadIdx.x; k < T.M; k += blockDim.x) y[k] = cmul<S>(y[k], bh[k]);
     __syncthreads();
     fft_dit<S>(y, T.M, T.log2M, (const cplx_t<S> *)T.twM, +1);          // bit-reversed -> natural (1 / M is folded into bhat)
@@ -164,11 +184,11 @@ __device__ void dct2_line(cplx_t<S> *x, cplx_t<S> *tmp, const LineTables &T) {
     } else if (T.bluestein) {
         // x[m]: samples in natural order; tmp[M]: Makhoul-permuted, chirp-modulated, zero-padded
         const cplx_t<S> *w = (const cplx_t<S> *)T.chirp, *q = (const cplx_t<S> *)T.q;
-        for (int j = n + threadIdx.x; j < T.M; j += blockDim.x) { cplx_t<S> z; z.x = (S)0; z.y = (S)0; tmp[j] = z; }
-        for (int m = threadIdx.x; m < n; m += blockDim.x) { const int pos = makhoul_pos(m, n); tmp[pos] = cmul<S>(x[m], w[pos]); }
+        for (int j = n + threadIdx.x; j < T.M; j += blockDim.x) { cplx_t<S> z; z.x = (S)0; z.y = (S)0; tmp[bs_in(j, T)] = z; }
+        for (int m = threadIdx.x; m < n; m += blockDim.x) { const int pos = makhoul_pos(m, n); tmp[bs_in(pos, T)] = cmul<S>(x[m], w[pos]); }
         __syncthreads();
         bluestein_core<S>(tmp, T);
-        for (int k = threadIdx.x; k < n; k += blockDim.x) x[k] = cmul<S>(tmp[k], w[k]);   // Z_k = FFT(v_a + i v_b)_k
+        for (int k = threadIdx.x; k < n; k += blockDim.x) x[k] = cmul<S>(tmp[bs_out(k, T)], w[k]);   // Z_k = FFT(v_a + i v_b)_k
         __syncthreads();
         for (int k = threadIdx.x; k <= (n >> 1); k += blockDim.x) {
             const int nk = k == 0 ? 0 : n - k;
@@ -241,7 +261,7 @@ __device__ void dct3_line(cplx_t<S> *x, cplx_t<S> *tmp, const LineTables &T) {
         const cplx_t<S> *w = (const cplx_t<S> *)T.chirp, *q = (const cplx_t<S> *)T.q;
         // h_j = (X_j - i X_{n-j}) e^{+i pi j / 2n} for both sequences, packed z_j = h_a + i h_b; the unnormalised inverse DFT
         // t = n IFFT(z) is conj(DFT(conj z)): tmp_j = conj(z_j) w_j
-        for (int j = n + threadIdx.x; j < T.M; j += blockDim.x) { cplx_t<S> z; z.x = (S)0; z.y = (S)0; tmp[j] = z; }
+        for (int j = n + threadIdx.x; j < T.M; j += blockDim.x) { cplx_t<S> z; z.x = (S)0; z.y = (S)0; tmp[bs_in(j, T)] = z; }
         for (int j = threadIdx.x; j < n; j += blockDim.x) {
             cplx_t<S> z;
             if (j == 0) z = x[0];
@@ -253,14 +273,14 @@ __device__ void dct3_line(cplx_t<S> *x, cplx_t<S> *tmp, const LineTables &T) {
                 z.x = har - hbi; z.y = hai + hbr;
             }
             z.y = -z.y;
-            tmp[j] = cmul<S>(z, w[j]);
+            tmp[bs_in(j, T)] = cmul<S>(z, w[j]);
         }
         __syncthreads();
         bluestein_core<S>(tmp, T);
         // sample m of the output is t[makhoul_pos(m)] (a[2m'] = Re t[m'], a[2m'+1] = Re t[n-1-m'])
         for (int m = threadIdx.x; m < n; m += blockDim.x) {
             const int pos = makhoul_pos(m, n);
-            cplx_t<S> t = cmul<S>(tmp[pos], w[pos]);
+            cplx_t<S> t = cmul<S>(tmp[bs_out(pos, T)], w[pos]);
             t.y = -t.y;
             x[m] = t;
         }
@@ -479,7 +499,13 @@ int build_tables(int n, LineTables *T, void **d_blob) {
                     b[(size_t)(blk + k + half)] = (p - m2) * wv;
                 }
         }
-        for (int k = 0; k < M; k++) { bhat[k].x = (S)(b[(size_t)k].real() / M); bhat[k].y = (S)(b[(size_t)k].imag() / M); }
+        // b[] now holds FFT_M(b) in bit-reversed order: kept like that for the radix-2 device path (M < 64), natural order for the fast one
+        for (int k = 0; k < M; k++) {
+            unsigned r = 0;
+            for (int t = 0; t < l; t++) r |= ((unsigned)k >> t & 1u) << (l - 1 - t);
+            const std::complex<double> v = l >= 6 ? b[(size_t)r] : b[(size_t)k];
+            bhat[k].x = (S)(v.real() / M); bhat[k].y = (S)(v.imag() / M);
+        }
         cudaError_t e = cudaMalloc(d_blob, sizeof(cplx_t<S>) * tot);
         if (e == cudaSuccess) e = cudaMemcpy(*d_blob, h, sizeof(cplx_t<S>) * tot, cudaMemcpyHostToDevice);
         free(h);
