@@ -1,6 +1,7 @@
 #include <src/ImageRegistration.h>
 
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 
 #include <mex.h>
@@ -179,7 +180,15 @@ of2d_engine* ImageRegistration::engine_for_level(int level) {
     }
     of2d_engine* e = nullptr;
     const int st = of2d_engine_create(of2d::context(), &d, &e);
-    if (st == OF2D_ERR_UNSUPPORTED) { engine_refused[L] = 1; return nullptr; }
+    if (st == OF2D_ERR_UNSUPPORTED) {
+        // the engine declined this configuration (e.g. SOR parameters whose sweep does not contract fast enough for overlapped
+        // tiles, kernels wider than 15): the per-iteration path runs instead -- same results, but one launch group and one host
+        // round trip per iteration (Elastic / Fluid: the exact wavefront sweep, ~150x slower per sweep at 2048^2).  Say so once.
+        engine_refused[L] = 1;
+        std::fprintf(stderr, "OpticalFlow2d: level %d (%u x %u) runs on the per-iteration path, not on the device-resident engine: %s\n", level, dimin[level].x, dimin[level].y,
+                     of2d_last_error());
+        return nullptr;
+    }
     of2d::check(st);
     engines[L] = e;
     return e;

@@ -117,7 +117,7 @@ def test_tiled_sweep_matches_exact_wavefront(bits, reg, params, niter, dimx, dim
     assert maxdiff(mf, ms) <= achieved
 
 
-def test_non_contracting_sweep_falls_back_to_exact_path():
+def test_non_contracting_sweep_falls_back_to_exact_path(capfd):
     dimx, dimy = 96, 80
     R, T = S.make_pair(dimx, dimy, "lattice", shift=(1.0, -0.5))
     params = [1.0, 0.25, 1.9]           # over-relaxation: the tile halos would not converge
@@ -126,6 +126,7 @@ def test_non_contracting_sweep_falls_back_to_exact_path():
     assert maxdiff(mf, ms) == 0.0
     want = oracle(32).register(R, T, of.ELASTIC, params, [6], nscales=0, nrefine=1, verbose=1)
     assert maxdiff(mf, want["motion"]) == 0.0
+    assert "runs on the per-iteration path" in capfd.readouterr().err      # the 150x slower path is taken loudly, not silently
 
 
 @pytest.mark.parametrize("reg,params,niter", [(of.DIFFUSION, [0.5], [6, 8, 10]), (of.FLUID, [0.1, 0.0], [8, 8, 12]), (of.THIRION, [1.0, 0.25, 1.5, 1.5, 5, 0], [5, 6, 8])],
