@@ -123,6 +123,26 @@ template <> struct PairOps<float> {
 };
 #endif
 
+// the thread's RPT = 4 consecutive ring elements (index r0 = 4 t: 32-byte aligned for {x, y} floats, 16-byte for float scalars).
+// fp32: 128-bit shared-memory loads -- the thread stride of 32 bytes makes 64-bit loads 4-way and 32-bit loads 4-way bank
+// conflicted, 128-bit ones 2-way (pairs) / conflict-free (scalars); fp64 elements are 128 / 64 bits wide already.
+__device__ __forceinline__ void ld_block4(const float2 *p, float2 (&o)[4]) {
+    const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 2);
+    o[0] = make_float2(a.x, a.y); o[1] = make_float2(a.z, a.w); o[2] = make_float2(b.x, b.y); o[3] = make_float2(b.z, b.w);
+}
+__device__ __forceinline__ void ld_block4(const double2 *p, double2 (&o)[4]) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) o[r] = p[r];
+}
+__device__ __forceinline__ void ld_block4(const float *p, float (&o)[4]) {
+    const float4 a = *reinterpret_cast<const float4 *>(p);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+}
+__device__ __forceinline__ void ld_block4(const double *p, double (&o)[4]) {
+    const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+
 template <class R, int RPT, bool FLUID, bool WARP>
 __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) {
     pdl_enter();
@@ -160,8 +180,8 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
     auto st_g = [&](int s) { return reinterpret_cast<V *>(smem_raw + s * stage_bytes + x_bytes); };
     auto st_u = [&](int s) { return reinterpret_cast<V *>(smem_raw + s * stage_bytes + x_bytes) + LR; };
     auto st_t = [&](int s) { return reinterpret_cast<R *>(smem_raw + s * stage_bytes + x_bytes + (size_t)LR * sizeof(V) * (FLUID ? 2 : 1)); };
-    struct Pub { V top, d0; };
-    Pub *pub = reinterpret_cast<Pub *>(smem_raw + SOR_NS * stage_bytes);   // [2][NT]
+    // exchange between the threads of a column step, double-buffered over k: [2][top NT | d0 NT] (separate arrays: consecutive threads, consecutive words)
+    V *pub = reinterpret_cast<V *>(smem_raw + SOR_NS * stage_bytes);
     const unsigned tx_bytes = (unsigned)((size_t)LR * (sizeof(V) * (FLUID ? 3 : 2) + sizeof(R)));
 
     auto issue = [&](int k) {   // thread 0: loaded column k -> stage k % NS (TMA bulk copies, one per field)
@@ -215,7 +235,7 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
     {
         const V *x0 = st_x(0), *x1 = st_x(1 % SOR_NS);
 #pragma unroll
-        for (int r = 0; r < RPT + 2; r++) { newW[r] = x0[r0 - 1 + r]; oldC[r] = x1[r0 - 1 + r]; }
+        for (int r = 0; r < RPT + 2; r++) { newW[r] = x0[r0 - 1 + r]; oldC[r] = x1[r0 - 1 + r]; }   // (once per tile)
     }
     // fluid: the estimate u on the thread's rows of the column to the west (for du/dx of the fused increment)
     V uW[RPT];
@@ -266,8 +286,12 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
         {
             const V *xe = st_x(sE);
             oldE[0] = xe[r0 - 1];
+            {
+                V blk[4];
+                ld_block4(xe + r0, blk);
 #pragma unroll
-            for (int r = 0; r < RPT; r++) oldE[r + 1] = xe[r0 + r];
+                for (int r = 0; r < RPT; r++) oldE[r + 1] = blk[r];
+            }
             oldE[RPT + 1] = xe[r0 + RPT];
         }
         // everything of the reference's expression that does not involve the cell below (S):
@@ -279,16 +303,21 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
             const R *ts = st_t(sC);
             const V *us = st_u(sC);
             if (FLUID && i >= is) { uS = us[r0 - 1]; uN = us[r0 + RPT]; }
+            V gblk[4], ublk[4];
+            R tblk[4];
+            ld_block4(gs + r0, gblk);
+            ld_block4(ts + r0, tblk);
+            if (FLUID) ld_block4(us + r0, ublk);
 #pragma unroll
             for (int r = 0; r < RPT; r++) {
                 const V Cc = oldC[r + 1], N = oldC[r + 2];
                 const V W = newW[r + 1], SW = newW[r], NW = newW[r + 2];
                 const V E = oldE[r + 1], SE = oldE[r], NE = oldE[r + 2];
-                uC[r] = FLUID ? us[r0 + r] : Cc;
+                uC[r] = FLUID ? ublk[r] : Cc;
 #if OF2D_RELAXED
                 {   // the same expression regrouped: d = ck C + (cr s) dI - (cr mu) sum3 - (cr mupl) k2, fused multiply-adds
-                    const V dI = gs[r0 + r];
-                    const R sf = ts[r0 + r] + uC[r].x * dI.x + uC[r].y * dI.y;
+                    const V dI = gblk[r];
+                    const R sf = tblk[r] + uC[r].x * dI.x + uC[r].y * dI.y;
                     const V ew = po.add(E, W);
                     sum3[r] = po.add(ew, N);
                     const V cr4 = po.scale((R)0.25f, po.add(po.sub(po.sub(NE, NW), SE), SW));
@@ -299,9 +328,9 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
                 }
 #endif
                 {   // OpticalFlow::get_force (OpticalFlow.cpp:33): s = It + u.x dI.x + u.y dI.y; f = dI s
-                    const V dI = gs[r0 + r];
+                    const V dI = gblk[r];
                     const V pr = po.mul(uC[r], dI);
-                    const R sf = ts[r0 + r] + pr.x + pr.y;
+                    const R sf = tblk[r] + pr.x + pr.y;
                     bb[r] = po.scale(sf, dI);
                 }
                 const V ew = po.add(E, W);
@@ -345,13 +374,9 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
             d0_above.x = __shfl_down_sync(0xffffffffu, d[0].x, 1);
             d0_above.y = __shfl_down_sync(0xffffffffu, d[0].y, 1);
         } else {
-            Pub *pb = pub + (k & 1) * NT;
-            {
-                Pub me;
-                me.top = xt[RPT - 1];
-                me.d0 = d[0];
-                pb[t] = me;
-            }
+            V *pb_top = pub + (k & 1) * 2 * NT, *pb_d0 = pb_top + NT;
+            pb_top[t] = xt[RPT - 1];
+            pb_d0[t] = d[0];
             asm volatile("bar.sync 1, %0;" ::"r"(NT) : "memory");   // the compute threads only
             if (t == 0) {   // every compute thread has read stage sC (and stage 0 after the first step): the producer may refill it
                 if (k == 1) mbar_arrive(&empty[0]);
@@ -360,16 +385,16 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
 #if OF2D_RELAXED
 #pragma unroll
             for (int q = 0; q < MQ; q++) {
-                if (q < A.M) carry = po.fma(cq[q], pb[tqi[q]].top, carry);   // M <= 3 at the relaxed truncation (uniform branch)
+                if (q < A.M) carry = po.fma(cq[q], pb_top[tqi[q]], carry);   // M <= 3 at the relaxed truncation (uniform branch)
             }
 #else
 #pragma unroll
             for (int q = 0; q < MQ; q++) {
-                const V tv = pb[tqi[q]].top;
+                const V tv = pb_top[tqi[q]];
                 carry = po.add(carry, po.scale(cq[q], tv));
             }
 #endif
-            if (t + 1 < NT) d0_above = pb[t + 1].d0;
+            if (t + 1 < NT) d0_above = pb_d0[t + 1];
         }
         // the reference's expression, literally, with S = the (estimated) new value of the cell below
         V xn[RPT];
@@ -400,7 +425,7 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_sor_tile(SorTileArgs<R> A) 
             if (FLUID) {   // u on the thread's rows of the column to the east (its stage is refilled one step from now)
                 const V *ue = st_u(sE);
 #pragma unroll
-                for (int r = 0; r < RPT; r++) uE[r] = ue[r0 + r];
+                for (int r = 0; r < RPT; r++) uE[r] = ue[r0 + r];   // (only on owned columns)
             }
 #pragma unroll
             for (int r = 0; r < RPT; r++) {
