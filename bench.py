@@ -330,6 +330,11 @@ def run_ours(args):
     size = args.size
     n = size * size
     of.set_stream(torch.cuda.current_stream().cuda_stream, 32)
+    if of.get_math(32) >= 2:
+        # relaxed engine, fp32 fields: the Curvature transforms and the spectrum between the passes are single precision
+        # (dct_reg.cuh, namespace rgf) -- SURVEY 8(d)'s 60 B/px layout; the exact engine keeps the reference's double spectrum (92)
+        BYTES_PER_PX_ITER["curvature"] = 60
+        KERNEL_BYTES_PER_PX.update({"curv_rows_fwd": 28, "curv_cols": 16, "curv_rows_inv": 24, "curv_rows_inv_fwd": 44})
 
     # host inputs (pinned doubles, as the MEX boundary delivers them) and resident sessions
     sessions, pinned = {}, {}

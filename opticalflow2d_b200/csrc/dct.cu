@@ -435,7 +435,16 @@ __global__ void __launch_bounds__(FFT_THREADS) k_dct_lines(int nlines, int n, si
 }  // namespace
 
 #include "dct_fast.cuh"
-#include "dct_reg.cuh"
+#include "dct_reg.cuh"     // namespace rg: double precision (the reference's)
+#define RG_NS rgf
+#define RG_C2 float2
+#define RG_S float
+#define RG_MK2 make_float2
+#ifndef OF2D_RGF_MINB
+#define OF2D_RGF_MINB 3
+#endif
+#define RG_MINB OF2D_RGF_MINB   // resident CTAs of 256 threads the register allocation aims at (16 float2 points per thread: 3 -> 85 registers)
+#include "dct_reg.cuh"     // namespace rgf: single precision (relaxed engine, fp32 fields)
 
 namespace {
 
@@ -536,6 +545,9 @@ struct of2d_curvature_plan {
     double tau, alpha, tau_alpha;
     LineTables Tx, Ty;
     void *blob_x, *blob_y;
+    LineTables Txf, Tyf;        // single-precision tables of the register path (relaxed engine, fp32 fields)
+    void *blob_xf, *blob_yf;
+    int spec_f32;
     double *d_cosx, *d_cosy;
     void *d_spec;    // spectrum between the row and the column pass (transposed on the fast paths)
     void *d_spec2;   // register path: column pass output in the natural layout
@@ -546,72 +558,90 @@ struct of2d_curvature_plan {
 
 namespace {
 
-// dct_reg.cuh: register-blocked radix-16 path (both line lengths in 512 .. 4096)
+// dct_reg.cuh: register-blocked radix-16 path (both line lengths in 512 .. 4096).  A = rg::Api (double transform) or rgf::Api
+// (float transform, tables P->Txf / P->Tyf: relaxed engine on fp32 fields).
 // fuse_next: the inverse row pass also runs the forward row pass of the next iteration (k_rg_rows_inv<.., FUSE>)
-template <class R, int LX>
+template <class A> const LineTables &tables_x(const of2d_curvature_plan *P) { return sizeof(typename A::C2) == 8 ? P->Txf : P->Tx; }
+template <class A> const LineTables &tables_y(const of2d_curvature_plan *P) { return sizeof(typename A::C2) == 8 ? P->Tyf : P->Ty; }
+template <class A, class R, int LX>
 int launch_reg_rows(of2d_curvature_plan *P, bool fwd, const R *u, R *unew, const R *gradI, const R *It, const CurvHook &H, int batch, bool fuse_next = false) {
+    using C2 = typename A::C2;
     of2d_ctx *ctx = P->ctx;
-    constexpr int LPC = 2, NT = LPC * rg::Geo<LX>::TPL;
-    const size_t smem = sizeof(double2) * (size_t)P->nx * LPC;
-    const rg::Tw16 T{(const double2 *)P->Tx.tw16a, (const double2 *)P->Tx.tw16b};
+    constexpr int LPC = 2, NT = LPC * A::template G<LX>::TPL;
+    const size_t smem = sizeof(C2) * (size_t)P->nx * LPC;
+    const LineTables &TX = tables_x<A>(P);
+    const typename A::Tw T{(const C2 *)TX.tw16a, (const C2 *)TX.tw16b};
     const R fourN = (R)4.0f * (R)(unsigned)(P->nx * P->ny);
     if (fwd) {
-        { int st = of2d_ensure_dynamic_smem((const void *)rg::k_rg_rows_fwd<R, LX, LPC>, smem); if (st) return st; }
+        constexpr auto kern = A::template rows_fwd<R, LX, LPC>();
+        { int st = of2d_ensure_dynamic_smem((const void *)kern, smem); if (st) return st; }
         ProfScope _ps(ctx, "curv_rows_fwd");
-        pdl_launch(rg::k_rg_rows_fwd<R, LX, LPC>, dim3(P->ny / LPC, batch), NT, smem, ctx->stream, P->ny, (const vec2_t<R> *)u, (const vec2_t<R> *)unew, (const vec2_t<R> *)gradI, It,
-                                                                                       (R)P->tau, (double2 *)P->d_spec, (const double2 *)P->Tx.q, T, H);
+        pdl_launch(kern, dim3(P->ny / LPC, batch), NT, smem, ctx->stream, P->ny, (const vec2_t<R> *)u, (const vec2_t<R> *)unew, (const vec2_t<R> *)gradI, It,
+                   (R)P->tau, (C2 *)P->d_spec, (const C2 *)TX.q, T, H);
     } else if (fuse_next) {
-        { int st = of2d_ensure_dynamic_smem((const void *)rg::k_rg_rows_inv<R, LX, LPC, true>, smem); if (st) return st; }
+        constexpr auto kern = A::template rows_inv<R, LX, LPC, true>();
+        { int st = of2d_ensure_dynamic_smem((const void *)kern, smem); if (st) return st; }
         ProfScope _ps(ctx, "curv_rows_inv_fwd");
-        pdl_launch(rg::k_rg_rows_inv<R, LX, LPC, true>, dim3(P->ny / LPC, batch), NT, smem, ctx->stream, P->ny, (const double2 *)P->d_spec2, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN,
-                   (const double2 *)P->Tx.q, T, H, (const vec2_t<R> *)gradI, It, (R)P->tau, (double2 *)P->d_spec);
+        pdl_launch(kern, dim3(P->ny / LPC, batch), NT, smem, ctx->stream, P->ny, (const C2 *)P->d_spec2, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN,
+                   (const C2 *)TX.q, T, H, (const vec2_t<R> *)gradI, It, (R)P->tau, (C2 *)P->d_spec);
     } else {
-        { int st = of2d_ensure_dynamic_smem((const void *)rg::k_rg_rows_inv<R, LX, LPC, false>, smem); if (st) return st; }
+        constexpr auto kern = A::template rows_inv<R, LX, LPC, false>();
+        { int st = of2d_ensure_dynamic_smem((const void *)kern, smem); if (st) return st; }
         ProfScope _ps(ctx, "curv_rows_inv");
-        pdl_launch(rg::k_rg_rows_inv<R, LX, LPC, false>, dim3(P->ny / LPC, batch), NT, smem, ctx->stream, P->ny, (const double2 *)P->d_spec2, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN,
-                   (const double2 *)P->Tx.q, T, H, (const vec2_t<R> *)nullptr, (const R *)nullptr, (R)0, (double2 *)nullptr);
+        pdl_launch(kern, dim3(P->ny / LPC, batch), NT, smem, ctx->stream, P->ny, (const C2 *)P->d_spec2, (vec2_t<R> *)u, (vec2_t<R> *)unew, fourN,
+                   (const C2 *)TX.q, T, H, (const vec2_t<R> *)nullptr, (const R *)nullptr, (R)0, (C2 *)nullptr);
     }
     OF2D_LAUNCH_CHECK(ctx);
     return OF2D_SUCCESS;
 }
-template <int LY>
+template <class A, int LY>
 int launch_reg_cols(of2d_curvature_plan *P, const CurvHook &H, int batch) {
+    using C2 = typename A::C2;
     of2d_ctx *ctx = P->ctx;
-    constexpr int NT = 2 * rg::Geo<LY>::TPL;
-    const size_t smem = sizeof(double2) * (size_t)P->ny * 2;
-    const rg::Tw16 T{(const double2 *)P->Ty.tw16a, (const double2 *)P->Ty.tw16b};
-    { int st = of2d_ensure_dynamic_smem((const void *)rg::k_rg_cols<LY>, smem); if (st) return st; }
+    constexpr int NT = 2 * A::template G<LY>::TPL;
+    const size_t smem = sizeof(C2) * (size_t)P->ny * 2;
+    const LineTables &TY = tables_y<A>(P);
+    const typename A::Tw T{(const C2 *)TY.tw16a, (const C2 *)TY.tw16b};
+    constexpr auto kern = A::template cols<LY>();
+    { int st = of2d_ensure_dynamic_smem((const void *)kern, smem); if (st) return st; }
     ProfScope _ps(ctx, "curv_cols");
-    pdl_launch(rg::k_rg_cols<LY>, dim3(P->nx / 2, batch), NT, smem, ctx->stream, P->nx, (const double2 *)P->d_spec, (double2 *)P->d_spec2, P->d_cosx, P->d_cosy, P->tau_alpha,
-                                                                      (const double2 *)P->Ty.q, T, H);
+    pdl_launch(kern, dim3(P->nx / 2, batch), NT, smem, ctx->stream, P->nx, (const C2 *)P->d_spec, (C2 *)P->d_spec2, P->d_cosx, P->d_cosy, P->tau_alpha,
+               (const C2 *)TY.q, T, H);
     OF2D_LAUNCH_CHECK(ctx);
     return OF2D_SUCCESS;
 }
 // flags (engine loop only): OF2D_CURV_SKIP_FWD = the forward row pass of this iteration was already run by the previous
 // iteration's fused inverse pass; OF2D_CURV_FUSE_NEXT = this iteration's inverse pass runs the next iteration's forward pass
-template <class R>
-int curvature_step_reg(of2d_curvature_plan *P, const R *u, R *unew, const R *gradI, const R *It, const CurvHook &H, int flags) {
+template <class A, class R>
+int curvature_step_reg_a(of2d_curvature_plan *P, const R *u, R *unew, const R *gradI, const R *It, const CurvHook &H, int flags) {
     const int batch = H.enabled ? P->batch : 1;
     int st = OF2D_SUCCESS;
     const bool fuse_next = H.enabled && (flags & OF2D_CURV_FUSE_NEXT);
     for (int phase = (H.enabled && (flags & OF2D_CURV_SKIP_FWD)) ? 1 : 0; phase < 3 && st == OF2D_SUCCESS; phase++) {
         if (phase == 1) {
             switch (P->Ty.log2n) {
-                case 9: st = launch_reg_cols<9>(P, H, batch); break;
-                case 10: st = launch_reg_cols<10>(P, H, batch); break;
-                case 11: st = launch_reg_cols<11>(P, H, batch); break;
-                default: st = launch_reg_cols<12>(P, H, batch); break;
+                case 9: st = launch_reg_cols<A, 9>(P, H, batch); break;
+                case 10: st = launch_reg_cols<A, 10>(P, H, batch); break;
+                case 11: st = launch_reg_cols<A, 11>(P, H, batch); break;
+                default: st = launch_reg_cols<A, 12>(P, H, batch); break;
             }
         } else {
             switch (P->Tx.log2n) {
-                case 9: st = launch_reg_rows<R, 9>(P, phase == 0, u, unew, gradI, It, H, batch, phase == 2 && fuse_next); break;
-                case 10: st = launch_reg_rows<R, 10>(P, phase == 0, u, unew, gradI, It, H, batch, phase == 2 && fuse_next); break;
-                case 11: st = launch_reg_rows<R, 11>(P, phase == 0, u, unew, gradI, It, H, batch, phase == 2 && fuse_next); break;
-                default: st = launch_reg_rows<R, 12>(P, phase == 0, u, unew, gradI, It, H, batch, phase == 2 && fuse_next); break;
+                case 9: st = launch_reg_rows<A, R, 9>(P, phase == 0, u, unew, gradI, It, H, batch, phase == 2 && fuse_next); break;
+                case 10: st = launch_reg_rows<A, R, 10>(P, phase == 0, u, unew, gradI, It, H, batch, phase == 2 && fuse_next); break;
+                case 11: st = launch_reg_rows<A, R, 11>(P, phase == 0, u, unew, gradI, It, H, batch, phase == 2 && fuse_next); break;
+                default: st = launch_reg_rows<A, R, 12>(P, phase == 0, u, unew, gradI, It, H, batch, phase == 2 && fuse_next); break;
             }
         }
     }
     return st;
+}
+template <class R>
+int curvature_step_reg(of2d_curvature_plan *P, const R *u, R *unew, const R *gradI, const R *It, const CurvHook &H, int flags) {
+    if constexpr (sizeof(R) == 4) {
+        if (P->spec_f32) return curvature_step_reg_a<rgf::Api, R>(P, u, unew, gradI, It, H, flags);
+    }
+    return curvature_step_reg_a<rg::Api, R>(P, u, unew, gradI, It, H, flags);
 }
 
 template <class R, class S>
@@ -713,7 +743,7 @@ int of2d_curvature_plan_create(of2d_ctx *ctx, int nx, int ny, double alpha, doub
 void of2d_curvature_plan_destroy(of2d_curvature_plan *P) {
     if (!P) return;
     cudaStreamSynchronize(P->ctx->stream);
-    cudaFree(P->blob_x); cudaFree(P->blob_y); cudaFree(P->d_cosx); cudaFree(P->d_cosy); cudaFree(P->d_spec); cudaFree(P->d_spec2);
+    cudaFree(P->blob_x); cudaFree(P->blob_y); cudaFree(P->blob_xf); cudaFree(P->blob_yf); cudaFree(P->d_cosx); cudaFree(P->d_cosy); cudaFree(P->d_spec); cudaFree(P->d_spec2);
     delete P;
 }
 
@@ -733,6 +763,18 @@ int of2d_curvature_step_f64(of2d_curvature_plan *P, const double *u, double *une
 }  // extern "C"
 
 // engine entry points (engine_internal.cuh)
+// relaxed engine, fp32 fields, register path: the DCTs and the spectrum between the passes in single precision
+int of2d_curvature_plan_set_relaxed(of2d_curvature_plan *P, int on) {
+    if (!on || P->real_is_double || !(P->Tx.tw16a && P->Ty.tw16a)) { P->spec_f32 = 0; return OF2D_SUCCESS; }
+    { const char *e = getenv("OF2D_CURV_F32"); if (e && atoi(e) == 0) { P->spec_f32 = 0; return OF2D_SUCCESS; } }
+    if (!P->blob_xf) {
+        int st = build_tables<float>(P->nx, &P->Txf, &P->blob_xf);
+        if (st == OF2D_SUCCESS) st = build_tables<float>(P->ny, &P->Tyf, &P->blob_yf);
+        if (st != OF2D_SUCCESS) return st;
+    }
+    P->spec_f32 = 1;
+    return OF2D_SUCCESS;
+}
 int of2d_curvature_plan_set_batch(of2d_curvature_plan *P, int batch) {
     if (batch == P->batch) return OF2D_SUCCESS;
     OF2D_CUDA_TRY(cudaStreamSynchronize(P->ctx->stream));

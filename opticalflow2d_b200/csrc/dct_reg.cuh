@@ -16,35 +16,45 @@
 //   * FMA is allowed inside the FFT (the reference's fftw has no defined operation order to reproduce); the
 //     reference's own expressions (force, rhs, 1/(4N), eigenvalue) keep their order and stay unfused.
 // Shared-memory indices go through the XOR swizzle of dct_fast.cuh (conflict-free for every power-of-two stride).
-#pragma once
+//
+// The file is included TWICE by dct.cu: namespace rg (RG_S = double: the reference's precision, used by the strict path, the exact
+// engine and fp64 fields) and namespace rgf (RG_S = float: the relaxed engine on fp32 fields -- transform, twiddles and the
+// spectrum between the passes in single precision, 60 instead of 92 B/px per iteration and half the registers per point).
+#ifndef RG_NS
+#define RG_NS rg
+#define RG_C2 double2
+#define RG_S double
+#define RG_MK2 make_double2
+#define RG_MINB 2
+#endif
 
 namespace {
-namespace rg {
+namespace RG_NS {
 
-__device__ __forceinline__ double2 cmulf(double2 a, double2 b) { return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x)); }
-__device__ __forceinline__ double2 cmulcf(double2 a, double2 b) { return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -(a.x * b.y))); }   // a conj(b)
-__device__ __forceinline__ double2 add2(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ double2 sub2(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-template <int SIGN> __device__ __forceinline__ double2 mul_i(double2 a) { return SIGN > 0 ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x); }   // a (SIGN i)
+__device__ __forceinline__ RG_C2 cmulf(RG_C2 a, RG_C2 b) { return RG_MK2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x)); }
+__device__ __forceinline__ RG_C2 cmulcf(RG_C2 a, RG_C2 b) { return RG_MK2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -(a.x * b.y))); }   // a conj(b)
+__device__ __forceinline__ RG_C2 add2(RG_C2 a, RG_C2 b) { return RG_MK2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ RG_C2 sub2(RG_C2 a, RG_C2 b) { return RG_MK2(a.x - b.x, a.y - b.y); }
+template <int SIGN> __device__ __forceinline__ RG_C2 mul_i(RG_C2 a) { return SIGN > 0 ? RG_MK2(-a.y, a.x) : RG_MK2(a.y, -a.x); }   // a (SIGN i)
 
 // a e^{SIGN 2 pi i n / 16}
-template <int SIGN, int n> __device__ __forceinline__ double2 mul_w16(double2 a) {
+template <int SIGN, int n> __device__ __forceinline__ RG_C2 mul_w16(RG_C2 a) {
     constexpr int m = n & 15;
     if constexpr (m == 0) return a;
     else if constexpr (m == 4) return mul_i<SIGN>(a);
-    else if constexpr (m == 8) return make_double2(-a.x, -a.y);
+    else if constexpr (m == 8) return RG_MK2(-a.x, -a.y);
     else if constexpr (m == 12) return mul_i<-SIGN>(a);
     else {
         constexpr double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, r = 0.70710678118654752440;
         constexpr double C[16] = {1, c1, r, s1, 0, -s1, -r, -c1, -1, -c1, -r, -s1, 0, s1, r, c1};
         constexpr double S[16] = {0, s1, r, c1, 1, c1, r, s1, 0, -s1, -r, -c1, -1, -c1, -r, -s1};
-        constexpr double c = C[m], s = SIGN * S[m];
-        return make_double2(fma(a.x, c, -(a.y * s)), fma(a.x, s, a.y * c));
+        constexpr RG_S c = (RG_S)C[m], s = (RG_S)(SIGN * S[m]);
+        return RG_MK2(fma(a.x, c, -(a.y * s)), fma(a.x, s, a.y * c));
     }
 }
 
-template <int SIGN> __device__ __forceinline__ void radix4(double2 &a0, double2 &a1, double2 &a2, double2 &a3) {
-    const double2 p02 = add2(a0, a2), m02 = sub2(a0, a2), p13 = add2(a1, a3), d = mul_i<SIGN>(sub2(a1, a3));
+template <int SIGN> __device__ __forceinline__ void radix4(RG_C2 &a0, RG_C2 &a1, RG_C2 &a2, RG_C2 &a3) {
+    const RG_C2 p02 = add2(a0, a2), m02 = sub2(a0, a2), p13 = add2(a1, a3), d = mul_i<SIGN>(sub2(a1, a3));
     a0 = add2(p02, p13); a1 = add2(m02, d); a2 = sub2(p02, p13); a3 = sub2(m02, d);
 }
 
@@ -52,9 +62,9 @@ template <int SIGN> __device__ __forceinline__ void radix4(double2 &a0, double2 
 __host__ __device__ constexpr int slot_q(int R, int s) { return R == 16 ? (s >> 2) + 4 * (s & 3) : R == 8 ? (s >> 1) + 4 * (s & 1) : s; }
 
 // unnormalised R-point DFT with kernel e^{SIGN 2 pi i j q / R} of a[OFF .. OFF+R): output q is left in slot OFF + s, q = slot_q(R, s)
-template <int R, int SIGN, int OFF> __device__ __forceinline__ void dft(double2 (&a)[16]) {
+template <int R, int SIGN, int OFF> __device__ __forceinline__ void dft(RG_C2 (&a)[16]) {
     if constexpr (R == 2) {
-        const double2 p = add2(a[OFF], a[OFF + 1]), m = sub2(a[OFF], a[OFF + 1]);
+        const RG_C2 p = add2(a[OFF], a[OFF + 1]), m = sub2(a[OFF], a[OFF + 1]);
         a[OFF] = p; a[OFF + 1] = m;
     } else if constexpr (R == 4) {
         radix4<SIGN>(a[OFF], a[OFF + 1], a[OFF + 2], a[OFF + 3]);
@@ -63,7 +73,7 @@ template <int R, int SIGN, int OFF> __device__ __forceinline__ void dft(double2 
         radix4<SIGN>(a[OFF + 1], a[OFF + 3], a[OFF + 5], a[OFF + 7]);
         a[OFF + 3] = mul_w16<SIGN, 2>(a[OFF + 3]); a[OFF + 5] = mul_w16<SIGN, 4>(a[OFF + 5]); a[OFF + 7] = mul_w16<SIGN, 6>(a[OFF + 7]);
 #pragma unroll
-        for (int q1 = 0; q1 < 4; q1++) { const double2 p = add2(a[OFF + 2 * q1], a[OFF + 2 * q1 + 1]), m = sub2(a[OFF + 2 * q1], a[OFF + 2 * q1 + 1]); a[OFF + 2 * q1] = p; a[OFF + 2 * q1 + 1] = m; }
+        for (int q1 = 0; q1 < 4; q1++) { const RG_C2 p = add2(a[OFF + 2 * q1], a[OFF + 2 * q1 + 1]), m = sub2(a[OFF + 2 * q1], a[OFF + 2 * q1 + 1]); a[OFF + 2 * q1] = p; a[OFF + 2 * q1 + 1] = m; }
     } else {                         // j = j0 + 4 j1, q = q1 + 4 q0
         radix4<SIGN>(a[0], a[4], a[8], a[12]);
         radix4<SIGN>(a[1], a[5], a[9], a[13]);
@@ -80,20 +90,20 @@ template <int R, int SIGN, int OFF> __device__ __forceinline__ void dft(double2 
 }
 
 // a[idx(q)] *= w^q (CONJ: conj(w)^q), q = 1..15, from w, w^2, w^4, w^8; SLOT: a[] is in dft<16> output order
-template <bool SLOT, bool CONJ> __device__ __forceinline__ void twiddle16(double2 (&a)[16], double2 w1, double2 w2, double2 w4, double2 w8) {
+template <bool SLOT, bool CONJ> __device__ __forceinline__ void twiddle16(RG_C2 (&a)[16], RG_C2 w1, RG_C2 w2, RG_C2 w4, RG_C2 w8) {
 #define RG_AT(q) a[SLOT ? slot_q(16, (q)) : (q)]
 #define RG_MUL(q, w) RG_AT(q) = CONJ ? cmulcf(RG_AT(q), w) : cmulf(RG_AT(q), w)
     RG_MUL(1, w1); RG_MUL(2, w2); RG_MUL(4, w4); RG_MUL(8, w8);
-    const double2 w3 = cmulf(w1, w2), w5 = cmulf(w1, w4), w6 = cmulf(w2, w4), w12 = cmulf(w4, w8);
+    const RG_C2 w3 = cmulf(w1, w2), w5 = cmulf(w1, w4), w6 = cmulf(w2, w4), w12 = cmulf(w4, w8);
     RG_MUL(3, w3); RG_MUL(5, w5); RG_MUL(6, w6); RG_MUL(12, w12);
-    const double2 w7 = cmulf(w3, w4);
+    const RG_C2 w7 = cmulf(w3, w4);
     RG_MUL(7, w7);
-    { const double2 w9 = cmulf(w1, w8); RG_MUL(9, w9); }
-    { const double2 w10 = cmulf(w2, w8); RG_MUL(10, w10); }
-    { const double2 w11 = cmulf(w3, w8); RG_MUL(11, w11); }
-    { const double2 w13 = cmulf(w5, w8); RG_MUL(13, w13); }
-    { const double2 w14 = cmulf(w6, w8); RG_MUL(14, w14); }
-    { const double2 w15 = cmulf(w7, w8); RG_MUL(15, w15); }
+    { const RG_C2 w9 = cmulf(w1, w8); RG_MUL(9, w9); }
+    { const RG_C2 w10 = cmulf(w2, w8); RG_MUL(10, w10); }
+    { const RG_C2 w11 = cmulf(w3, w8); RG_MUL(11, w11); }
+    { const RG_C2 w13 = cmulf(w5, w8); RG_MUL(13, w13); }
+    { const RG_C2 w14 = cmulf(w6, w8); RG_MUL(14, w14); }
+    { const RG_C2 w15 = cmulf(w7, w8); RG_MUL(15, w15); }
 #undef RG_MUL
 #undef RG_AT
 }
@@ -110,12 +120,12 @@ template <int L> struct Geo {
     }
 };
 
-struct Tw16 { const double2 *a, *b; };   // [4][S1] for super-pass 1 (w_N), [4][S2] for super-pass 2 (w_{N/16}); forward sign
+struct Tw16 { const RG_C2 *a, *b; };   // [4][S1] for super-pass 1 (w_N), [4][S2] for super-pass 2 (w_{N/16}); forward sign
 
 // ---- forward (DIF): registers -> ... -> shared memory, digit-reversed --------------------------------------------
 // in: a[j] = v[k + S1 j] (natural order); the threads of a line hold k1 = a permutation of 0 .. S1-1 and u = 0 .. S1-1.
 // out: X_k at xl[swz(pos(k))], after the trailing barrier.
-template <int L> __device__ __forceinline__ void fft_fwd(double2 (&a)[16], double2 *xl, int u, int k1, Tw16 T) {
+template <int L> __device__ __forceinline__ void fft_fwd(RG_C2 (&a)[16], RG_C2 *xl, int u, int k1, Tw16 T) {
     using G = Geo<L>;
     {
         const int k = k1;
@@ -152,7 +162,7 @@ template <int L> __device__ __forceinline__ void fft_fwd(double2 (&a)[16], doubl
 // in: h_k at xl[swz(pos(k))] (caller has synchronised).  out: a[s] = t[k1 + S1 q], q = slot_q(16, s).
 // `before_last_barrier` runs while a[] is dead (prefetches of the epilogue go there).
 struct NoHook { __device__ __forceinline__ void operator()() const {} };
-template <int L, class Hook = NoHook> __device__ __forceinline__ void fft_inv(double2 (&a)[16], double2 *xl, int u, int k1, Tw16 T, Hook before_last_barrier = Hook()) {
+template <int L, class Hook = NoHook> __device__ __forceinline__ void fft_inv(RG_C2 (&a)[16], RG_C2 *xl, int u, int k1, Tw16 T, Hook before_last_barrier = Hook()) {
     using G = Geo<L>;
     {
 #pragma unroll
@@ -187,17 +197,17 @@ template <int L, class Hook = NoHook> __device__ __forceinline__ void fft_inv(do
 
 // DCT-II post-twiddle of the pair (k, N-k) of the packed FFT output (same algebra as dct2_post_pair with the factors
 // 1/2 and 2 cancelled and q_{N-k} = -i conj(q_k)): ok = (A_k, B_k), on = (A_{N-k}, B_{N-k}).  zn = zk for k = 0, N/2.
-__device__ __forceinline__ void post_pair(double2 zk, double2 zn, double2 q, double2 &ok, double2 &on) {
-    const double sx = zk.x + zn.x, sy = zk.y - zn.y, dx = zk.x - zn.x, dy = zk.y + zn.y;
-    ok = make_double2(fma(sx, q.x, -(sy * q.y)), fma(dy, q.x, dx * q.y));
-    on = make_double2(-fma(sx, q.y, sy * q.x), fma(dx, q.x, -(dy * q.y)));
+__device__ __forceinline__ void post_pair(RG_C2 zk, RG_C2 zn, RG_C2 q, RG_C2 &ok, RG_C2 &on) {
+    const RG_S sx = zk.x + zn.x, sy = zk.y - zn.y, dx = zk.x - zn.x, dy = zk.y + zn.y;
+    ok = RG_MK2(fma(sx, q.x, -(sy * q.y)), fma(dy, q.x, dx * q.y));
+    on = RG_MK2(-fma(sx, q.y, sy * q.x), fma(dx, q.x, -(dy * q.y)));
 }
 // DCT-III pre-twiddle of the pair (j, N-j), j >= 1: h_j = (X_j - i X_{N-j}) conj(q_j) for both packed sequences
-__device__ __forceinline__ void pre_pair(double2 Xj, double2 Xn, double2 q, double2 &oj, double2 &on) {
-    const double har = fma(Xj.x, q.x, -(Xn.x * q.y)), hai = -fma(Xj.x, q.y, Xn.x * q.x);
-    const double hbr = fma(Xj.y, q.x, -(Xn.y * q.y)), hbi = -fma(Xj.y, q.y, Xn.y * q.x);
-    oj = make_double2(har - hbi, hai + hbr);
-    on = make_double2(har + hbi, hbr - hai);
+__device__ __forceinline__ void pre_pair(RG_C2 Xj, RG_C2 Xn, RG_C2 q, RG_C2 &oj, RG_C2 &on) {
+    const RG_S har = fma(Xj.x, q.x, -(Xn.x * q.y)), hai = -fma(Xj.x, q.y, Xn.x * q.x);
+    const RG_S hbr = fma(Xj.y, q.x, -(Xn.y * q.y)), hbi = -fma(Xj.y, q.y, Xn.y * q.x);
+    oj = RG_MK2(har - hbi, hai + hbr);
+    on = RG_MK2(har + hbi, hbr - hai);
 }
 
 template <class R> __device__ __forceinline__ void load_px_pair(const vec2_t<R> *p, vec2_t<R> &a, vec2_t<R> &b) { a = p[0]; b = p[1]; }
@@ -212,14 +222,14 @@ template <> __device__ __forceinline__ void load_s_pair<float>(const float *p, f
 
 // ---- P1: LPC rows per CTA.  rhs = u - tau f, DCT-II along x, spectrum written transposed -----------------------------
 template <class R, int L, int LPC>
-__global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 2 : 1) k_rg_rows_fwd(int ny, const vec2_t<R> *est0, const vec2_t<R> *est1, const vec2_t<R> *__restrict__ gradI,
-                                                                   const R *__restrict__ It, R tau, double2 *__restrict__ specT, const double2 *__restrict__ q, Tw16 T,
+__global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? RG_MINB : 1) k_rg_rows_fwd(int ny, const vec2_t<R> *est0, const vec2_t<R> *est1, const vec2_t<R> *__restrict__ gradI,
+                                                                   const R *__restrict__ It, R tau, RG_C2 *__restrict__ specT, const RG_C2 *__restrict__ q, Tw16 T,
                                                                    CurvHook H) {
     pdl_enter();
     using G = Geo<L>;
     constexpr int N = G::N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *x = reinterpret_cast<double2 *>(smem_raw);   // [LPC][N]
+    RG_C2 *x = reinterpret_cast<RG_C2 *>(smem_raw);   // [LPC][N]
     const size_t pair_off = (size_t)blockIdx.y * N * ny;
     const vec2_t<R> *__restrict__ uin = est0;
     if (H.enabled) {
@@ -229,8 +239,8 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
     }
     uin += pair_off; gradI += pair_off; It += pair_off; specT += pair_off;
     const int tid = threadIdx.x, l = tid / G::TPL, u = tid % G::TPL, j0 = blockIdx.x * LPC;
-    double2 *xl = x + l * N;
-    double2 a[16];
+    RG_C2 *xl = x + l * N;
+    RG_C2 a[16];
     {   // pixel pairs (2m, 2m+1), m = k + S1 j (j < 8): the even pixel is v[m] (mine), the odd one v[N-1-m] (lane ^ 16, element 15-j)
         const int k = G::k1(u);
         const size_t row = (size_t)(j0 + l) * N;
@@ -241,16 +251,16 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
             load_px_pair<R>(uin + g, u0, u1); load_px_pair<R>(gradI + g, g0, g1); load_s_pair<R>(It + g, t0, t1);
             const vec2_t<R> f0 = lssd_force<R>(g0, t0, u0), f1 = lssd_force<R>(g1, t1, u1);                  // OpticalFlow.cpp:33
             const R ex = u0.x - tau * f0.x, ey = u0.y - tau * f0.y, ox = u1.x - tau * f1.x, oy = u1.y - tau * f1.y;   // OpticalFlowCurvature.cpp:90-91
-            a[j] = make_double2((double)ex, (double)ey);
-            a[15 - j] = make_double2((double)__shfl_xor_sync(0xffffffffu, ox, 16), (double)__shfl_xor_sync(0xffffffffu, oy, 16));
+            a[j] = RG_MK2((RG_S)ex, (RG_S)ey);
+            a[15 - j] = RG_MK2((RG_S)__shfl_xor_sync(0xffffffffu, ox, 16), (RG_S)__shfl_xor_sync(0xffffffffu, oy, 16));
         }
     }
     fft_fwd<L>(a, xl, u, G::k1(u), T);
     constexpr int hp = (N >> 1) + 1;
     for (int e = tid; e < LPC * hp; e += LPC * G::TPL) {
         const int ll = e % LPC, k = e / LPC, nk = (N - k) & (N - 1);
-        const double2 *base = x + ll * N;
-        double2 ok, on;
+        const RG_C2 *base = x + ll * N;
+        RG_C2 ok, on;
         post_pair(base[swz(G::pos(k))], base[swz(G::pos(nk))], q[k], ok, on);
         specT[(size_t)k * ny + j0 + ll] = ok;
         if (nk != k) specT[(size_t)nk * ny + j0 + ll] = on;
@@ -262,20 +272,20 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
 // shared-memory phases stay conflict-free), and the result goes out in the NATURAL layout spec_N[y][p]: lane pairs
 // (l, l+16) fill whole 32-byte sectors, so P3 reads contiguous rows and all scattered traffic of the iteration is writes.
 template <int L>
-__global__ void __launch_bounds__(2 * Geo<L>::TPL, 2 * Geo<L>::TPL <= 256 ? 2 : 1) k_rg_cols(int nx, const double2 *__restrict__ specT, double2 *__restrict__ specN,
+__global__ void __launch_bounds__(2 * Geo<L>::TPL, 2 * Geo<L>::TPL <= 256 ? RG_MINB : 1) k_rg_cols(int nx, const RG_C2 *__restrict__ specT, RG_C2 *__restrict__ specN,
                                                                                         const double *__restrict__ cosx, const double *__restrict__ cosy, double tau_alpha,
-                                                                                        const double2 *__restrict__ q, Tw16 T, CurvHook H) {
+                                                                                        const RG_C2 *__restrict__ q, Tw16 T, CurvHook H) {
     pdl_enter();
     using G = Geo<L>;
     constexpr int N = G::N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *x = reinterpret_cast<double2 *>(smem_raw);   // [2][N]
+    RG_C2 *x = reinterpret_cast<RG_C2 *>(smem_raw);   // [2][N]
     if (H.enabled && !__ldcg(&H.ctl[blockIdx.y].active)) return;
     const int tid = threadIdx.x, lane = tid & 31, l = lane >> 4, u = (tid >> 5) * 16 + (lane & 15), p = blockIdx.x * 2 + l;
-    double2 *xl = x + l * N;
-    const double2 *__restrict__ line = specT + (size_t)blockIdx.y * nx * N + (size_t)p * N;
+    RG_C2 *xl = x + l * N;
+    const RG_C2 *__restrict__ line = specT + (size_t)blockIdx.y * nx * N + (size_t)p * N;
     specN += (size_t)blockIdx.y * nx * N;
-    double2 a[16];
+    RG_C2 a[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) {
         const int m = u + G::S1 * j;
@@ -287,15 +297,15 @@ __global__ void __launch_bounds__(2 * Geo<L>::TPL, 2 * Geo<L>::TPL <= 256 ? 2 : 
     for (int c = 0; c < 8; c++) {   // pairs (k, N-k), k = 1 .. N/2-1 (and the self pair k = 0: thread 0, c = 0)
         const int k = u + G::TPL * c, nk = (N - k) & (N - 1);
         const int sk = swz(G::pos(k)), sn = swz(G::pos(nk));
-        const double2 qk = q[k];
-        double2 ak, an;
+        const RG_C2 qk = q[k];
+        RG_C2 ak, an;
         post_pair(xl[sk], xl[sn], qk, ak, an);
         // OpticalFlowCurvature.cpp:24, :135-136: 1 / (1 + tau alpha lap^2) for k and N-k, with one division for the two
         const double lk = -4 + cxp + cosy[k], ln = -4 + cxp + cosy[nk];
         const double dk = 1.0f + tau_alpha * (lk * lk), dn = 1.0f + tau_alpha * (ln * ln);
         const double r = 1.0 / (dk * dn), ek = r * dn, en = r * dk;
-        ak.x *= ek; ak.y *= ek; an.x *= en; an.y *= en;
-        double2 oj, on;
+        { const RG_S fk = (RG_S)ek, fn = (RG_S)en; ak.x *= fk; ak.y *= fk; an.x *= fn; an.y *= fn; }
+        RG_C2 oj, on;
         pre_pair(ak, an, qk, oj, on);
         if (k == 0) {                             // h_0 = X_0
             xl[sk] = ak;
@@ -307,13 +317,13 @@ __global__ void __launch_bounds__(2 * Geo<L>::TPL, 2 * Geo<L>::TPL <= 256 ? 2 : 
     if (u == 0) {                                 // self pair k = N/2
         constexpr int k = N >> 1;
         const int sk = swz(G::pos(k));
-        const double2 qk = q[k], z = xl[sk];
-        double2 ak, an;
+        const RG_C2 qk = q[k], z = xl[sk];
+        RG_C2 ak, an;
         post_pair(z, z, qk, ak, an);
         const double lk = -4 + cxp + cosy[k];
         const double ek = 1.0f / (1.0f + tau_alpha * (lk * lk));
-        ak.x *= ek; ak.y *= ek;
-        double2 oj, on;
+        { const RG_S fk = (RG_S)ek; ak.x *= fk; ak.y *= fk; }
+        RG_C2 oj, on;
         pre_pair(ak, ak, qk, oj, on);
         xl[sk] = oj;
     }
@@ -332,14 +342,14 @@ __global__ void __launch_bounds__(2 * Geo<L>::TPL, 2 * Geo<L>::TPL <= 256 ? 2 : 
 // two launches (columns, rows) and u' is not read back.  The forward part runs whatever the Logger decides: if the
 // loop ends here its spectrum is simply never used.
 template <class R, int L, int LPC, bool FUSE>
-__global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 2 : 1) k_rg_rows_inv(int ny, const double2 *__restrict__ specN, vec2_t<R> *est0, vec2_t<R> *est1, R fourN,
-                                                                   const double2 *__restrict__ q, Tw16 T, CurvHook H, const vec2_t<R> *__restrict__ gradI,
-                                                                   const R *__restrict__ It, R tau, double2 *__restrict__ specT) {
+__global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? RG_MINB : 1) k_rg_rows_inv(int ny, const RG_C2 *__restrict__ specN, vec2_t<R> *est0, vec2_t<R> *est1, R fourN,
+                                                                   const RG_C2 *__restrict__ q, Tw16 T, CurvHook H, const vec2_t<R> *__restrict__ gradI,
+                                                                   const R *__restrict__ It, R tau, RG_C2 *__restrict__ specT) {
     pdl_enter();
     using G = Geo<L>;
     constexpr int N = G::N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *x = reinterpret_cast<double2 *>(smem_raw);   // [LPC][N]
+    RG_C2 *x = reinterpret_cast<RG_C2 *>(smem_raw);   // [LPC][N]
     const int pair = blockIdx.y;
     const size_t pair_off = (size_t)pair * N * ny;
     vec2_t<R> *__restrict__ unew = est1;
@@ -352,22 +362,22 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
     }
     unew += pair_off; uold += pair_off; specN += pair_off;
     const int tid = threadIdx.x, l = tid / G::TPL, u = tid % G::TPL, j0 = blockIdx.x * LPC;
-    double2 a[16];
+    RG_C2 a[16];
     {   // pairs (j, N-j), j = 1 .. N/2-1 of each line (contiguous in spec_N): 8 per thread, all 16 loads issued before the first use
         constexpr int NT = LPC * G::TPL, per_line = (N >> 1) - 1, items = LPC * per_line;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
             const int e = tid + NT * c, ll = e / per_line, j = 1 + e % per_line;
             if (e < items) {
-                const double2 *ln = specN + (size_t)(j0 + ll) * N;
+                const RG_C2 *ln = specN + (size_t)(j0 + ll) * N;
                 a[2 * c] = ln[j];
                 a[2 * c + 1] = ln[N - j];
             }
         }
         if (tid < 2 * LPC) {                                          // j = 0 (h_0 = X_0; pos(0) = 0 = swz(0)) and the self pair j = N/2
             const int ll = tid % LPC, j = (tid / LPC) * (N >> 1);
-            const double2 Xj = specN[(size_t)(j0 + ll) * N + j];
-            double2 oj = Xj, on;
+            const RG_C2 Xj = specN[(size_t)(j0 + ll) * N + j];
+            RG_C2 oj = Xj, on;
             if (j) pre_pair(Xj, Xj, q[j], oj, on);
             x[ll * N + swz(G::pos(j))] = oj;
         }
@@ -375,7 +385,7 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
         for (int c = 0; c < 8; c++) {
             const int e = tid + NT * c, ll = e / per_line, j = 1 + e % per_line;
             if (e < items) {
-                double2 oj, on;
+                RG_C2 oj, on;
                 pre_pair(a[2 * c], a[2 * c + 1], q[j], oj, on);
                 x[ll * N + swz(G::pos(j))] = oj;
                 x[ll * N + swz(G::pos(N - j))] = on;
@@ -402,7 +412,7 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
 #pragma unroll
         for (int qq = 0; qq < 8; qq++) {
             // t[m] (mine, m = k + S1 qq) is pixel 2m; pixel 2m+1 is t[N-1-m] = element 15-qq of lane ^ 16
-            const double2 ve = a[slot_q(16, qq)], vs = a[slot_q(16, 15 - qq)];
+            const RG_C2 ve = a[slot_q(16, qq)], vs = a[slot_q(16, 15 - qq)];
             const vec2_t<R> o0 = mk2<R>((R)ve.x / fourN, (R)ve.y / fourN);                      // OpticalFlowCurvature.cpp:116-117
             const vec2_t<R> os = mk2<R>((R)vs.x / fourN, (R)vs.y / fourN);
             const vec2_t<R> o1 = mk2<R>(__shfl_xor_sync(0xffffffffu, os.x, 16), __shfl_xor_sync(0xffffffffu, os.y, 16));
@@ -432,16 +442,16 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
             const vec2_t<R> u0 = ue[j], u1 = uo[j];
             const vec2_t<R> f0 = lssd_force<R>(g0, t0, u0), f1 = lssd_force<R>(g1, t1, u1);                  // OpticalFlow.cpp:33
             const R ex = u0.x - tau * f0.x, ey = u0.y - tau * f0.y, ox = u1.x - tau * f1.x, oy = u1.y - tau * f1.y;   // OpticalFlowCurvature.cpp:90-91
-            a[j] = make_double2((double)ex, (double)ey);
-            a[15 - j] = make_double2((double)__shfl_xor_sync(0xffffffffu, ox, 16), (double)__shfl_xor_sync(0xffffffffu, oy, 16));
+            a[j] = RG_MK2((RG_S)ex, (RG_S)ey);
+            a[15 - j] = RG_MK2((RG_S)__shfl_xor_sync(0xffffffffu, ox, 16), (RG_S)__shfl_xor_sync(0xffffffffu, oy, 16));
         }
         __syncthreads();   // every thread has left the last shared-memory phase of the inverse transform
         fft_fwd<L>(a, x + l * N, u, k, T);
         constexpr int hp = (N >> 1) + 1;
         for (int e = tid; e < LPC * hp; e += LPC * G::TPL) {
             const int ll = e % LPC, kk = e / LPC, nk = (N - kk) & (N - 1);
-            const double2 *base = x + ll * N;
-            double2 ok, on;
+            const RG_C2 *base = x + ll * N;
+            RG_C2 ok, on;
             post_pair(base[swz(G::pos(kk))], base[swz(G::pos(nk))], q[kk], ok, on);
             specT[(size_t)kk * ny + j0 + ll] = ok;
             if (nk != kk) specT[(size_t)nk * ny + j0 + ll] = on;
@@ -461,5 +471,21 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
     }
 }
 
-}  // namespace rg
+// handle for the host launch code (dct.cu), which is written once for both instantiations of this file
+struct Api {
+    using C2 = RG_C2;
+    using Tw = Tw16;
+    template <int L> using G = Geo<L>;
+    template <class R, int L, int LPC> static constexpr auto rows_fwd() { return &k_rg_rows_fwd<R, L, LPC>; }
+    template <class R, int L, int LPC, bool FUSE> static constexpr auto rows_inv() { return &k_rg_rows_inv<R, L, LPC, FUSE>; }
+    template <int L> static constexpr auto cols() { return &k_rg_cols<L>; }
+};
+
+}  // namespace RG_NS
 }  // namespace
+
+#undef RG_NS
+#undef RG_C2
+#undef RG_S
+#undef RG_MK2
+#undef RG_MINB

@@ -546,6 +546,9 @@ int ENG(create)(of2d_ctx *ctx, const of2d_engine_desc *desc, of2d_engine_head **
     if (m == 1) {
         if ((st = of2d_curvature_plan_create(ctx, nx, ny, desc->alpha, desc->tau, E->dbl ? 1 : 0, &E->plan))) return fail(st);
         if ((st = of2d_curvature_plan_set_batch(E->plan, B))) return fail(st);
+#if OF2D_RELAXED
+        if ((st = of2d_curvature_plan_set_relaxed(E->plan, 1))) return fail(st);
+#endif
     }
     if (cudaHostAlloc((void **)&E->h_snap, sizeof(int) * 2, cudaHostAllocDefault) != cudaSuccess) { of2d_set_error("engine: pinned allocation failed"); return fail(OF2D_ERR_CUDA); }
     for (int k = 0; k < 2; k++)

@@ -13,6 +13,7 @@ int of2d_curvature_engine_step(of2d_curvature_plan *plan, PairCtl *ctl, int *n_a
                                const void *gradI, const void *It, int flags);
 int of2d_curvature_plan_fuses_rows(const of2d_curvature_plan *plan);   // 1 if the plan takes that path (else flags are ignored: pass 0)
 int of2d_curvature_plan_set_batch(of2d_curvature_plan *plan, int batch);
+int of2d_curvature_plan_set_relaxed(of2d_curvature_plan *plan, int on);   // fp32 fields on the register path: single-precision transform and spectrum
 
 // ---- the two builds of the iteration engine (engine.cu compiled as is, and through engine_relaxed.cu) ---------------
 // Both define the same object behind an `of2d_engine_head`; engine_dispatch.cu exports the public of2d_engine_* entry
