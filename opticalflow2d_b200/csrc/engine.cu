@@ -202,7 +202,8 @@ int enqueue_fused_demons_kw(of2d_engine *E, const EngK<R> &K, const R *d_Iref, c
     const of2d_engine_desc &d = E->d;
     const R si = (R)d.sigma_i, sx = (R)d.sigma_x;
     const R sratio = (si * si) / (sx * sx);
-    const size_t sm1 = fused_smem_force<R, KW>(), sm2 = fused_smem_compose<R, KW>();
+    // fp32: the kernels hold their arrays in static shared memory
+    const size_t sm1 = sizeof(R) == 4 ? 0 : fused_smem_force<R, KW>(), sm2 = sizeof(R) == 4 ? 0 : fused_smem_compose<R, KW>();
     const int mode = fused_demons_mode(), nf = fused_nofast();
     const R sxsq = sx * sx;
     int ex = 0;

@@ -22,6 +22,9 @@
 
 namespace {
 
+#ifndef OF2D_FUSED_MINB
+#define OF2D_FUSED_MINB 4   // resident CTAs per SM the register allocation of the fp32 kernels aims at
+#endif
 constexpr int FW = 48;   // side of the staged source window
 constexpr int FO = 8;    // the tile starts at (FO, FO) of the window: origin (i0 - 8, j0 - 8) keeps every row 32-byte aligned
 
@@ -81,10 +84,15 @@ struct TapBox {
 };
 
 // Image::warp2d for pixel (x, y) (Image.cpp:144-173), every other case than "four taps inside the window": taps from global
-// memory, the reference's renormalisation on the last row / column, the kept value outside the image
+// memory, the reference's renormalisation on the last row / column, the kept value outside the image.  Recomputes the sampling
+// position from (x, y, u), so the hot path keeps nothing alive for it.
 template <class R>
-__device__ __noinline__ R warp_slow(const R *__restrict__ src, int nx, int ny, int dx, int dy, R fx, R fy, long lin_self) {
-    if (dx < 0 || dx >= nx || dy < 0 || dy >= ny) return src[lin_self];
+__device__ __noinline__ R warp_slow(const R *__restrict__ src, int nx, int ny, int x, int y, R ux, R uy) {
+    const R px = (R)x + ux, flx = r_floor(px), py = (R)y + uy, fly = r_floor(py);
+    const int dx = (int)flx, dy = (int)fly;
+    const R fx = px - flx, fy = py - fly;
+    const long self = (long)y * nx + x;
+    if (dx < 0 || dx >= nx || dy < 0 || dy >= ny) return src[self];
     const long o = (long)dy * nx + dx;
     if (dx < nx - 1 && dy < ny - 1) {
         const R s00 = src[o], s10 = src[o + 1], s01 = src[o + nx], s11 = src[o + nx + 1];
@@ -95,29 +103,34 @@ __device__ __noinline__ R warp_slow(const R *__restrict__ src, int nx, int ny, i
     R val = src[o] * (one - fx) * (one - fy), weight = (one - fx) * (one - fy);
     if (dx < nx - 1) { val += src[o + 1] * fx * (one - fy); weight += fx * (one - fy); }
     if (dy < ny - 1) { val += src[o + nx] * (one - fx) * fy; weight += (one - fx) * fy; }
-    return weight != 0 ? val / weight : src[lin_self];
+    return weight != 0 ? val / weight : src[self];
 }
-// straight-line hot path (taps from the staged window, weights sum to 1: no renormalisation); the rare rest goes to warp_slow
+// straight-line hot path (taps from the staged window, weights sum to 1: no renormalisation); the rare rest goes to warp_slow.
+// (xf, yf) = (float)(x, y); (ox, oy) = window origin; the tap box is passed as four scalars.
 template <class R>
-__device__ __forceinline__ R warp_windowed(const R *sI, const R *__restrict__ src, int nx, int ny, int wx0, int wy0, const TapBox &tb, int x, int y, vec2_t<R> u, long lin_self) {
-    const R px = (R)x + u.x, flx = r_floor(px), py = (R)y + u.y, fly = r_floor(py);
-    const int dx = (int)flx, dy = (int)fly;
+__device__ __forceinline__ R warp_windowed(const R *sI, const R *__restrict__ src, int nx, int ny, int ox, int oy, int lx0, unsigned lxn, int ly0, unsigned lyn,
+                                            int x, int y, R xf, R yf, vec2_t<R> u) {
+    const R px = xf + u.x, flx = r_floor(px), py = yf + u.y, fly = r_floor(py);
+    const int lx = (int)flx - ox, ly = (int)fly - oy;
     const R fx = px - flx, fy = py - fly;
-    const int lx = dx - wx0, ly = dy - wy0;
-    const bool ok = (unsigned)(lx - tb.lx0) < tb.lxn && (unsigned)(ly - tb.ly0) < tb.lyn;
+    const bool ok = (unsigned)(lx - lx0) < lxn && (unsigned)(ly - ly0) < lyn;
     const R *p = sI + (ok ? ly * FW + lx : 0);
     const R s00 = p[0], s10 = p[1], s01 = p[FW], s11 = p[FW + 1];
     const R lo = s00 + fx * (s10 - s00), hi = s01 + fx * (s11 - s01);
     R val = lo + fy * (hi - lo);
-    if (!ok) val = warp_slow<R>(src, nx, ny, dx, dy, fx, fy, lin_self);
+    if (!ok) val = warp_slow<R>(src, nx, ny, x, y, u.x, u.y);
     return val;
 }
 
 // Motion::accumulate for pixel (x, y) (Motion.cpp:137-169): v + u o (id + v); outside the image the pixel keeps u
 template <class R>
-__device__ __noinline__ vec2_t<R> compose_slow(const vec2_t<R> *__restrict__ u, int nx, int ny, int dx, int dy, R fx, R fy, vec2_t<R> v, long lin_self) {
+__device__ __noinline__ vec2_t<R> compose_slow(const vec2_t<R> *__restrict__ u, int nx, int ny, int x, int y, R vx_, R vy_) {
     using V = vec2_t<R>;
-    if (dx < 0 || dx >= nx || dy < 0 || dy >= ny) return u[lin_self];
+    const V v = mk2<R>(vx_, vy_);
+    const R px = (R)x + v.x, flx = r_floor(px), py = (R)y + v.y, fly = r_floor(py);
+    const int dx = (int)flx, dy = (int)fly;
+    const R fx = px - flx, fy = py - fly;
+    if (dx < 0 || dx >= nx || dy < 0 || dy >= ny) return u[(long)y * nx + x];
     const long o = (long)dy * nx + dx;
     if (dx < nx - 1 && dy < ny - 1) {
         const V s00 = u[o], s10 = u[o + 1], s01 = u[o + nx], s11 = u[o + nx + 1];
@@ -134,19 +147,19 @@ __device__ __noinline__ vec2_t<R> compose_slow(const vec2_t<R> *__restrict__ u, 
     return v;
 }
 template <class R>
-__device__ __forceinline__ vec2_t<R> compose_windowed(const vec2_t<R> *sU, const vec2_t<R> *__restrict__ u, int nx, int ny, int wx0, int wy0, const TapBox &tb, int x, int y, vec2_t<R> v, long lin_self) {
+__device__ __forceinline__ vec2_t<R> compose_windowed(const vec2_t<R> *sU, const vec2_t<R> *__restrict__ u, int nx, int ny, int ox, int oy, int lx0, unsigned lxn, int ly0, unsigned lyn,
+                                                      int x, int y, R xf, R yf, vec2_t<R> v) {
     using V = vec2_t<R>;
-    const R px = (R)x + v.x, flx = r_floor(px), py = (R)y + v.y, fly = r_floor(py);
-    const int dx = (int)flx, dy = (int)fly;
+    const R px = xf + v.x, flx = r_floor(px), py = yf + v.y, fly = r_floor(py);
+    const int lx = (int)flx - ox, ly = (int)fly - oy;
     const R fx = px - flx, fy = py - fly;
-    const int lx = dx - wx0, ly = dy - wy0;
-    const bool ok = (unsigned)(lx - tb.lx0) < tb.lxn && (unsigned)(ly - tb.ly0) < tb.lyn;
+    const bool ok = (unsigned)(lx - lx0) < lxn && (unsigned)(ly - ly0) < lyn;
     const V *p = sU + (ok ? ly * FW + lx : 0);
     const V s00 = p[0], s10 = p[1], s01 = p[FW], s11 = p[FW + 1];
     const R lx_ = s00.x + fx * (s10.x - s00.x), hx_ = s01.x + fx * (s11.x - s01.x);
     const R ly_ = s00.y + fx * (s10.y - s00.y), hy_ = s01.y + fx * (s11.y - s01.y);
     V o = mk2<R>(v.x + (lx_ + fy * (hx_ - lx_)), v.y + (ly_ + fy * (hy_ - ly_)));
-    if (!ok) o = compose_slow<R>(u, nx, ny, dx, dy, fx, fy, v, lin_self);
+    if (!ok) o = compose_slow<R>(u, nx, ny, x, y, v.x, v.y);
     return o;
 }
 
@@ -227,6 +240,15 @@ __device__ __forceinline__ void fused_conv(const vec2_t<R> *sC, const ConvW<R> &
     }
 }
 
+template <class R, int KW> constexpr size_t fused_smem_force() {
+    using G = FusedGeom<KW>;
+    return sizeof(R) * FW * FW + sizeof(vec2_t<R>) * G::CW * G::CP + sizeof(R) * G::WW * G::WP;
+}
+template <class R, int KW> constexpr size_t fused_smem_compose() {
+    using G = FusedGeom<KW>;
+    return sizeof(vec2_t<R>) * (FW * FW + G::CW * G::CP);
+}
+
 // Window elements -> threads.  A window of side TILE + 2 H is the 32 columns of the tile (H .. H + 31: thread column
 // threadIdx.x, rows threadIdx.y + 8 k, so a warp reads one aligned 32-element row segment and consecutive k differ by the
 // constant 8 nx) plus two side strips of H columns each (2 H (TILE + 2 H) elements, one per thread in a single extra pass).
@@ -265,10 +287,9 @@ struct ForceConvTile {
     }
     static __device__ __forceinline__ void warp_elem(R *sW, const R *sI, const R *__restrict__ Imov, int nx, int ny, int n, int i0, int j0, const TapBox &tb, int r, int cc, V uu) {
         int x = i0 - HW + cc, y = j0 - HW + r;
-        long lin = (long)y * nx + x;
         bool valid = true;
-        if (!FAST) valid = flat_pixel(i0 - HW + cc, j0 - HW + r, nx, n, x, y, lin);
-        sW[r * WP + cc] = valid ? warp_windowed<R>(sI, Imov, nx, ny, i0 - FO, j0 - FO, tb, x, y, uu, lin) : (R)0;
+        if (!FAST) { long lin; valid = flat_pixel(i0 - HW + cc, j0 - HW + r, nx, n, x, y, lin); }
+        sW[r * WP + cc] = valid ? warp_windowed<R>(sI, Imov, nx, ny, i0 - FO, j0 - FO, tb.lx0, tb.lxn, tb.ly0, tb.lyn, x, y, (R)x, (R)y, uu) : (R)0;
     }
     static __device__ __forceinline__ void force_elem(V *sC, const R *sW, int nx, int ny, int n, int i0, int j0, int r, int cc, R iref, R sratio, bool &divzero) {
         const R *w = sW + (r + 1) * WP + (cc + 1);
@@ -345,15 +366,21 @@ struct ForceConvTile {
 };
 
 template <class R, int EPI, int KW>
-__global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 4 : 2)
+__global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? OF2D_FUSED_MINB : 2)
 k_rx_force_conv(EngK<R> K, const R *__restrict__ Iref_all, const R *__restrict__ Imov_all, R sratio, const __grid_constant__ ConvW<R> W, int dst_buf, int nsq_cap, int nofast) {
     pdl_enter();
     using V = vec2_t<R>;
     using G = FusedGeom<KW>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    R *sI = reinterpret_cast<R *>(smem_raw);                              // [FW][FW]   source window (Imov)
-    V *sC = reinterpret_cast<V *>(sI + FW * FW);                          // [CW][CP]   unsmoothed correspondence
-    R *sW = reinterpret_cast<R *>(sC + G::CW * G::CP);                    // [WW][WP]   warped image
+    // fp32: static shared arrays (every address a compile-time constant); fp64 needs more than the 48 KiB static limit
+    constexpr bool STATIC = sizeof(R) == 4;
+    __shared__ __align__(128) R sI_static[STATIC ? FW * FW : 1];
+    __shared__ __align__(16) V sC_static[STATIC ? G::CW * G::CP : 1];
+    __shared__ __align__(16) R sW_static[STATIC ? G::WW * G::WP : 1];
+    extern __shared__ __align__(128) unsigned char smem_dynamic[];
+    R *sI, *sW;                                  // [FW][FW] source window (Imov); [WW][WP] warped image
+    V *sC;                                       // [CW][CP] unsmoothed correspondence
+    if constexpr (STATIC) { sI = sI_static; sC = sC_static; sW = sW_static; }
+    else { sI = reinterpret_cast<R *>(smem_dynamic); sC = reinterpret_cast<V *>(sI + FW * FW); sW = reinterpret_cast<R *>(sC + G::CW * G::CP); }
     __shared__ uint64_t bar;
     const int pair = blockIdx.y;
     PairCtl *c = K.ctl + pair;
@@ -422,7 +449,7 @@ struct ComposeConvTile {
     }
     static __device__ __forceinline__ void compose_elem(V *sS, const V *sU, const V *__restrict__ u, int nx, int ny, int n, int i0, int j0, const TapBox &tb, int r, int cc, V vv, int add_only) {
         int x = i0 - CX + cc, y = j0 - CX + r;
-        long lin = (long)y * nx + x;
+        long lin = 0;
         bool valid = true;
         if (!FAST) valid = flat_pixel(i0 - CX + cc, j0 - CX + r, nx, n, x, y, lin);
         V s = mk2<R>((R)0, (R)0);
@@ -430,7 +457,7 @@ struct ComposeConvTile {
             if (add_only) {
                 const V uc = FAST ? sU[(r - CX + FO) * FW + (cc - CX + FO)] : u[lin];
                 s = mk2<R>(uc.x + vv.x, uc.y + vv.y);
-            } else s = compose_windowed<R>(sU, u, nx, ny, i0 - FO, j0 - FO, tb, x, y, vv, lin);
+            } else s = compose_windowed<R>(sU, u, nx, ny, i0 - FO, j0 - FO, tb.lx0, tb.lxn, tb.ly0, tb.lyn, x, y, (R)x, (R)y, vv);
         }
         sS[r * CP + cc] = s;
     }
@@ -466,14 +493,19 @@ struct ComposeConvTile {
 };
 
 template <class R, int KW>
-__global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 4 : 2)
+__global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? OF2D_FUSED_MINB : 2)
 k_rx_compose_conv(EngK<R> K, int v_buf, int add_only, const __grid_constant__ ConvW<R> W, int nofast) {
     pdl_enter();
     using V = vec2_t<R>;
     using G = FusedGeom<KW>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    V *sU = reinterpret_cast<V *>(smem_raw);     // [FW][FW]   window of the current estimate
-    V *sS = sU + FW * FW;                        // [CW][CP]   composed, unsmoothed field
+    // fp32: static shared arrays (addresses are compile-time constants); fp64 needs more than the 48 KiB static limit
+    constexpr bool STATIC = sizeof(R) == 4;
+    __shared__ __align__(128) V sU_static[STATIC ? FW * FW : 1];
+    __shared__ __align__(16) V sS_static[STATIC ? G::CW * G::CP : 1];
+    extern __shared__ __align__(128) unsigned char smem_dynamic[];
+    V *sU, *sS;                                  // [FW][FW] window of the current estimate; [CW][CP] composed, unsmoothed field
+    if constexpr (STATIC) { sU = sU_static; sS = sS_static; }
+    else { sU = reinterpret_cast<V *>(smem_dynamic); sS = sU + FW * FW; }
     __shared__ uint64_t bar;
     const int pair = blockIdx.y;
     PairCtl *c = K.ctl + pair;
@@ -497,15 +529,6 @@ k_rx_compose_conv(EngK<R> K, int v_buf, int add_only, const __grid_constant__ Co
         else ComposeConvTile<R, KW, false>::run(sU, sS, &bar, uses, SC_, u, v, out, nx, ny, n, i0, j0, add_only, W, acc);
     }
     logger_epilogue<R>(K, c, pair, acc.dsd, acc.dsp);
-}
-
-template <class R, int KW> constexpr size_t fused_smem_force() {
-    using G = FusedGeom<KW>;
-    return sizeof(R) * FW * FW + sizeof(vec2_t<R>) * G::CW * G::CP + sizeof(R) * G::WW * G::WP;
-}
-template <class R, int KW> constexpr size_t fused_smem_compose() {
-    using G = FusedGeom<KW>;
-    return sizeof(vec2_t<R>) * (FW * FW + G::CW * G::CP);
 }
 
 }  // namespace
