@@ -205,8 +205,10 @@ int of2d_dct2d_f64(of2d_ctx *ctx, int n0, int n1, int kind, double *d_data);
  * motion <- estimate + motion o (id + estimate).
  *   ImageRegistrationOpticalFlow.cpp:97-151, ImageRegistrationDemons.cpp:86-137, ImageRegistrationFluid.cpp:67-142.
  * Decisions (break, time step, regrid, number of squarings) are taken by device-side reductions; the host
- * only polls a counter of running pairs.  Arithmetic is the fast mode (FMA in the convolution; Elastic /
- * Fluid sweep as overlapped tiles, see csrc/sor_tile.cuh); the per-step entry points above stay bit-exact. */
+ * only polls a counter of running pairs.  The engine exists in two builds, picked from the context's arithmetic level
+ * when the engine is created (of2d_ctx_set_fast_math): level 1 "exact" = the reference's unfused arithmetic (Elastic /
+ * Fluid sweep as overlapped tiles, csrc/sor_tile.cuh), level 2 "relaxed" = FMA contraction, approximate division and
+ * equivalent shortcuts (csrc/engine_relaxed.cu); the per-step entry points above are bit-exact at every level. */
 typedef struct of2d_engine of2d_engine;
 typedef struct {
     int method;                 /* enum Regularisation, src/SolverOptions.h:4: 0 Diffusion .. 5 Fluid */

@@ -95,6 +95,8 @@ SOR = [
     (of.ELASTIC, [1.0, 0.25], [20]),
     (of.ELASTIC, [1.0, 0.0, 0.9], [10]),
     (of.ELASTIC, [0.5, 2.0, 0.5], [10]),
+    (of.ELASTIC, [0.37, 0.13], [12]),          # non-dyadic parameters: the tile coefficients must round like the reference's float expression
+    (of.FLUID, [0.37, 0.13], [12]),
     (of.FLUID, [0.1, 0.0], [30]),
     (of.FLUID, [0.2, 0.1, 0.8], [20]),
 ]
