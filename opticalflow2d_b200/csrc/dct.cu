@@ -436,7 +436,16 @@ __global__ void __launch_bounds__(FFT_THREADS) k_dct_lines(int nlines, int n, si
 
 #include "dct_fast.cuh"
 #include "dct_reg.cuh"     // namespace rg: double precision (the reference's)
+namespace {
+// bank swizzle for 8-byte elements (float2): a shared-memory wavefront is 16 of them, so the low FOUR index bits are XORed with the
+// folded higher bits (swz of dct_fast.cuh, made for 16-byte elements, spreads power-of-two strides over 8 slots only: 2-way conflicts)
+__device__ __forceinline__ int swz8(int i) {
+    const int x = i >> 4;
+    return i ^ ((x ^ (x >> 4) ^ (x >> 8)) & 15);
+}
+}  // namespace
 #define RG_NS rgf
+#define RG_SWZ swz8
 #define RG_C2 float2
 #define RG_S float
 #define RG_MK2 make_float2

@@ -15,7 +15,8 @@
 //     one shuffle turns register contents into complete pixel pairs and global loads / stores are full 16-byte accesses;
 //   * FMA is allowed inside the FFT (the reference's fftw has no defined operation order to reproduce); the
 //     reference's own expressions (force, rhs, 1/(4N), eigenvalue) keep their order and stay unfused.
-// Shared-memory indices go through the XOR swizzle of dct_fast.cuh (conflict-free for every power-of-two stride).
+// Shared-memory indices go through an XOR swizzle (RG_SWZ: dct_fast.cuh's swz for 16-byte elements, swz8 below for 8-byte ones),
+// conflict-free for every power-of-two stride.
 //
 // The file is included TWICE by dct.cu: namespace rg (RG_S = double: the reference's precision, used by the strict path, the exact
 // engine and fp64 fields) and namespace rgf (RG_S = float: the relaxed engine on fp32 fields -- transform, twiddles and the
@@ -26,6 +27,7 @@
 #define RG_S double
 #define RG_MK2 make_double2
 #define RG_MINB 2
+#define RG_SWZ swz
 #endif
 
 namespace {
@@ -124,7 +126,7 @@ struct Tw16 { const RG_C2 *a, *b; };   // [4][S1] for super-pass 1 (w_N), [4][S2
 
 // ---- forward (DIF): registers -> ... -> shared memory, digit-reversed --------------------------------------------
 // in: a[j] = v[k + S1 j] (natural order); the threads of a line hold k1 = a permutation of 0 .. S1-1 and u = 0 .. S1-1.
-// out: X_k at xl[swz(pos(k))], after the trailing barrier.
+// out: X_k at xl[RG_SWZ(pos(k))], after the trailing barrier.
 template <int L> __device__ __forceinline__ void fft_fwd(RG_C2 (&a)[16], RG_C2 *xl, int u, int k1, Tw16 T) {
     using G = Geo<L>;
     {
@@ -132,64 +134,64 @@ template <int L> __device__ __forceinline__ void fft_fwd(RG_C2 (&a)[16], RG_C2 *
         dft<16, -1, 0>(a);
         twiddle16<true, false>(a, T.a[k], T.a[G::S1 + k], T.a[2 * G::S1 + k], T.a[3 * G::S1 + k]);
 #pragma unroll
-        for (int s = 0; s < 16; s++) xl[swz(k + G::S1 * slot_q(16, s))] = a[s];
+        for (int s = 0; s < 16; s++) xl[RG_SWZ(k + G::S1 * slot_q(16, s))] = a[s];
     }
     __syncthreads();
     {
         const int b = u / G::S2, k = u % G::S2, base = b * G::S1 + k;
 #pragma unroll
-        for (int j = 0; j < 16; j++) a[j] = xl[swz(base + G::S2 * j)];
+        for (int j = 0; j < 16; j++) a[j] = xl[RG_SWZ(base + G::S2 * j)];
         dft<16, -1, 0>(a);
         twiddle16<true, false>(a, T.b[k], T.b[G::S2 + k], T.b[2 * G::S2 + k], T.b[3 * G::S2 + k]);
 #pragma unroll
-        for (int s = 0; s < 16; s++) xl[swz(base + G::S2 * slot_q(16, s))] = a[s];
+        for (int s = 0; s < 16; s++) xl[RG_SWZ(base + G::S2 * slot_q(16, s))] = a[s];
     }
     __syncthreads();
     {
 #pragma unroll
-        for (int j = 0; j < 16; j++) a[j] = xl[swz(16 * u + j)];
+        for (int j = 0; j < 16; j++) a[j] = xl[RG_SWZ(16 * u + j)];
         if constexpr (G::M3 == 16) dft<16, -1, 0>(a);
         if constexpr (G::M3 == 8) { dft<8, -1, 0>(a); dft<8, -1, 8>(a); }
         if constexpr (G::M3 == 4) { dft<4, -1, 0>(a); dft<4, -1, 4>(a); dft<4, -1, 8>(a); dft<4, -1, 12>(a); }
         if constexpr (G::M3 == 2) { dft<2, -1, 0>(a); dft<2, -1, 2>(a); dft<2, -1, 4>(a); dft<2, -1, 6>(a); dft<2, -1, 8>(a); dft<2, -1, 10>(a); dft<2, -1, 12>(a); dft<2, -1, 14>(a); }
 #pragma unroll
-        for (int s = 0; s < 16; s++) xl[swz(16 * u + (s & ~(G::M3 - 1)) + slot_q(G::M3, s & (G::M3 - 1)))] = a[s];
+        for (int s = 0; s < 16; s++) xl[RG_SWZ(16 * u + (s & ~(G::M3 - 1)) + slot_q(G::M3, s & (G::M3 - 1)))] = a[s];
     }
     __syncthreads();
 }
 
 // ---- inverse (DIT, unnormalised): shared memory, digit-reversed -> ... -> registers -------------------------------
-// in: h_k at xl[swz(pos(k))] (caller has synchronised).  out: a[s] = t[k1 + S1 q], q = slot_q(16, s).
+// in: h_k at xl[RG_SWZ(pos(k))] (caller has synchronised).  out: a[s] = t[k1 + S1 q], q = slot_q(16, s).
 // `before_last_barrier` runs while a[] is dead (prefetches of the epilogue go there).
 struct NoHook { __device__ __forceinline__ void operator()() const {} };
 template <int L, class Hook = NoHook> __device__ __forceinline__ void fft_inv(RG_C2 (&a)[16], RG_C2 *xl, int u, int k1, Tw16 T, Hook before_last_barrier = Hook()) {
     using G = Geo<L>;
     {
 #pragma unroll
-        for (int j = 0; j < 16; j++) a[j] = xl[swz(16 * u + j)];
+        for (int j = 0; j < 16; j++) a[j] = xl[RG_SWZ(16 * u + j)];
         if constexpr (G::M3 == 16) dft<16, +1, 0>(a);
         if constexpr (G::M3 == 8) { dft<8, +1, 0>(a); dft<8, +1, 8>(a); }
         if constexpr (G::M3 == 4) { dft<4, +1, 0>(a); dft<4, +1, 4>(a); dft<4, +1, 8>(a); dft<4, +1, 12>(a); }
         if constexpr (G::M3 == 2) { dft<2, +1, 0>(a); dft<2, +1, 2>(a); dft<2, +1, 4>(a); dft<2, +1, 6>(a); dft<2, +1, 8>(a); dft<2, +1, 10>(a); dft<2, +1, 12>(a); dft<2, +1, 14>(a); }
 #pragma unroll
-        for (int s = 0; s < 16; s++) xl[swz(16 * u + (s & ~(G::M3 - 1)) + slot_q(G::M3, s & (G::M3 - 1)))] = a[s];
+        for (int s = 0; s < 16; s++) xl[RG_SWZ(16 * u + (s & ~(G::M3 - 1)) + slot_q(G::M3, s & (G::M3 - 1)))] = a[s];
     }
     __syncthreads();
     {
         const int b = u / G::S2, k = u % G::S2, base = b * G::S1 + k;
 #pragma unroll
-        for (int j = 0; j < 16; j++) a[j] = xl[swz(base + G::S2 * j)];
+        for (int j = 0; j < 16; j++) a[j] = xl[RG_SWZ(base + G::S2 * j)];
         twiddle16<false, true>(a, T.b[k], T.b[G::S2 + k], T.b[2 * G::S2 + k], T.b[3 * G::S2 + k]);
         dft<16, +1, 0>(a);
 #pragma unroll
-        for (int s = 0; s < 16; s++) xl[swz(base + G::S2 * slot_q(16, s))] = a[s];
+        for (int s = 0; s < 16; s++) xl[RG_SWZ(base + G::S2 * slot_q(16, s))] = a[s];
     }
     before_last_barrier();
     __syncthreads();
     {
         const int k = k1;
 #pragma unroll
-        for (int j = 0; j < 16; j++) a[j] = xl[swz(k + G::S1 * j)];
+        for (int j = 0; j < 16; j++) a[j] = xl[RG_SWZ(k + G::S1 * j)];
         twiddle16<false, true>(a, T.a[k], T.a[G::S1 + k], T.a[2 * G::S1 + k], T.a[3 * G::S1 + k]);
         dft<16, +1, 0>(a);
     }
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
         const int ll = e % LPC, k = e / LPC, nk = (N - k) & (N - 1);
         const RG_C2 *base = x + ll * N;
         RG_C2 ok, on;
-        post_pair(base[swz(G::pos(k))], base[swz(G::pos(nk))], q[k], ok, on);
+        post_pair(base[RG_SWZ(G::pos(k))], base[RG_SWZ(G::pos(nk))], q[k], ok, on);
         specT[(size_t)k * ny + j0 + ll] = ok;
         if (nk != k) specT[(size_t)nk * ny + j0 + ll] = on;
     }
@@ -292,18 +294,18 @@ __global__ void __launch_bounds__(2 * Geo<L>::TPL, 2 * Geo<L>::TPL <= 256 ? RG_M
         a[j] = line[j < 8 ? 2 * m : 2 * (N - 1 - m) + 1];
     }
     fft_fwd<L>(a, xl, u, u, T);
-    const double cxp = cosx[p];
+    const RG_S cxp = (RG_S)cosx[p], ta = (RG_S)tau_alpha;   // (rgf: the eigenvalue in single precision as well)
 #pragma unroll 4
     for (int c = 0; c < 8; c++) {   // pairs (k, N-k), k = 1 .. N/2-1 (and the self pair k = 0: thread 0, c = 0)
         const int k = u + G::TPL * c, nk = (N - k) & (N - 1);
-        const int sk = swz(G::pos(k)), sn = swz(G::pos(nk));
+        const int sk = RG_SWZ(G::pos(k)), sn = RG_SWZ(G::pos(nk));
         const RG_C2 qk = q[k];
         RG_C2 ak, an;
         post_pair(xl[sk], xl[sn], qk, ak, an);
         // OpticalFlowCurvature.cpp:24, :135-136: 1 / (1 + tau alpha lap^2) for k and N-k, with one division for the two
-        const double lk = -4 + cxp + cosy[k], ln = -4 + cxp + cosy[nk];
-        const double dk = 1.0f + tau_alpha * (lk * lk), dn = 1.0f + tau_alpha * (ln * ln);
-        const double r = 1.0 / (dk * dn), ek = r * dn, en = r * dk;
+        const RG_S lk = -4 + cxp + (RG_S)cosy[k], ln = -4 + cxp + (RG_S)cosy[nk];
+        const RG_S dk = 1.0f + ta * (lk * lk), dn = 1.0f + ta * (ln * ln);
+        const RG_S r = (RG_S)1 / (dk * dn), ek = r * dn, en = r * dk;
         { const RG_S fk = (RG_S)ek, fn = (RG_S)en; ak.x *= fk; ak.y *= fk; an.x *= fn; an.y *= fn; }
         RG_C2 oj, on;
         pre_pair(ak, an, qk, oj, on);
@@ -316,12 +318,12 @@ __global__ void __launch_bounds__(2 * Geo<L>::TPL, 2 * Geo<L>::TPL <= 256 ? RG_M
     }
     if (u == 0) {                                 // self pair k = N/2
         constexpr int k = N >> 1;
-        const int sk = swz(G::pos(k));
+        const int sk = RG_SWZ(G::pos(k));
         const RG_C2 qk = q[k], z = xl[sk];
         RG_C2 ak, an;
         post_pair(z, z, qk, ak, an);
-        const double lk = -4 + cxp + cosy[k];
-        const double ek = 1.0f / (1.0f + tau_alpha * (lk * lk));
+        const RG_S lk = -4 + cxp + (RG_S)cosy[k];
+        const RG_S ek = 1.0f / (1.0f + ta * (lk * lk));
         { const RG_S fk = (RG_S)ek; ak.x *= fk; ak.y *= fk; }
         RG_C2 oj, on;
         pre_pair(ak, ak, qk, oj, on);
@@ -374,12 +376,12 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
                 a[2 * c + 1] = ln[N - j];
             }
         }
-        if (tid < 2 * LPC) {                                          // j = 0 (h_0 = X_0; pos(0) = 0 = swz(0)) and the self pair j = N/2
+        if (tid < 2 * LPC) {                                          // j = 0 (h_0 = X_0; pos(0) = 0 = RG_SWZ(0)) and the self pair j = N/2
             const int ll = tid % LPC, j = (tid / LPC) * (N >> 1);
             const RG_C2 Xj = specN[(size_t)(j0 + ll) * N + j];
             RG_C2 oj = Xj, on;
             if (j) pre_pair(Xj, Xj, q[j], oj, on);
-            x[ll * N + swz(G::pos(j))] = oj;
+            x[ll * N + RG_SWZ(G::pos(j))] = oj;
         }
 #pragma unroll
         for (int c = 0; c < 8; c++) {
@@ -387,8 +389,8 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
             if (e < items) {
                 RG_C2 oj, on;
                 pre_pair(a[2 * c], a[2 * c + 1], q[j], oj, on);
-                x[ll * N + swz(G::pos(j))] = oj;
-                x[ll * N + swz(G::pos(N - j))] = on;
+                x[ll * N + RG_SWZ(G::pos(j))] = oj;
+                x[ll * N + RG_SWZ(G::pos(N - j))] = on;
             }
         }
     }
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
             const int ll = e % LPC, kk = e / LPC, nk = (N - kk) & (N - 1);
             const RG_C2 *base = x + ll * N;
             RG_C2 ok, on;
-            post_pair(base[swz(G::pos(kk))], base[swz(G::pos(nk))], q[kk], ok, on);
+            post_pair(base[RG_SWZ(G::pos(kk))], base[RG_SWZ(G::pos(nk))], q[kk], ok, on);
             specT[(size_t)kk * ny + j0 + ll] = ok;
             if (nk != kk) specT[(size_t)nk * ny + j0 + ll] = on;
         }
@@ -489,3 +491,4 @@ struct Api {
 #undef RG_S
 #undef RG_MK2
 #undef RG_MINB
+#undef RG_SWZ
