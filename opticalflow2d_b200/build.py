@@ -74,7 +74,7 @@ def build_cuda(force=False, verbose=False) -> str:
         o = os.path.join(OBJDIR, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
         if force or _newer(o, [s] + hdrs + ([s.replace("_relaxed.cu", ".cu")] if s.endswith("_relaxed.cu") else [])):
-            jobs.append([nvcc] + NVCC_FLAGS + (RELAXED_FLAGS if s.endswith("_relaxed.cu") else EXACT_FLAGS) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            jobs.append([nvcc] + NVCC_FLAGS + (RELAXED_FLAGS if s.endswith("_relaxed.cu") else EXACT_FLAGS) + os.environ.get("OF2D_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
         list(ex.map(lambda c: _run(c, verbose), jobs))
     if jobs or force or _newer(out, objs):

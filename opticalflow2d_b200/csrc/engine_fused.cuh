@@ -22,8 +22,16 @@
 
 namespace {
 
+// resident CTAs per SM the register allocation of the fp32 kernels aims at.  Measured (Thirion / Diffeomorphic, 50 iterations at 2048^2):
+// 4 CTAs (64 registers): 6.78 / 7.35 ms; 3 CTAs (80 registers): 5.73 / 6.83 ms; 2 CTAs (118 registers): 7.03 / 8.15 ms
 #ifndef OF2D_FUSED_MINB
-#define OF2D_FUSED_MINB 4   // resident CTAs per SM the register allocation of the fp32 kernels aims at
+#define OF2D_FUSED_MINB 3
+#endif
+#ifndef OF2D_FUSED_MINB_K1
+#define OF2D_FUSED_MINB_K1 OF2D_FUSED_MINB
+#endif
+#ifndef OF2D_FUSED_MINB_K2
+#define OF2D_FUSED_MINB_K2 OF2D_FUSED_MINB
 #endif
 constexpr int FW = 48;   // side of the staged source window
 constexpr int FO = 8;    // the tile starts at (FO, FO) of the window: origin (i0 - 8, j0 - 8) keeps every row 32-byte aligned
@@ -366,7 +374,7 @@ struct ForceConvTile {
 };
 
 template <class R, int EPI, int KW>
-__global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? OF2D_FUSED_MINB : 2)
+__global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? OF2D_FUSED_MINB_K1 : 2)
 k_rx_force_conv(EngK<R> K, const R *__restrict__ Iref_all, const R *__restrict__ Imov_all, R sratio, const __grid_constant__ ConvW<R> W, int dst_buf, int nsq_cap, int nofast) {
     pdl_enter();
     using V = vec2_t<R>;
@@ -493,7 +501,7 @@ struct ComposeConvTile {
 };
 
 template <class R, int KW>
-__global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? OF2D_FUSED_MINB : 2)
+__global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? OF2D_FUSED_MINB_K2 : 2)
 k_rx_compose_conv(EngK<R> K, int v_buf, int add_only, const __grid_constant__ ConvW<R> W, int nofast) {
     pdl_enter();
     using V = vec2_t<R>;
