@@ -15,6 +15,12 @@
 
 namespace {
 
+#ifndef OF2D_HS_MINB
+#define OF2D_HS_MINB 3      // k_hs_pair, fp32: resident CTAs per SM the register allocation aims at
+#endif
+#ifndef OF2D_INTEG_MINB
+#define OF2D_INTEG_MINB 1   // k_fl_integrate (1: no register cap)
+#endif
 constexpr int TX = 32, TY = 8, PY = 4;
 constexpr int TILE = 32;
 
@@ -286,7 +292,7 @@ __device__ __forceinline__ vec2_t<R> hs_point(vec2_t<R> a, vec2_t<R> b, vec2_t<R
 }
 
 template <class R>
-__global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 3 : 2) k_hs_pair(EngK<R> K, const vec2_t<R> *__restrict__ gradI_all, const R *__restrict__ It_all, R alphasq) {
+__global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? OF2D_HS_MINB : 2) k_hs_pair(EngK<R> K, const vec2_t<R> *__restrict__ gradI_all, const R *__restrict__ It_all, R alphasq) {
     pdl_enter();
     constexpr int H0 = TILE + 4, H1 = TILE + 2, NRING = 4 * H1 - 4;
     __shared__ vec2_t<R> s0[H0 * H0];   // u^k on the 36 x 36 halo tile
@@ -1000,7 +1006,7 @@ __global__ void __launch_bounds__(TX *TY) k_e_derivatives(EngK<R> K, int gate, c
 // integrate u += dt R (OpticalFlowFluid.cpp:97-121) + Logger + Jacobian minimum of the new field
 // (Image.cpp:189-218, :96-104) + break / regrid decisions (ImageRegistrationFluid.cpp:99-124)
 template <class R>
-__global__ void __launch_bounds__(TX *TY) k_fl_integrate(EngK<R> K, const vec2_t<R> *__restrict__ incr_all) {
+__global__ void __launch_bounds__(TX *TY, OF2D_INTEG_MINB) k_fl_integrate(EngK<R> K, const vec2_t<R> *__restrict__ incr_all) {
     pdl_enter();
     const int pair = blockIdx.y;
     PairCtl *c = K.ctl + pair;
