@@ -42,6 +42,7 @@
 
 #include "engine_kernels.cuh"
 #include "engine_fused.cuh"
+#include "engine_fused_tma.cuh"
 #include "sor_tile.cuh"
 
 // =================================================================================================
@@ -75,6 +76,12 @@ struct Engine {
     uint64_t iterations_enqueued;
     const void *cur_Imov;
     int last_niter;
+#if OF2D_RELAXED
+    // tensor maps of the pipelined Demons kernels (engine_fused_tma.cuh; fp32 fields, kernel widths 3 and 5)
+    bool tma_ready;
+    CUtensorMap tm_est_win[2], tm_est_tile[2], tm_c_tile[2], tm_imov_win, tm_iref_tile;
+    const void *tm_iref_ptr;
+#endif
 };
 #define of2d_engine Engine
 
@@ -195,6 +202,12 @@ inline int fused_nofast() {
     if (v < 0) { const char *e = getenv("OF2D_FUSED_NOFAST"); v = e && atoi(e) != 0 ? 1 : 0; }
     return v;
 }
+// OF2D_FUSED_TMA: 3 (default) both fused kernels as tensor-map pipelines (engine_fused_tma.cuh), 1 / 2 only the first / second, 0 neither
+inline int fused_tma_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("OF2D_FUSED_TMA"); v = e ? (atoi(e) & 3) : 3; }
+    return v;
+}
 template <class R, int KW>
 int enqueue_fused_demons_kw(of2d_engine *E, const EngK<R> &K, const R *d_Iref, const ConvW<R> &Wf, const ConvW<R> &Wd) {
     cudaStream_t s = E->ctx->stream;
@@ -205,6 +218,16 @@ int enqueue_fused_demons_kw(of2d_engine *E, const EngK<R> &K, const R *d_Iref, c
     // fp32: the kernels hold their arrays in static shared memory
     const size_t sm1 = sizeof(R) == 4 ? 0 : fused_smem_force<R, KW>(), sm2 = sizeof(R) == 4 ? 0 : fused_smem_compose<R, KW>();
     const int mode = fused_demons_mode(), nf = fused_nofast();
+    // the pipelined instances (engine_fused_tma.cuh): fp32 fields whose layout meets TMA's alignment rules
+    bool tma_force = false, tma_compose = false;
+    if constexpr (sizeof(R) == 4) {
+        if (mode == 1 && !nf && fused_tma_enabled() && E->tma_ready) {
+            if (E->tm_iref_ptr != (const void *)d_Iref)
+                E->tm_iref_ptr = make_field_map(&E->tm_iref_tile, d_Iref, 4, d.dimx, d.dimy, d.batch, RT_TW, RtGeom<KW>::CW) ? (const void *)d_Iref : nullptr;
+            tma_force = E->tm_iref_ptr != nullptr && (fused_tma_enabled() & 1);
+            tma_compose = (fused_tma_enabled() & 2) != 0;
+        }
+    }
     const R sxsq = sx * sx;
     int ex = 0;
     const R inv_sxsq = (sxsq > 0 && frexp((double)sxsq, &ex) == 0.5 && ex > -100 && ex < 100) ? (R)ldexp(1.0, 1 - ex) : (R)0;
@@ -212,6 +235,20 @@ int enqueue_fused_demons_kw(of2d_engine *E, const EngK<R> &K, const R *d_Iref, c
         { ProfScope _ps(E->ctx, "demons_force"); pdl_launch(k_e_demons_force<R>, grid_tiles(E, k_e_demons_force<R>), b, 0, s, K, d_Iref, (const R *)E->aux, si * si, sxsq, inv_sxsq); }
         OF2D_LAUNCH_CHECK(E->ctx);
         if (d.method == 3) TRY((launch_conv<R, 0>(E, K, B_C0, B_C1, 0))); else TRY((launch_conv<R, 2>(E, K, B_C0, B_C1, 0)));
+    } else if (tma_force) {
+        if constexpr (sizeof(R) == 4) {
+            using RG = RtGeom<KW>;
+            TmaMaps4 MF;
+            MF.m[0] = E->tm_est_tile[0]; MF.m[1] = E->tm_est_tile[1]; MF.m[2] = E->tm_imov_win; MF.m[3] = E->tm_iref_tile;
+            if (d.method == 3) {
+                TRY(of2d_ensure_dynamic_smem((const void *)k_rt_force_conv<0, KW>, RG::F_SMEM));
+                { ProfScope _ps(E->ctx, "force_conv"); pdl_launch(k_rt_force_conv<0, KW>, grid_tiles(E, k_rt_force_conv<0, KW>, RG::F_SMEM), b, RG::F_SMEM, s, K, d_Iref, (const R *)E->aux, sratio, Wf, (int)B_C1, E->nsq_cap, MF); }
+            } else {
+                TRY(of2d_ensure_dynamic_smem((const void *)k_rt_force_conv<2, KW>, RG::F_SMEM));
+                { ProfScope _ps(E->ctx, "force_conv_maxabs"); pdl_launch(k_rt_force_conv<2, KW>, grid_tiles(E, k_rt_force_conv<2, KW>, RG::F_SMEM), b, RG::F_SMEM, s, K, d_Iref, (const R *)E->aux, sratio, Wf, (int)B_C1, E->nsq_cap, MF); }
+            }
+            OF2D_LAUNCH_CHECK(E->ctx);
+        }
     } else if (d.method == 3) {
         TRY(of2d_ensure_dynamic_smem((const void *)k_rx_force_conv<R, 0, KW>, sm1));
         { ProfScope _ps(E->ctx, "force_conv"); pdl_launch(k_rx_force_conv<R, 0, KW>, grid_tiles(E, k_rx_force_conv<R, 0, KW>, sm1), b, sm1, s, K, d_Iref, (const R *)E->aux, sratio, Wf, (int)B_C1, E->nsq_cap, nf); }
@@ -235,6 +272,17 @@ int enqueue_fused_demons_kw(of2d_engine *E, const EngK<R> &K, const R *d_Iref, c
             { ProfScope _pc(E->ctx, "compose"); pdl_launch(k_e_compose<R, false>, grid_tiles(E, k_e_compose<R, false>), b, 0, s, K, G_ACTIVE, B_EST_CUR, B_CRES, B_CTMP, 0); }
             OF2D_LAUNCH_CHECK(E->ctx);
             TRY((launch_conv<R, 1>(E, K, B_CTMP, B_EST_NEXT, 1)));
+        }
+        return OF2D_SUCCESS;
+    }
+    if (tma_compose) {
+        if constexpr (sizeof(R) == 4) {
+            using RG = RtGeom<KW>;
+            TmaMaps4 MC;
+            MC.m[0] = E->tm_est_win[0]; MC.m[1] = E->tm_est_win[1]; MC.m[2] = E->tm_c_tile[0]; MC.m[3] = E->tm_c_tile[1];
+            TRY(of2d_ensure_dynamic_smem((const void *)k_rt_compose_conv<KW>, RG::C_SMEM));
+            { ProfScope _pc(E->ctx, "compose_conv_logger"); pdl_launch(k_rt_compose_conv<KW>, grid_tiles(E, k_rt_compose_conv<KW>, RG::C_SMEM), b, RG::C_SMEM, s, K, d.method == 3 ? (int)B_C1 : (int)B_CRES, d.method == 3 && d.accumulation == 1 ? 1 : 0, Wd, MC); }
+            OF2D_LAUNCH_CHECK(E->ctx);
         }
         return OF2D_SUCCESS;
     }
@@ -544,6 +592,19 @@ int ENG(create)(of2d_ctx *ctx, const of2d_engine_desc *desc, of2d_engine_head **
             if (E->nsq_cap > 16) { of2d_set_error("engine: sigma_x / sigma_i too large for scaling and squaring"); return fail(OF2D_ERR_UNSUPPORTED); }
         }
     }
+#if OF2D_RELAXED
+    E->tma_ready = false;
+    E->tm_iref_ptr = nullptr;
+    if ((m == 3 || m == 4) && !E->dbl && (desc->kernel_w == 3 || desc->kernel_w == 5)) {
+        const int cx = (desc->kernel_w - 1) / 2, cw = TILE + 2 * cx, ww = cw + 2;
+        bool ok = true;
+        for (int k = 0; k < 2 && ok; k++)
+            ok = make_field_map(&E->tm_est_win[k], E->est[k], 8, nx, ny, B, FW, FW) && make_field_map(&E->tm_est_tile[k], E->est[k], 8, nx, ny, B, RT_TW, ww) &&
+                 make_field_map(&E->tm_c_tile[k], E->c[k], 8, nx, ny, B, RT_VP, cw);
+        ok = ok && make_field_map(&E->tm_imov_win, E->aux, 4, nx, ny, B, FW, FW);
+        E->tma_ready = ok;
+    }
+#endif
     if (m == 1) {
         if ((st = of2d_curvature_plan_create(ctx, nx, ny, desc->alpha, desc->tau, E->dbl ? 1 : 0, &E->plan))) return fail(st);
         if ((st = of2d_curvature_plan_set_batch(E->plan, B))) return fail(st);

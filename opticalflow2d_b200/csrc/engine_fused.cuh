@@ -174,11 +174,11 @@ __device__ __forceinline__ vec2_t<R> compose_windowed(const vec2_t<R> *sU, const
 // Gaussian smoothing of the field held in shared memory (tile + CX halo, flat addressing) for the thread's 4 vertically
 // adjacent pixels (column threadIdx.x, rows 4 threadIdx.y ..): separable taps where every tap of the window is inside the
 // array, the reference's dense loop with its renormalisation (Field.tpp:236-262) on the first / last CX rows of the field
-template <class R, int KW, class Emit>
-__device__ __forceinline__ void fused_conv(const vec2_t<R> *sC, const ConvW<R> &W, int i0, int j0, int nx, int ny, long n, bool fast, Emit emit) {
+template <class R, int KW, int CP, class Emit>
+__device__ __forceinline__ void fused_conv_p(const vec2_t<R> *sC, const ConvW<R> &W, int i0, int j0, int nx, int ny, long n, bool fast, Emit emit) {   // CP: row pitch of sC
     using V = vec2_t<R>;
     using G = FusedGeom<KW>;
-    constexpr int CX = G::CX, CP = G::CP, NRW = 4 + KW - 1;
+    constexpr int CX = G::CX, NRW = 4 + KW - 1;
     const int x = threadIdx.x, jl0 = 4 * threadIdx.y;
     // a tap's flat index leaves [0, n) for rows < CX and >= ny - CX, and on the first / last CX pixels of rows CX and ny - 1 - CX
     const bool dense = !fast && (j0 + jl0 <= CX || j0 + jl0 + 3 >= ny - 1 - CX);
@@ -246,6 +246,11 @@ __device__ __forceinline__ void fused_conv(const vec2_t<R> *sC, const ConvW<R> &
         else o = sC[(jl0 + q + CX) * CP + x + CX];
         emit(q, o);
     }
+}
+
+template <class R, int KW, class Emit>
+__device__ __forceinline__ void fused_conv(const vec2_t<R> *sC, const ConvW<R> &W, int i0, int j0, int nx, int ny, long n, bool fast, Emit emit) {
+    fused_conv_p<R, KW, FusedGeom<KW>::CP>(sC, W, i0, j0, nx, ny, n, fast, emit);
 }
 
 template <class R, int KW> constexpr size_t fused_smem_force() {
@@ -373,6 +378,33 @@ struct ForceConvTile {
     }
 };
 
+// Diffeomorphic: maxabs of the smoothed correspondence -> number of squarings of Motion::exp (Motion.cpp:253-260), decided by the last CTA
+template <class R>
+__device__ __forceinline__ void demons_nsquares_epilogue(const EngK<R> &K, PairCtl *c, int pair, R mx, int nsq_cap) {
+    const int tid = threadIdx.x + threadIdx.y * TX;
+    mx = block_extreme<R, true>(mx);
+    const double vals[1] = {(double)mx};
+    double *part = K.partials + (size_t)pair * K.pstride;
+    if (publish_partials<1>(vals, part, &c->ticket[1], gridDim.x, blockIdx.x)) {
+        double o1[1];
+        reduce_partials<1>(part, gridDim.x, o1, 1u, 0u);
+        if (tid == 0) {
+            const R ma = sizeof(R) == 4 ? (R)sqrtf((float)o1[0]) : (R)sqrt(o1[0]);
+            int nsq = 0;
+            if (ma != 0) {
+                nsq = sizeof(R) == 4 ? (int)ceilf(1 + log2f((float)ma)) : (int)ceil(1 + log2((double)ma));
+                if (nsq < 0) nsq = 0;
+            }
+            if (nsq > nsq_cap) { c->overflow = 1; nsq = nsq_cap; }
+            c->nsquares = nsq;
+            c->maxabs = (double)ma;
+            c->scale = (double)(R)pow(2.0, (double)-nsq);
+            const int it = c->iter;
+            if (it < K.tr.cap) { K.tr.nsq[(size_t)pair * K.tr.cap + it] = nsq; K.tr.maxabs[(size_t)pair * K.tr.cap + it] = (double)ma; }
+        }
+    }
+}
+
 template <class R, int EPI, int KW>
 __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? OF2D_FUSED_MINB_K1 : 2)
 k_rx_force_conv(EngK<R> K, const R *__restrict__ Iref_all, const R *__restrict__ Imov_all, R sratio, const __grid_constant__ ConvW<R> W, int dst_buf, int nsq_cap, int nofast) {
@@ -416,29 +448,7 @@ k_rx_force_conv(EngK<R> K, const R *__restrict__ Iref_all, const R *__restrict__
         else ForceConvTile<R, KW, false>::template run<EPI>(sI, sC, sW, &bar, uses, SW_, SC_, u, Iref, Imov, out, nx, ny, n, i0, j0, sratio, W, divzero, mx);
     }
     if (divzero) atomicOr(&c->flags, OF2D_FLAG_DIVZERO);
-    if (EPI == 2) {
-        mx = block_extreme<R, true>(mx);
-        const double vals[1] = {(double)mx};
-        double *part = K.partials + (size_t)pair * K.pstride;
-        if (publish_partials<1>(vals, part, &c->ticket[1], gridDim.x, blockIdx.x)) {
-            double o1[1];
-            reduce_partials<1>(part, gridDim.x, o1, 1u, 0u);
-            if (tid == 0) {   // Motion::exp, Motion.cpp:253-260
-                const R ma = sizeof(R) == 4 ? (R)sqrtf((float)o1[0]) : (R)sqrt(o1[0]);
-                int nsq = 0;
-                if (ma != 0) {
-                    nsq = sizeof(R) == 4 ? (int)ceilf(1 + log2f((float)ma)) : (int)ceil(1 + log2((double)ma));
-                    if (nsq < 0) nsq = 0;
-                }
-                if (nsq > nsq_cap) { c->overflow = 1; nsq = nsq_cap; }
-                c->nsquares = nsq;
-                c->maxabs = (double)ma;
-                c->scale = (double)(R)pow(2.0, (double)-nsq);
-                const int it = c->iter;
-                if (it < K.tr.cap) { K.tr.nsq[(size_t)pair * K.tr.cap + it] = nsq; K.tr.maxabs[(size_t)pair * K.tr.cap + it] = (double)ma; }
-            }
-        }
-    }
+    if (EPI == 2) demons_nsquares_epilogue<R>(K, c, pair, mx, nsq_cap);
 }
 
 // ---------------------------------------------------------------------------------------------
