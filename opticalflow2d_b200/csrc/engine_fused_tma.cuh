@@ -51,16 +51,51 @@ __device__ __forceinline__ bool rt_tile_fast(int i0, int j0, int nx, int ny) {
     return i0 >= FO && j0 >= FO && i0 - FO + FW <= nx && j0 - FO + FW <= ny;
 }
 
+// Window elements -> threads, balanced over the 8 warps: the 32 x 32 core of a (32 + 2H)^2 window goes as "column H + tx,
+// rows ty + 8k, k < 4" (aligned row segments, constant strides); the other elements (the rows under the core, then the two
+// side strips) are dealt out as q = tid + 256 m, so every warp handles 4 + NX / 256 elements (+-1).
+template <int H> struct Spread {
+    static constexpr int W = TILE + 2 * H;
+    static constexpr int NB = (W - TILE) * TILE;   // rows 32 .. W-1 of the core columns
+    static constexpr int NX = NB + 2 * H * W;      // + the side strips
+    static constexpr int NM = (NX + TX * TY - 1) / (TX * TY);
+    int rc[NM];                                     // (row << 8 | column) of the thread's m-th extra element, -1: none
+    __device__ __forceinline__ explicit Spread(int tid) {
+#pragma unroll
+        for (int m = 0; m < NM; m++) {
+            int q = tid + TX * TY * m;
+            if (q >= NX) rc[m] = -1;
+            else if (q < NB) rc[m] = ((TILE + (q >> 5)) << 8) | (H + (q & 31));
+            else { q -= NB; const int r = q / (2 * H), t = q - r * (2 * H); rc[m] = (r << 8) | (t < H ? t : t + TILE); }
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // compose + smoothing + Logger
 // ---------------------------------------------------------------------------------------------
+// elements whose taps left the staged window (correspondences of several pixels): Motion::accumulate from global memory
+template <int KW>
+__device__ __noinline__ void rt_compose_fixup(unsigned bad, float2 *sV, const float2 *__restrict__ u, int nx, int ny, int i0, int j0, const Spread<RtGeom<KW>::CX> X) {
+    constexpr int CX = RtGeom<KW>::CX;
+    for (int bit = 0; bad >> bit; bit++) {
+        if (!(bad >> bit & 1u)) continue;
+        int r = threadIdx.y + TY * bit, cc = CX + threadIdx.x;
+        if (bit >= 4) { r = X.rc[bit - 4 < Spread<CX>::NM ? bit - 4 : 0] >> 8; cc = X.rc[bit - 4 < Spread<CX>::NM ? bit - 4 : 0] & 255; }
+        float2 *pv = sV + r * RT_VP + cc;
+        const float2 v = *pv;
+        *pv = compose_slow<float>(u, nx, ny, i0 - CX + cc, j0 - CX + r, v.x, v.y);
+    }
+}
+
 template <int KW>
 struct RtComposeTile {
     using V = float2;
     using RG = RtGeom<KW>;
     static constexpr int CX = RG::CX, CW = RG::CW;
 
-    static __device__ __forceinline__ void elem(V *sV, const V *sU, const V *__restrict__ u, int nx, int ny, int i0, int j0, int r, int cc, float xf, float yf) {
+    // v + u o (id + v) with the four taps from the staged window; returns true (and leaves v in place) when a tap is outside
+    static __device__ __forceinline__ bool elem(V *sV, const V *sU, int i0, int j0, int r, int cc, float xf, float yf) {
         V *pv = sV + r * RT_VP + cc;
         const V v = *pv;
         const float px = xf + v.x, flx = floorf(px), py = yf + v.y, fly = floorf(py);
@@ -71,29 +106,35 @@ struct RtComposeTile {
         const V s00 = p[0], s10 = p[1], s01 = p[FW], s11 = p[FW + 1];
         const float lx_ = s00.x + fx * (s10.x - s00.x), hx_ = s01.x + fx * (s11.x - s01.x);
         const float ly_ = s00.y + fx * (s10.y - s00.y), hy_ = s01.y + fx * (s11.y - s01.y);
-        V o = make_float2(v.x + (lx_ + fy * (hx_ - lx_)), v.y + (ly_ + fy * (hy_ - ly_)));
-        if (!ok) o = compose_slow<float>(u, nx, ny, i0 - CX + cc, j0 - CX + r, v.x, v.y);
-        *pv = o;
+        if (ok) *pv = make_float2(v.x + (lx_ + fy * (hx_ - lx_)), v.y + (ly_ + fy * (hy_ - ly_)));
+        return !ok;
     }
     static __device__ __forceinline__ void elem_add(V *sV, const V *sU, int r, int cc) {
         V *pv = sV + r * RT_VP + cc;
         const V v = *pv, uc = sU[(r - CX + FO) * FW + (cc - CX + FO)];
         *pv = make_float2(uc.x + v.x, uc.y + v.y);
     }
-    static __device__ __forceinline__ void run(const V *sU, V *sVtile, const Strip<CX> &SC_, const V *__restrict__ u, V *__restrict__ out, int nx, int ny, int i0, int j0,
+    static __device__ __forceinline__ void run(const V *sU, V *sVtile, const Spread<CX> &X, const V *__restrict__ u, V *__restrict__ out, int nx, int ny, int i0, int j0,
                                                int add_only, const ConvW<float> &W, NormAcc<float> &acc) {
         const int tx = threadIdx.x, ty = threadIdx.y;
         V *sV = sVtile + RG::VOFF;   // element (r, cc) of the composed window at sV[r * RT_VP + cc]
-        constexpr int NC = Strip<CX>::NMAIN;
         if (add_only) {
 #pragma unroll
-            for (int k = 0; k < NC; k++) { const int r = ty + TY * k; if (r < CW) elem_add(sV, sU, r, CX + tx); }
-            if (SC_.sr >= 0) elem_add(sV, sU, SC_.sr, SC_.sc);
+            for (int k = 0; k < 4; k++) elem_add(sV, sU, ty + TY * k, CX + tx);
+#pragma unroll
+            for (int m = 0; m < Spread<CX>::NM; m++) if (X.rc[m] >= 0) elem_add(sV, sU, X.rc[m] >> 8, X.rc[m] & 255);
         } else {
             const float xf = (float)(i0 + tx), yf = (float)(j0 - CX + ty);
+            unsigned bad = 0u;
 #pragma unroll
-            for (int k = 0; k < NC; k++) { const int r = ty + TY * k; if (r < CW) elem(sV, sU, u, nx, ny, i0, j0, r, CX + tx, xf, yf + (float)(TY * k)); }
-            if (SC_.sr >= 0) elem(sV, sU, u, nx, ny, i0, j0, SC_.sr, SC_.sc, (float)(i0 - CX + SC_.sc), (float)(j0 - CX + SC_.sr));
+            for (int k = 0; k < 4; k++) bad |= elem(sV, sU, i0, j0, ty + TY * k, CX + tx, xf, yf + (float)(TY * k)) ? 1u << k : 0u;
+#pragma unroll
+            for (int m = 0; m < Spread<CX>::NM; m++)
+                if (X.rc[m] >= 0) {
+                    const int r = X.rc[m] >> 8, cc = X.rc[m] & 255;
+                    bad |= elem(sV, sU, i0, j0, r, cc, (float)(i0 - CX + cc), (float)(j0 - CX + r)) ? 1u << (4 + m) : 0u;
+                }
+            if (bad) rt_compose_fixup<KW>(bad, sV, u, nx, ny, i0, j0, X);
         }
         __syncthreads();
         const int i = i0 + tx, jb = j0 + 4 * ty;
@@ -131,6 +172,7 @@ k_rt_compose_conv(EngK<float> K, int v_buf, int add_only, const __grid_constant_
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init_fence(); }
     unsigned phase = 0u, uses = 0u;   // bit s of phase: parity the next wait on full[s] expects
     const Strip<G::CX> SC_(tid);
+    const Spread<G::CX> X(tid);
     const TileWalk T(nx, ny);
     NormAcc<float> acc;
     auto stage_u = [&](int s) { return reinterpret_cast<V *>(smem_dynamic + (unsigned)s * RG::C_STAGE); };
@@ -154,7 +196,7 @@ k_rt_compose_conv(EngK<float> K, int v_buf, int add_only, const __grid_constant_
         if (rt_tile_fast(i0, j0, nx, ny)) {
             mbar_wait(&bars[s], (phase >> s) & 1u);
             phase ^= 1u << s;
-            RtComposeTile<KW>::run(stage_u(s), stage_v(s), SC_, u, out, nx, ny, i0, j0, add_only, W, acc);
+            RtComposeTile<KW>::run(stage_u(s), stage_v(s), X, u, out, nx, ny, i0, j0, add_only, W, acc);
         } else {
             ComposeConvTile<float, KW, false>::run(stage_u(s), stage_v(s), &bars[2], uses, SC_, u, v, out, nx, ny, n, i0, j0, add_only, W, acc);
         }
@@ -166,13 +208,26 @@ k_rt_compose_conv(EngK<float> K, int v_buf, int add_only, const __grid_constant_
 // ---------------------------------------------------------------------------------------------
 // warp -> derivatives -> demons force -> smoothing (EPI 2: + maxabs -> number of squarings)
 // ---------------------------------------------------------------------------------------------
+// warped-image elements whose taps left the staged window (estimates of several pixels): Image::warp2d from global memory
+template <int KW>
+__device__ __noinline__ void rt_warp_fixup(unsigned bad, float *sW, const float2 *sUt, const float *__restrict__ Imov, int nx, int ny, int i0, int j0, const Spread<RtGeom<KW>::HW> X) {
+    constexpr int HW = RtGeom<KW>::HW, WP = RtGeom<KW>::WP;
+    for (int bit = 0; bad >> bit; bit++) {
+        if (!(bad >> bit & 1u)) continue;
+        int r = threadIdx.y + TY * bit, cc = HW + threadIdx.x;
+        if (bit >= 4) { r = X.rc[bit - 4 < Spread<HW>::NM ? bit - 4 : 0] >> 8; cc = X.rc[bit - 4 < Spread<HW>::NM ? bit - 4 : 0] & 255; }
+        const float2 uu = sUt[r * RT_TW + cc + (4 - HW)];
+        sW[r * WP + cc] = warp_slow<float>(Imov, nx, ny, i0 - HW + cc, j0 - HW + r, uu.x, uu.y);
+    }
+}
+
 template <int KW>
 struct RtForceTile {
     using V = float2;
     using RG = RtGeom<KW>;
     static constexpr int CX = RG::CX, HW = RG::HW, WW = RG::WW, WP = RG::WP, CW = RG::CW;
 
-    static __device__ __forceinline__ void warp_elem(float *sW, const float *sI, const V *sUt, const float *__restrict__ Imov, int nx, int ny, int i0, int j0, int r, int cc, float xf, float yf) {
+    static __device__ __forceinline__ bool warp_elem(float *sW, const float *sI, const V *sUt, int i0, int j0, int r, int cc, float xf, float yf) {
         const V uu = sUt[r * RT_TW + cc + (4 - HW)];
         const float px = xf + uu.x, flx = floorf(px), py = yf + uu.y, fly = floorf(py);
         const int lx = (int)flx - (i0 - FO), ly = (int)fly - (j0 - FO);
@@ -181,9 +236,8 @@ struct RtForceTile {
         const float *p = sI + (ok ? ly * FW + lx : 0);
         const float s00 = p[0], s10 = p[1], s01 = p[FW], s11 = p[FW + 1];
         const float lo = s00 + fx * (s10 - s00), hi = s01 + fx * (s11 - s01);
-        float val = lo + fy * (hi - lo);
-        if (!ok) val = warp_slow<float>(Imov, nx, ny, i0 - HW + cc, j0 - HW + r, uu.x, uu.y);
-        sW[r * WP + cc] = val;
+        sW[r * WP + cc] = lo + fy * (hi - lo);
+        return !ok;
     }
     static __device__ __forceinline__ void force_elem(V *sC, const float *sW, const float *sR, int r, int cc, float sratio, bool &divzero) {
         const float *w = sW + (r + 1) * WP + (cc + 1);
@@ -197,21 +251,28 @@ struct RtForceTile {
         sC[r * CW + cc] = cv;
     }
     template <int EPI>
-    static __device__ __forceinline__ void run(const float *sI, const V *sUt, const float *sR, float *sW, V *sC, const Strip<HW> &SW_, const Strip<CX> &SC_,
+    static __device__ __forceinline__ void run(const float *sI, const V *sUt, const float *sR, float *sW, V *sC, const Spread<HW> &XW, const Spread<CX> &XC,
                                                const float *__restrict__ Imov, V *__restrict__ out, int nx, int ny, int i0, int j0, float sratio, const ConvW<float> &W,
                                                bool &divzero, float &mx) {
         const int tx = threadIdx.x, ty = threadIdx.y;
-        constexpr int NW = Strip<HW>::NMAIN, NC = Strip<CX>::NMAIN;
         {
             const float xf = (float)(i0 + tx), yf = (float)(j0 - HW + ty);
+            unsigned bad = 0u;
 #pragma unroll
-            for (int k = 0; k < NW; k++) { const int r = ty + TY * k; if (r < WW) warp_elem(sW, sI, sUt, Imov, nx, ny, i0, j0, r, HW + tx, xf, yf + (float)(TY * k)); }
-            if (SW_.sr >= 0) warp_elem(sW, sI, sUt, Imov, nx, ny, i0, j0, SW_.sr, SW_.sc, (float)(i0 - HW + SW_.sc), (float)(j0 - HW + SW_.sr));
+            for (int k = 0; k < 4; k++) bad |= warp_elem(sW, sI, sUt, i0, j0, ty + TY * k, HW + tx, xf, yf + (float)(TY * k)) ? 1u << k : 0u;
+#pragma unroll
+            for (int m = 0; m < Spread<HW>::NM; m++)
+                if (XW.rc[m] >= 0) {
+                    const int r = XW.rc[m] >> 8, cc = XW.rc[m] & 255;
+                    bad |= warp_elem(sW, sI, sUt, i0, j0, r, cc, (float)(i0 - HW + cc), (float)(j0 - HW + r)) ? 1u << (4 + m) : 0u;
+                }
+            if (bad) rt_warp_fixup<KW>(bad, sW, sUt, Imov, nx, ny, i0, j0, XW);
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < NC; k++) { const int r = ty + TY * k; if (r < CW) force_elem(sC, sW, sR, r, CX + tx, sratio, divzero); }
-        if (SC_.sr >= 0) force_elem(sC, sW, sR, SC_.sr, SC_.sc, sratio, divzero);
+        for (int k = 0; k < 4; k++) force_elem(sC, sW, sR, ty + TY * k, CX + tx, sratio, divzero);
+#pragma unroll
+        for (int m = 0; m < Spread<CX>::NM; m++) if (XC.rc[m] >= 0) force_elem(sC, sW, sR, XC.rc[m] >> 8, XC.rc[m] & 255, sratio, divzero);
         __syncthreads();
         const int i = i0 + tx, jb = j0 + 4 * ty;
         V *op = out + (i + jb * nx);
@@ -247,6 +308,8 @@ k_rt_force_conv(EngK<float> K, const float *__restrict__ Iref_all, const float *
     unsigned phase = 0u, uses = 0u;
     const Strip<G::HW> SW_(tid);
     const Strip<G::CX> SC_(tid);
+    const Spread<G::HW> XW(tid);
+    const Spread<G::CX> XC(tid);
     const TileWalk T(nx, ny);
     bool divzero = false;
     float mx = 0.0f;
@@ -275,7 +338,7 @@ k_rt_force_conv(EngK<float> K, const float *__restrict__ Iref_all, const float *
         if (rt_tile_fast(i0, j0, nx, ny)) {
             mbar_wait(&bars[s], (phase >> s) & 1u);
             phase ^= 1u << s;
-            RtForceTile<KW>::template run<EPI>(stage_i(s), stage_u(s), stage_r(s), sW, sC, SW_, SC_, Imov, out, nx, ny, i0, j0, sratio, W, divzero, mx);
+            RtForceTile<KW>::template run<EPI>(stage_i(s), stage_u(s), stage_r(s), sW, sC, XW, XC, Imov, out, nx, ny, i0, j0, sratio, W, divzero, mx);
         } else {
             // the general instance of engine_fused.cuh: its own staging into stage s's window array
             ForceConvTile<float, KW, false>::template run<EPI>(stage_i(s), sC, sW, &bars[2], uses, SW_, SC_, u, Iref, Imov, out, nx, ny, n, i0, j0, sratio, W, divzero, mx);

@@ -87,7 +87,11 @@ __device__ __forceinline__ bool gate_open(const CtlHot &h, int gate) {
 
 // Motion::norm addend (Motion.cpp:45).  The reference takes the square root in double of float data;
 // the fp32 build of the engine takes it in float (1 ulp of a term that is then averaged over all pixels).
+#if OF2D_RELAXED   // subnormal squares (differences below 1e-19 px) are flushed to zero: no scaling fix-up around MUFU.SQRT
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
 __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#endif
 __device__ __forceinline__ float norm_term_f(float2 v) { return sqrt_approx(v.x * v.x + v.y * v.y); }
 __device__ __forceinline__ double norm_term(float2 v) { return (double)norm_term_f(v); }
 __device__ __forceinline__ double norm_term(double2 v) { return sqrt(v.x * v.x + v.y * v.y); }
