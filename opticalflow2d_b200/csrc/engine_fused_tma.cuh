@@ -19,6 +19,9 @@
 
 namespace {
 
+#ifndef OF2D_RT_MINB
+#define OF2D_RT_MINB 3   // resident CTAs per SM the register allocation aims at (4 = 64 registers: Thirion 4.86 -> 5.30 ms, measured)
+#endif
 struct TmaMaps4 { CUtensorMap m[4]; };
 
 // one tensor-map TMA load of a {bx, by, 1} box at (x, y, z); out-of-range elements arrive as zeros
@@ -149,14 +152,14 @@ struct RtComposeTile {
 };
 
 template <int KW>
-__global__ void __launch_bounds__(TX *TY, 3)
+__global__ void __launch_bounds__(TX *TY, OF2D_RT_MINB)
 k_rt_compose_conv(EngK<float> K, int v_buf, int add_only, const __grid_constant__ ConvW<float> W, const __grid_constant__ TmaMaps4 M) {
     pdl_enter();
     using V = float2;
     using RG = RtGeom<KW>;
     using G = FusedGeom<KW>;
     static_assert(G::CP == G::CW && G::CW <= RT_VP, "the general instance works on a dense [CW][CW] array inside the stage's [CW][RT_VP] tile");
-    extern __shared__ __align__(1024) unsigned char smem_dynamic[];
+    extern __shared__ __align__(128) unsigned char smem_dynamic[];
     __shared__ uint64_t bars[3];   // full[0], full[1], the general instance's own barrier
     const int pair = blockIdx.y;
     PairCtl *c = K.ctl + pair;
@@ -284,14 +287,14 @@ struct RtForceTile {
 };
 
 template <int EPI, int KW>
-__global__ void __launch_bounds__(TX *TY, 3)
+__global__ void __launch_bounds__(TX *TY, OF2D_RT_MINB)
 k_rt_force_conv(EngK<float> K, const float *__restrict__ Iref_all, const float *__restrict__ Imov_all, float sratio, const __grid_constant__ ConvW<float> W, int dst_buf, int nsq_cap,
                 const __grid_constant__ TmaMaps4 M) {
     pdl_enter();
     using V = float2;
     using RG = RtGeom<KW>;
     using G = FusedGeom<KW>;
-    extern __shared__ __align__(1024) unsigned char smem_dynamic[];
+    extern __shared__ __align__(128) unsigned char smem_dynamic[];
     __shared__ uint64_t bars[3];
     const int pair = blockIdx.y;
     PairCtl *c = K.ctl + pair;
