@@ -241,9 +241,10 @@ except (OSError, ValueError):
 
 BATCH_METHODS = ["thirion", "fluid"]
 BATCH_PX = 512
-# pairs resident in the engine at a time (measured, 1 GPU, resident / e2e pairs/s -- Thirion: 64: 1025 / 950, 128: 1039 / 961, 256: 1178 / 1076;
-# Fluid, whose pairs stop after different iteration counts so that a wave lasts as long as its slowest pair: 64: 1621 / 1525, 128: 1564 / 1440, 256: 1459 / 1310)
-BATCH_WAVE = {"thirion": 256, "fluid": 64}
+# pairs resident in the engine at a time (measured, 1 GPU, 512 pairs per call, resident / e2e pairs/s -- Thirion: 64: 1617 / 1418, 128: 1665 / 1499,
+# 148: 1670 / 1445, 222: 1498 / 1313, 256: 1159 / 1060 (a pair's CTAs times the wave must fill, not exceed, the 444 resident slots of the fused kernels);
+# Fluid, whose pairs stop after different iteration counts so that a wave lasts as long as its slowest pair: 32: 1493 / 1410, 64: 1404 / 1328, 128: 1382 / 1298)
+BATCH_WAVE = {"thirion": 128, "fluid": 32}
 if os.environ.get("OF2D_BENCH_WAVE"):
     BATCH_WAVE = {m: int(os.environ["OF2D_BENCH_WAVE"]) for m in BATCH_WAVE}
 BATCH_NITER = {"thirion": 100, "fluid": 60}   # Fluid: the cap at which all sampled pairs are pinned to 1e-3 px (tests/test_configs_gpu.py)

@@ -78,7 +78,7 @@ int of2d_host_kernel(int kind, int w, double sigma, double *out);               
 /* extension: `batch` independent pairs of one size registered together on this process's GPU (BASELINE.json
    configs[4]; one level, cold start per pair = what a fresh ImageRegistration* object with nscales = 0 computes).
    Iref / Imov: batch images back to back; planar_out: per pair the x plane then the y plane.
-   wave: pairs resident in the engine at a time (0 = default 256); the waves are balanced and a partial last wave is
+   wave: pairs resident in the engine at a time (0 = default 128); the waves are balanced and a partial last wave is
    padded internally, so any batch size works. */
 typedef struct of2d_batch of2d_batch;
 int of2d_batch_create(int dimx, int dimy, int batch, int niter, int nrefine, int reg, const double *regparams, int nparams, int wave, of2d_batch **out);

@@ -123,7 +123,11 @@ inline int ctas_per_sm(const void *kernel, size_t smem) {
 template <class KernelT>
 inline dim3 grid_tiles(const of2d_engine *E, KernelT kernel, size_t smem = 0) {
     const int ntiles = ceil_div(E->d.dimx, TILE) * ceil_div(E->d.dimy, TILE);
-    int per_pair = ceil_div((long)E->ctx->sm_count * ctas_per_sm((const void *)kernel, smem), E->d.batch);
+    // batches: the CTAs of all pairs together must not exceed the resident slots (a second, partly filled wave would double the time)
+    static int use_ceil = -1;
+    if (use_ceil < 0) { const char *e = getenv("OF2D_GRID_CEIL"); use_ceil = e && atoi(e) != 0 ? 1 : 0; }
+    const long slots = (long)E->ctx->sm_count * ctas_per_sm((const void *)kernel, smem);
+    int per_pair = use_ceil ? ceil_div(slots, E->d.batch) : (int)(slots / E->d.batch);
     if (per_pair > ntiles) per_pair = ntiles;
     if (per_pair < 1) per_pair = 1;
     return dim3(per_pair, E->d.batch);

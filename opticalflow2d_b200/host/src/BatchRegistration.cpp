@@ -33,7 +33,7 @@ BatchRegistration::BatchRegistration(const dim dimin, const int batch_, const in
     } else {
         if (wave <= 0) {
             const char* e = std::getenv("OF2D_BATCH_WAVE");
-            wave = e && std::atoi(e) > 0 ? std::atoi(e) : 256;
+            wave = e && std::atoi(e) > 0 ? std::atoi(e) : 128;
         }
         if (wave > batch) wave = batch;
         nwaves = (batch + wave - 1) / wave;
