@@ -65,6 +65,10 @@ int of2d_session_reset(of2d_session *s);
 int of2d_session_get_motion(of2d_session *s, double *planar_out);      /* 2*N doubles: x plane, y plane */
 int of2d_session_get_motion_aos(of2d_session *s, void *out_real);       /* N {x,y} pairs in the field precision */
 int of2d_session_warp(of2d_session *s, const double *img, double *out);
+/* extension: of2d_session_set_images + of2d_session_estimate + of2d_session_get_motion of n distinct sessions in one call,
+   job k+1's host -> device copies and job k-1's device -> host copy running under job k's solve (three streams; pinned host
+   buffers make the copies asynchronous, pageable ones still work).  Same results as the separate calls. */
+int of2d_sessions_register(of2d_session *const *sessions, int n, const double *const *Iref, const double *const *Imov, double *const *planar_out);
 
 /* the reference's public Image / Motion / Kernel methods that no driver calls, on host arrays:
    op 0: Image::sum / max / min -> scalars[0..2] (src/Image.cpp:78-104); op 1: Image::normalize -> out (:107-116);

@@ -261,6 +261,18 @@ class Session:
     def trace(self) -> dict:
         return _read_trace(self.lib, self.handle)
 
+    @staticmethod
+    def register_many_raw(sessions, Iref_ptrs, Imov_ptrs, out_ptrs):
+        """of2d_sessions_register: set_images + estimate + motion of several distinct sessions (same precision) in one call,
+        the copies of the neighbouring jobs under each solve.  Host pointers as in set_images_raw / motion_raw."""
+        n = len(sessions)
+        lib = sessions[0].lib
+        hs = (C.c_void_p * n)(*[s.handle for s in sessions])
+        a = (C.c_void_p * n)(*[C.c_void_p(p) for p in Iref_ptrs])
+        b = (C.c_void_p * n)(*[C.c_void_p(p) for p in Imov_ptrs])
+        o = (C.c_void_p * n)(*[C.c_void_p(p) for p in out_ptrs])
+        _check(lib, lib.of2d_sessions_register(hs, n, a, b, o))
+
     def close(self):
         if self.handle:
             self.lib.of2d_session_destroy(self.handle)

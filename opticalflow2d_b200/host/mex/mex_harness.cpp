@@ -206,6 +206,97 @@ int of2d_session_get_motion(of2d_session* s, double* planar_out) {
         m.copy_motion_to_input(planar_out);
     });
 }
+// ---- several registrations in one call, copies under the solves -------------------------------------------------------
+// set_images / estimate_motion / copy_estimated_motion of sessions[0 .. n-1] with three streams: `in` (host -> device copy and
+// double -> real cast of job k+1, pyramids included), the context's compute stream (job k), `out` (real -> planar double and
+// device -> host copy of job k-1).  Results are the ones the three separate calls give; the sessions must be distinct.
+namespace {
+struct SidePipes {
+    of2d_ctx* main = nullptr;
+    of2d_ctx* in = nullptr;
+    of2d_ctx* out = nullptr;
+    of2d::Buffer* s_in[2] = {nullptr, nullptr};
+    of2d::Buffer* s_out[2] = {nullptr, nullptr};
+    size_t cap = 0;   // pixels the staging buffers hold
+};
+thread_local SidePipes tl_pipes;
+
+void ensure_pipes(size_t npix) {
+    SidePipes& P = tl_pipes;
+    of2d_ctx* ctx = of2d::context();
+    if (P.main != ctx) {   // (contexts live as long as the process: a changed main context just gets new side streams)
+        P = SidePipes();
+        P.main = ctx;
+        of2d::check(of2d_ctx_create(of2d_ctx_device(ctx), &P.in));
+        of2d::check(of2d_ctx_create(of2d_ctx_device(ctx), &P.out));
+        of2d::check(of2d_ctx_make_current(ctx));
+    }
+    if (P.cap < npix) {
+        of2d::check(of2d_ctx_sync(P.in));
+        of2d::check(of2d_ctx_sync(P.out));
+        for (int k = 0; k < 2; k++) {
+            delete P.s_in[k]; delete P.s_out[k];
+            P.s_in[k] = new of2d::Buffer(sizeof(double) * 2 * npix);
+            P.s_out[k] = new of2d::Buffer(sizeof(double) * 2 * npix);
+        }
+        P.cap = npix;
+        of2d::check(of2d_ctx_sync(ctx));   // allocations and clears are ordered on the compute stream: visible to the copy streams from here on
+    }
+}
+}  // namespace
+
+int of2d_sessions_register(of2d_session* const* sessions, int n, const double* const* Iref, const double* const* Imov, double* const* planar_out) {
+    return guarded([&] {
+        if (n <= 0) return;
+        size_t cap = 0;
+        for (int k = 0; k < n; k++) {
+            if (!sessions[k] || !Iref[k] || !Imov[k] || !planar_out[k]) throw std::invalid_argument("of2d_sessions_register: null argument");
+            for (int q = 0; q < k; q++) if (sessions[q] == sessions[k]) throw std::invalid_argument("of2d_sessions_register: the sessions must be distinct");
+            const size_t np = (size_t)sessions[k]->grid.x * sessions[k]->grid.y;
+            cap = np > cap ? np : cap;
+        }
+        ensure_pipes(cap);
+        SidePipes& P = tl_pipes;
+        of2d_ctx* ctx = P.main;
+        auto npix = [&](int k) { return (size_t)sessions[k]->grid.x * sessions[k]->grid.y; };
+        auto upload = [&](int k) {   // `in` stream
+            const size_t np = npix(k);
+            double* st = (double*)P.s_in[k & 1]->device_discard();
+            ImageRegistration* reg = sessions[k]->reg.get();
+            of2d::check(of2d_h2d(P.in, st, Iref[k], sizeof(double) * np));
+            of2d::check(of2d_h2d(P.in, st + np, Imov[k], sizeof(double) * np));
+            of2d_real* dr = reg->reference_level0()->device_overwrite();
+            of2d_real* dm = reg->moving_level0()->device_overwrite();
+            of2d::check(sizeof(of2d_real) == 8 ? of2d_image_from_double_f64(P.in, np, st, (double*)dr) : of2d_image_from_double_f32(P.in, np, st, (float*)dr));
+            of2d::check(sizeof(of2d_real) == 8 ? of2d_image_from_double_f64(P.in, np, st + np, (double*)dm) : of2d_image_from_double_f32(P.in, np, st + np, (float*)dm));
+            of2d::set_thread_context(P.in);      // the coarser levels on the same stream
+            try { reg->rebuild_image_pyramids(); } catch (...) { of2d::set_thread_context(nullptr); of2d_ctx_make_current(ctx); throw; }
+            of2d::set_thread_context(nullptr);
+            of2d::check(of2d_ctx_make_current(ctx));
+        };
+        auto download = [&](int k) {   // `out` stream, after the compute stream has finished job k
+            const size_t np = npix(k);
+            double* st = (double*)P.s_out[k & 1]->device_discard();
+            const of2d_real* mo = reinterpret_cast<const of2d_real*>(sessions[k]->reg->get_estimated_motion()->device());
+            of2d::check(of2d_ctx_wait_for(P.out, ctx));
+            of2d::check(sizeof(of2d_real) == 8 ? of2d_motion_to_planar_double_f64(P.out, np, (const double*)mo, st) : of2d_motion_to_planar_double_f32(P.out, np, (const float*)mo, st));
+            of2d::check(of2d_d2h_async(P.out, planar_out[k], st, sizeof(double) * 2 * np));
+        };
+        struct Drain {   // the caller's buffers must not be in flight when the call returns, error or not
+            SidePipes& P;
+            ~Drain() { of2d_ctx_sync(P.in); of2d_ctx_sync(P.out); }
+        } drain{P};
+        upload(0);
+        for (int k = 0; k < n; k++) {
+            of2d::check(of2d_ctx_wait_for(ctx, P.in));   // job k's images are in place (job k+1's copies are enqueued after this point)
+            if (k + 1 < n) upload(k + 1);
+            if (k >= 1) download(k - 1);
+            sessions[k]->reg->estimate_motion();
+        }
+        download(n - 1);
+    });
+}
+
 int of2d_session_get_motion_aos(of2d_session* s, void* out_real) {
     return guarded([&] {
         const Motion* m = s->reg->get_estimated_motion();

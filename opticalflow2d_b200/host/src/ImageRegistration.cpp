@@ -110,6 +110,10 @@ void ImageRegistration::set_moving_image(const Image& im) {
     for (int s = nscales; s >= 1; s--) Imov[s]->downSample(*Imov[0]);
 }
 
+void ImageRegistration::rebuild_image_pyramids() {
+    for (int s = nscales; s >= 1; s--) { Iref[s]->downSample(*Iref[0]); Imov[s]->downSample(*Imov[0]); }
+}
+
 Motion* ImageRegistration::get_estimated_motion() const { return motion[0]; }
 void ImageRegistration::copy_estimated_motion(Motion& mo) const { mo = *motion[0]; }
 

@@ -51,6 +51,12 @@ public:
 
     const RegistrationTrace& get_trace() const { return trace; }
 
+    // extension (pipelined sessions, of2d_sessions_register): the finest-level images as device arrays, to be filled on a copy
+    // stream, and the coarser levels rebuilt from them (what set_reference_image / set_moving_image do after their copy)
+    Image* reference_level0() { return Iref[0]; }
+    Image* moving_level0() { return Imov[0]; }
+    void rebuild_image_pyramids();
+
 protected:
     void display_registration_parameters(const Regularisation reg, const of2d_real* regparams, const unsigned int nparams) const;
 

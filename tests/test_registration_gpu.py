@@ -120,3 +120,35 @@ def test_second_register_call_warm_starts_like_reference():
     finally:
         f.close()
     assert maxdiff(m1, m2) > 1e-4
+
+
+@pytest.mark.parametrize("bits", [32, 64])
+def test_sessions_register_equals_the_three_separate_calls(bits):
+    """of2d_sessions_register (include/of2d_host.h): set_images + estimate + get_motion of several sessions in one call with the
+    copies of the neighbouring jobs under each solve -- same motion, same traces as the separate calls, for different methods,
+    sizes and pyramid depths in one list."""
+    jobs = [((96, 64), [6], 0, of.DIFFUSION, [0.5]), ((128, 96), [5, 6], 1, of.THIRION, [1.0, 0.25, 1.5, 1.5, 5, 0]), ((96, 64), [8], 0, of.FLUID, [0.1, 0.0]),
+            ((64, 64), [4], 0, of.CURVATURE, [0.25, 1.0]), ((160, 96), [4, 4, 5], 2, of.ELASTIC, [1.0, 0.25])]
+    pairs = [S.make_pair(d[0], d[1], "lattice", shift=(1.0 + 0.2 * k, -0.5), smooth=True) for k, (d, *_r) in enumerate(jobs)]
+    want, want_it = [], []
+    for (dims, niter, nscales, reg, params), (R, T) in zip(jobs, pairs):
+        with of.Session(dims, niter, nscales, reg, params, bits=bits) as s:
+            s.set_images(R, T)
+            s.estimate()
+            want.append(s.motion()); want_it.append(s.trace()["total_iterations"])
+    sessions = [of.Session(dims, niter, nscales, reg, params, bits=bits) for dims, niter, nscales, reg, params in jobs]
+    try:
+        Rs = [np.ascontiguousarray(R, dtype=np.float64) for R, _ in pairs]
+        Ts = [np.ascontiguousarray(T, dtype=np.float64) for _, T in pairs]
+        outs = [np.zeros((2,) + R.shape) for R in Rs]
+        for rep in range(2):   # the second call reuses the staging buffers and the side streams
+            for s in sessions:
+                s.reset()
+            of.Session.register_many_raw(sessions, [a.ctypes.data for a in Rs], [a.ctypes.data for a in Ts], [o.ctypes.data for o in outs])
+            for k, s in enumerate(sessions):
+                got = np.stack([outs[k][0], outs[k][1]], axis=-1)
+                assert s.trace()["total_iterations"] == want_it[k]
+                assert np.array_equal(got, want[k]), (rep, k, float(np.abs(got - want[k]).max()))
+    finally:
+        for s in sessions:
+            s.close()
