@@ -43,6 +43,7 @@
 #include "engine_kernels.cuh"
 #include "engine_fused.cuh"
 #include "engine_fused_tma.cuh"
+#include "engine_fluid_tma.cuh"
 #include "sor_tile.cuh"
 
 // =================================================================================================
@@ -81,6 +82,8 @@ struct Engine {
     bool tma_ready;
     CUtensorMap tm_est_win[2], tm_est_tile[2], tm_c_tile[2], tm_imov_win, tm_iref_tile;
     const void *tm_iref_ptr;
+    bool tma_fluid;              // engine_fluid_tma.cuh: maps of the two estimate buffers and the increment (transposed layout)
+    CUtensorMap tm_fl[5];
 #endif
 };
 #define of2d_engine Engine
@@ -360,8 +363,23 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref, int cur
             TRY(sor_tile_launch<R>(E->ctx, E->sor, K.ctl, K.n_active, K.partials, K.pstride, K.tr, 1, (vec2_t<R> *)E->vel[0], (vec2_t<R> *)E->vel[1],
                                    (const vec2_t<R> *)E->est[0], (const vec2_t<R> *)E->est[1], (const vec2_t<R> *)E->gradI, (const R *)E->It, (vec2_t<R> *)E->incr));
             // (the increment of the new velocity and the time step are produced by the sweep kernel itself)
-            { ProfScope _ps(E->ctx, "fluid_integrate"); pdl_launch(k_fl_integrate<R>, grid_tiles(E, k_fl_integrate<R>), b, 0, s, K, (const vec2_t<R> *)E->incr); }
-            OF2D_LAUNCH_CHECK(E->ctx);
+            bool integ_done = false;
+#if OF2D_RELAXED
+            if constexpr (sizeof(R) == 4) {
+                if (E->tma_fluid && (fused_tma_enabled() & 1)) {
+                    TmaMaps5 MI;
+                    for (int q = 0; q < 5; q++) MI.m[q] = E->tm_fl[q];
+                    TRY(of2d_ensure_dynamic_smem((const void *)k_rt_fl_integrate, FI_SMEM));
+                    { ProfScope _ps(E->ctx, "fluid_integrate"); pdl_launch(k_rt_fl_integrate, grid_tiles(E, k_rt_fl_integrate, FI_SMEM), b, FI_SMEM, s, K, (const float2 *)E->incr, MI); }
+                    OF2D_LAUNCH_CHECK(E->ctx);
+                    integ_done = true;
+                }
+            }
+#endif
+            if (!integ_done) {
+                { ProfScope _ps(E->ctx, "fluid_integrate"); pdl_launch(k_fl_integrate<R>, grid_tiles(E, k_fl_integrate<R>), b, 0, s, K, (const vec2_t<R> *)E->incr); }
+                OF2D_LAUNCH_CHECK(E->ctx);
+            }
             // regrid (ImageRegistrationFluid.cpp:108-124): level <- est + level o (id + est); est <- 0; re-warp; derivatives
             { ProfScope _pc(E->ctx, "regrid_compose"); pdl_launch(k_e_compose<R, true>, grid_tiles(E, k_e_compose<R, true>), b, 0, s, K, G_REGRID, B_LVL_CUR, B_EST_CUR, B_LVL_NEXT, 0); }
             OF2D_LAUNCH_CHECK(E->ctx);
@@ -607,6 +625,14 @@ int ENG(create)(of2d_ctx *ctx, const of2d_engine_desc *desc, of2d_engine_head **
                  make_field_map(&E->tm_c_tile[k], E->c[k], 8, nx, ny, B, RT_VP, cw);
         ok = ok && make_field_map(&E->tm_imov_win, E->aux, 4, nx, ny, B, FW, FW);
         E->tma_ready = ok;
+    }
+    E->tma_fluid = false;
+    if (m == 5 && !E->dbl) {   // transposed layout: P elements per line, nx lines per pair, nT elements per pair
+        const void *bufs3[3] = {E->est[0], E->est[1], E->incr};
+        bool ok = (E->nT % 2) == 0 && (E->P % 2) == 0;
+        for (int k = 0; k < 3 && ok; k++) ok = make_field_map_pitched(&E->tm_fl[k], bufs3[k], 8, E->P, nx, (size_t)E->nT, B, FI_W, FI_H);
+        for (int k = 0; k < 2 && ok; k++) ok = make_field_map_pitched(&E->tm_fl[3 + k], E->est[k], 8, E->P, nx, (size_t)E->nT, B, TILE, TILE);
+        E->tma_fluid = ok;
     }
 #endif
     if (m == 1) {

@@ -369,19 +369,24 @@ inline of2d_encode_tiled_fn tensor_map_encoder() {
     }
     return fn;
 }
-// field of `batch` images of nx x ny elements of `esize` bytes (4: float, 8: float2), box {bx, by, 1}; false when the layout does not
-// meet TMA's alignment rules (base and strides multiples of 16 bytes) or the driver has no encoder
-inline bool make_field_map(CUtensorMap *m, const void *base, int esize, int nx, int ny, int batch, int bx, int by) {
+// `batch` images of `rows` lines of `line` elements of `esize` bytes (4: float, 8: float2), `img` elements from one image to the next,
+// box {bx, by, 1}; false when the layout does not meet TMA's alignment rules (base and strides multiples of 16 bytes) or the
+// driver has no encoder
+inline bool make_field_map_pitched(CUtensorMap *m, const void *base, int esize, int line, int rows, size_t img_elems, int batch, int bx, int by) {
     const of2d_encode_tiled_fn enc = tensor_map_encoder();
     if (!enc || !base) return false;
-    const size_t row = (size_t)nx * esize, img = row * ny;
-    if (((uintptr_t)base & 15u) || (row & 15u) || (img & 15u) || ((size_t)bx * esize & 15u) || bx > 256 || by > 256) return false;
-    const cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)batch};
+    const size_t row = (size_t)line * esize, img = img_elems * esize;
+    if (((uintptr_t)base & 15u) || (row & 15u) || (img & 15u) || ((size_t)bx * esize & 31u) || bx > 256 || by > 256) return false;   // (32-byte box rows: see RT_VP)
+    const cuuint64_t dims[3] = {(cuuint64_t)line, (cuuint64_t)rows, (cuuint64_t)batch};
     const cuuint64_t strides[2] = {(cuuint64_t)row, (cuuint64_t)img};
     const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     return enc(m, esize == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// field of `batch` images of nx x ny elements, image after image
+inline bool make_field_map(CUtensorMap *m, const void *base, int esize, int nx, int ny, int batch, int bx, int by) {
+    return make_field_map_pitched(m, base, esize, nx, ny, (size_t)nx * ny, batch, bx, by);
 }
 
 }  // namespace

@@ -1009,6 +1009,68 @@ __global__ void __launch_bounds__(TX *TY) k_e_derivatives(EngK<R> K, int gate, c
 
 // integrate u += dt R (OpticalFlowFluid.cpp:97-121) + Logger + Jacobian minimum of the new field
 // (Image.cpp:189-218, :96-104) + break / regrid decisions (ImageRegistrationFluid.cpp:99-124)
+// one tile of k_fl_integrate on the general path: any tile (image border, partial tiles, skipped integration), one-sided differences at the edges
+template <class R>
+__device__ __forceinline__ void fl_integrate_general_tile(const vec2_t<R> *__restrict__ u, vec2_t<R> *un, const vec2_t<R> *__restrict__ incr, int nx, int ny, int P, int i0, int j0,
+                                                          bool skip, bool prev_other, R dt, NormAcc<R> &acc, R &mj) {
+    auto unew_at = [&](size_t o) -> vec2_t<R> {
+        vec2_t<R> v = u[o];
+        if (!skip) { const vec2_t<R> r = incr[o]; v.x += r.x * dt; v.y += r.y * dt; }
+        return v;
+    };
+    const int j = j0 + threadIdx.x;
+    const int ib = i0 + threadIdx.y;
+    if (j >= ny) return;
+#pragma unroll
+    for (int p = 0; p < PY; p++) {
+        const int i = ib + p * TY;
+        if (i >= nx) continue;
+        const size_t o = (size_t)i * P + j;
+        const vec2_t<R> nv = unew_at(o);
+        const vec2_t<R> prev = prev_other ? un[o] : u[o];   // after a regrid Logger's prev is the pre-reset estimate
+        acc.add(nv, prev);
+        // Jacobian of the new field (one-sided at the edges, gradients.h:9-32)
+        vec2_t<R> dx, dy;
+        if (i == 0) { const vec2_t<R> a = unew_at(o + P); dx = mk2<R>(a.x - nv.x, a.y - nv.y); }
+        else if (i == nx - 1) { const vec2_t<R> b = unew_at(o - P); dx = mk2<R>(nv.x - b.x, nv.y - b.y); }
+        else { const vec2_t<R> a = unew_at(o + P), b = unew_at(o - P); dx = mk2<R>((a.x - b.x) / (R)2.0f, (a.y - b.y) / (R)2.0f); }
+        if (j == 0) { const vec2_t<R> a = unew_at(o + 1); dy = mk2<R>(a.x - nv.x, a.y - nv.y); }
+        else if (j == ny - 1) { const vec2_t<R> b = unew_at(o - 1); dy = mk2<R>(nv.x - b.x, nv.y - b.y); }
+        else { const vec2_t<R> a = unew_at(o + 1), b = unew_at(o - 1); dy = mk2<R>((a.x - b.x) / (R)2.0f, (a.y - b.y) / (R)2.0f); }
+        const R J = ((R)1.0f + dx.x) * ((R)1.0f + dy.y) - dx.y * dy.x;
+        mj = J < mj ? J : mj;
+        un[o] = nv;
+    }
+    acc.flush();
+}
+
+// Logger + break test + regrid decision of a Fluid iteration (ImageRegistrationFluid.cpp:99-124), taken by the last CTA
+template <class R>
+__device__ __forceinline__ void fl_integrate_epilogue(const EngK<R> &K, PairCtl *c, int pair, const NormAcc<R> &acc, R mj) {
+    double sd = acc.dsd, sp = acc.dsp;
+    block_sum2(sd, sp);
+    mj = block_extreme<R, false>(mj);
+    const double vals[3] = {sd, sp, (double)mj};
+    double *part = K.partials + (size_t)pair * K.pstride;
+    if (publish_partials<3>(vals, part, &c->ticket[0], gridDim.x, blockIdx.x)) {
+        double o3[3];
+        reduce_partials<3>(part, gridDim.x, o3, 0u, 4u);
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            const int it = c->iter;
+            c->sel ^= 1;
+            c->prev_other = 0;
+            finalize_logger<R>(c, K.tr, pair, o3[0], o3[1], (unsigned)K.n, K.n_active);
+            const bool brk = (R)c->err < (R)0.001f && it > 1;
+            const R minjac = (R)o3[2];
+            int rg = 0;
+            if (!brk && minjac < (R)0.5) rg = 1;
+            c->regrid = rg;
+            c->minjac = (double)minjac;
+            if (it < K.tr.cap) { K.tr.regrid[(size_t)pair * K.tr.cap + it] = rg; K.tr.minjac[(size_t)pair * K.tr.cap + it] = (double)minjac; }
+        }
+    }
+}
+
 template <class R>
 __global__ void __launch_bounds__(TX *TY, OF2D_INTEG_MINB) k_fl_integrate(EngK<R> K, const vec2_t<R> *__restrict__ incr_all) {
     pdl_enter();
@@ -1024,11 +1086,6 @@ __global__ void __launch_bounds__(TX *TY, OF2D_INTEG_MINB) k_fl_integrate(EngK<R
     const bool prev_other = h.prev_other != 0;
     const R dt = (R)__ldcg(&c->dt);
     __shared__ vec2_t<R> s_new[(TILE + 2) * (TILE + 2)], s_old[(TILE + 2) * (TILE + 2)];   // halo tile of an interior tile: new and old field
-    auto unew_at = [&](size_t o) -> vec2_t<R> {
-        vec2_t<R> v = u[o];
-        if (!skip) { const vec2_t<R> r = incr[o]; v.x += r.x * dt; v.y += r.y * dt; }
-        return v;
-    };
     const TileWalk T(ny, nx);
     NormAcc<R> acc;
     R mj = (R)INFINITY;
@@ -1086,53 +1143,9 @@ __global__ void __launch_bounds__(TX *TY, OF2D_INTEG_MINB) k_fl_integrate(EngK<R
             acc.flush();
             continue;
         }
-        const int j = j0 + threadIdx.x;
-        const int ib = i0 + threadIdx.y;
-        if (j >= ny) continue;
-#pragma unroll
-        for (int p = 0; p < PY; p++) {
-            const int i = ib + p * TY;
-            if (i >= nx) continue;
-            const size_t o = (size_t)i * P + j;
-            const vec2_t<R> nv = unew_at(o);
-            const vec2_t<R> prev = prev_other ? un[o] : u[o];   // after a regrid Logger's prev is the pre-reset estimate
-            acc.add(nv, prev);
-            // Jacobian of the new field (one-sided at the edges, gradients.h:9-32)
-            vec2_t<R> dx, dy;
-            if (i == 0) { const vec2_t<R> a = unew_at(o + P); dx = mk2<R>(a.x - nv.x, a.y - nv.y); }
-            else if (i == nx - 1) { const vec2_t<R> b = unew_at(o - P); dx = mk2<R>(nv.x - b.x, nv.y - b.y); }
-            else { const vec2_t<R> a = unew_at(o + P), b = unew_at(o - P); dx = mk2<R>((a.x - b.x) / (R)2.0f, (a.y - b.y) / (R)2.0f); }
-            if (j == 0) { const vec2_t<R> a = unew_at(o + 1); dy = mk2<R>(a.x - nv.x, a.y - nv.y); }
-            else if (j == ny - 1) { const vec2_t<R> b = unew_at(o - 1); dy = mk2<R>(nv.x - b.x, nv.y - b.y); }
-            else { const vec2_t<R> a = unew_at(o + 1), b = unew_at(o - 1); dy = mk2<R>((a.x - b.x) / (R)2.0f, (a.y - b.y) / (R)2.0f); }
-            const R J = ((R)1.0f + dx.x) * ((R)1.0f + dy.y) - dx.y * dy.x;
-            mj = J < mj ? J : mj;
-            un[o] = nv;
-        }
-        acc.flush();
+        fl_integrate_general_tile<R>(u, un, incr, nx, ny, P, i0, j0, skip, prev_other, dt, acc, mj);
     }
-    double sd = acc.dsd, sp = acc.dsp;
-    block_sum2(sd, sp);
-    mj = block_extreme<R, false>(mj);
-    const double vals[3] = {sd, sp, (double)mj};
-    double *part = K.partials + (size_t)pair * K.pstride;
-    if (publish_partials<3>(vals, part, &c->ticket[0], gridDim.x, blockIdx.x)) {
-        double o3[3];
-        reduce_partials<3>(part, gridDim.x, o3, 0u, 4u);
-        if (threadIdx.x == 0 && threadIdx.y == 0) {
-            const int it = c->iter;
-            c->sel ^= 1;
-            c->prev_other = 0;
-            finalize_logger<R>(c, K.tr, pair, o3[0], o3[1], (unsigned)K.n, K.n_active);
-            const bool brk = (R)c->err < (R)0.001f && it > 1;
-            const R minjac = (R)o3[2];
-            int rg = 0;
-            if (!brk && minjac < (R)0.5) rg = 1;
-            c->regrid = rg;
-            c->minjac = (double)minjac;
-            if (it < K.tr.cap) { K.tr.regrid[(size_t)pair * K.tr.cap + it] = rg; K.tr.minjac[(size_t)pair * K.tr.cap + it] = (double)minjac; }
-        }
-    }
+    fl_integrate_epilogue<R>(K, c, pair, acc, mj);
 }
 
 // Fluid regrid, second half (ImageRegistrationFluid.cpp:116-124): Iaux = Imov o (id + level motion), derivatives of
