@@ -514,6 +514,35 @@ __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? 4 : 1) k_e_compose(En
     }
 }
 
+// one pixel of a squaring step of Motion::exp (Motion.cpp:262-274): w + w o (id + w) at (i, j), w = sc * src (taps from global memory)
+template <class R>
+__device__ __forceinline__ vec2_t<R> square_pixel(const vec2_t<R> *__restrict__ src, int nx, int ny, int i, int j, R sc) {
+    const int idx = i + j * nx;
+    vec2_t<R> v = src[idx];
+    v.x *= sc; v.y *= sc;
+    const Bilin<R> b = bilin_setup<R>(i, j, v.x, v.y, nx, ny);
+    vec2_t<R> o = v;   // out of bounds: keeps the (scaled) value
+#if OF2D_RELAXED
+    if (b.inside && b.hx && b.hy) {   // all four taps inside: weights sum to 1; the power-of-two scale commutes with the interpolation
+        const vec2_t<R> s00 = src[b.idxO], s10 = src[b.idxO + 1], s01 = src[b.idxO + nx], s11 = src[b.idxO + nx + 1];
+        const R lx = s00.x + b.fx * (s10.x - s00.x), hx = s01.x + b.fx * (s11.x - s01.x);
+        const R ly = s00.y + b.fx * (s10.y - s00.y), hy = s01.y + b.fx * (s11.y - s01.y);
+        o = mk2<R>(v.x + sc * (lx + b.fy * (hx - lx)), v.y + sc * (ly + b.fy * (hy - ly)));
+    } else
+#endif
+    if (b.inside) {
+        const R one = (R)1;
+        vec2_t<R> t = src[b.idxO];
+        R vx = (t.x * sc) * (one - b.fx) * (one - b.fy), vy = (t.y * sc) * (one - b.fx) * (one - b.fy);
+        R weight = (one - b.fx) * (one - b.fy);
+        if (b.hx) { t = src[b.idxO + 1]; vx += (t.x * sc) * b.fx * (one - b.fy); vy += (t.y * sc) * b.fx * (one - b.fy); weight += b.fx * (one - b.fy); }
+        if (b.hy) { t = src[b.idxO + nx]; vx += (t.x * sc) * (one - b.fx) * b.fy; vy += (t.y * sc) * (one - b.fx) * b.fy; weight += (one - b.fx) * b.fy; }
+        if (b.hx && b.hy) { t = src[b.idxO + 1 + nx]; vx += (t.x * sc) * b.fx * b.fy; vy += (t.y * sc) * b.fx * b.fy; weight += b.fx * b.fy; }
+        if (weight != 0) o = mk2<R>(v.x + vx / weight, v.y + vy / weight);
+    }
+    return o;
+}
+
 // one squaring of Motion::exp (Motion.cpp:262-274): dst = w + w o (id + w), w = scale * src (scale only at s == 0;
 // a power of two, so scaling the taps on the fly is exact)
 template <class R>
@@ -538,28 +567,7 @@ __global__ void __launch_bounds__(TX *TY) k_e_square(EngK<R> K, int s) {
             const int j = jb + p * TY;
             if (j >= ny) continue;
             const int idx = i + j * nx;
-            vec2_t<R> v = src[idx];
-            v.x *= sc; v.y *= sc;
-            const Bilin<R> b = bilin_setup<R>(i, j, v.x, v.y, nx, ny);
-            vec2_t<R> o = v;   // out of bounds: keeps the (scaled) value
-#if OF2D_RELAXED
-            if (b.inside && b.hx && b.hy) {   // all four taps inside: weights sum to 1; the power-of-two scale commutes with the interpolation
-                const vec2_t<R> s00 = src[b.idxO], s10 = src[b.idxO + 1], s01 = src[b.idxO + nx], s11 = src[b.idxO + nx + 1];
-                const R lx = s00.x + b.fx * (s10.x - s00.x), hx = s01.x + b.fx * (s11.x - s01.x);
-                const R ly = s00.y + b.fx * (s10.y - s00.y), hy = s01.y + b.fx * (s11.y - s01.y);
-                o = mk2<R>(v.x + sc * (lx + b.fy * (hx - lx)), v.y + sc * (ly + b.fy * (hy - ly)));
-            } else
-#endif
-            if (b.inside) {
-                const R one = (R)1;
-                vec2_t<R> t = src[b.idxO];
-                R vx = (t.x * sc) * (one - b.fx) * (one - b.fy), vy = (t.y * sc) * (one - b.fx) * (one - b.fy);
-                R weight = (one - b.fx) * (one - b.fy);
-                if (b.hx) { t = src[b.idxO + 1]; vx += (t.x * sc) * b.fx * (one - b.fy); vy += (t.y * sc) * b.fx * (one - b.fy); weight += b.fx * (one - b.fy); }
-                if (b.hy) { t = src[b.idxO + nx]; vx += (t.x * sc) * (one - b.fx) * b.fy; vy += (t.y * sc) * (one - b.fx) * b.fy; weight += (one - b.fx) * b.fy; }
-                if (b.hx && b.hy) { t = src[b.idxO + 1 + nx]; vx += (t.x * sc) * b.fx * b.fy; vy += (t.y * sc) * b.fx * b.fy; weight += b.fx * b.fy; }
-                if (weight != 0) o = mk2<R>(v.x + vx / weight, v.y + vy / weight);
-            }
+            const vec2_t<R> o = square_pixel<R>(src, nx, ny, i, j, sc);
             dst[idx] = o;
         }
     }
