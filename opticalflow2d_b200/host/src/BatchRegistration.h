@@ -24,7 +24,7 @@
 class BatchRegistration {
 public:
     // regparams / nparams as for the single-pair classes (same validation); `wave`: pairs resident in the
-    // engine at a time (0 = default 256; balanced over the waves, a partial last wave is padded internally);
+    // engine at a time (0 = default 128; balanced over the waves, a partial last wave is padded internally);
     // `frames` > 1: cine chains (see above; batch must be a multiple of frames, wave = batch / frames)
     BatchRegistration(const dim dimin, const int batch, const int niter, const int nrefine, const Regularisation reg, const of2d_real* regparams,
                       const unsigned int nparams, const int wave = 0, const int frames = 1);

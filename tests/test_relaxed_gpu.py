@@ -149,3 +149,17 @@ def test_relaxed_divide_by_zero_is_reported_like_the_reference():
         with pytest.raises(of.OF2DError) as e:
             s.estimate()
         assert e.value.code == 3 and "Divide by zero" in e.value.msg
+
+
+@pytest.mark.parametrize("dimx,dimy", [(96, 64), (160, 100)])
+def test_relaxed_fluid_skips_the_step_when_the_time_step_is_too_large(dimx, dimy):
+    """OpticalFlowFluid.cpp:135-137: dt >= 65 leaves the estimate alone.  A shift of 0.3 px gives dt = 156, 80 (skipped) and 55
+    (integrated; the Logger then sees prev == 0 and the loop ends): the staged integrate kernel runs a skipped step with dt = 0."""
+    R, T = S.make_pair(dimx, dimy, "lattice", shift=(0.3, 0.0), smooth=True, sigma_b=6.0)
+    mr, tr, _ = run(32, "relaxed", (dimx, dimy), R, T, of.FLUID, [0.1, 0.0], [12])
+    want = oracle(32).register(R, T, of.FLUID, [0.1, 0.0], [12], nscales=0, nrefine=1, verbose=1)
+    dts = np.asarray(want["fluid_dt"])
+    assert (dts >= 65).any() and (dts < 65).any()
+    assert tr["total_iterations"] == len(want["err"])
+    assert np.allclose(series(tr, "fluid_dt"), dts, rtol=1e-4)
+    assert maxdiff(mr, want["motion"]) <= 1e-5
