@@ -338,10 +338,11 @@ struct ForceConvTile {
     template <int EPI>
     static __device__ __forceinline__ void run(R *sI, V *sC, R *sW, uint64_t *bar, unsigned &uses, const Strip<HW> &SW_, const Strip<CX> &SC_,
                                                const V *__restrict__ u, const R *__restrict__ Iref, const R *__restrict__ Imov, V *__restrict__ out,
-                                               int nx, int ny, int n, int i0, int j0, R sratio, const ConvW<R> &W, bool &divzero, R &mx) {
+                                               int nx, int ny, int n, int i0, int j0, R sratio, const ConvW<R> &W, bool &divzero, R &mx, const bool prestaged = false) {
         const int tid = threadIdx.x + threadIdx.y * TX;
         const int tx = threadIdx.x, ty = threadIdx.y;
-        const bool tma = stage_window<R>(sI, Imov, nx, (long)n, i0 - FO, j0 - FO, bar, tid);
+        // prestaged: the caller has filled sI with the window (zeros outside the field: no tap box reaches them) and waited for it
+        const bool tma = prestaged ? false : stage_window<R>(sI, Imov, nx, (long)n, i0 - FO, j0 - FO, bar, tid);
         // loads that do not depend on the window: u on the warped-image window, Iref on the correspondence window
         constexpr int NW = Strip<HW>::NMAIN, NC = Strip<CX>::NMAIN;
         const int baseW = (j0 - HW) * nx + (i0 - HW), baseC = (j0 - CX) * nx + (i0 - CX);
@@ -354,7 +355,7 @@ struct ForceConvTile {
         for (int k = 0; k < NC; k++) { const int r = min(ty + TY * k, CW - 1); ir[k] = load_s(Iref, nx, n, baseC, r, CX + tx); }
         if (SC_.sr >= 0) irside = load_s(Iref, nx, n, baseC, SC_.sr, SC_.sc);
         if (tma) { mbar_wait(bar, uses & 1u); uses++; }
-        else __syncthreads();
+        else if (!prestaged) __syncthreads();
         // ---- warped image on the tile + HW halo
         const TapBox tb(i0 - FO, j0 - FO, nx, ny);
 #pragma unroll
@@ -480,10 +481,11 @@ struct ComposeConvTile {
         sS[r * CP + cc] = s;
     }
     static __device__ __forceinline__ void run(V *sU, V *sS, uint64_t *bar, unsigned &uses, const Strip<CX> &SC_, const V *__restrict__ u, const V *__restrict__ v,
-                                               V *__restrict__ out, int nx, int ny, int n, int i0, int j0, int add_only, const ConvW<R> &W, NormAcc<R> &acc) {
+                                               V *__restrict__ out, int nx, int ny, int n, int i0, int j0, int add_only, const ConvW<R> &W, NormAcc<R> &acc,
+                                               const bool prestaged = false) {
         const int tid = threadIdx.x + threadIdx.y * TX;
         const int tx = threadIdx.x, ty = threadIdx.y;
-        const bool tma = stage_window<V>(sU, u, nx, (long)n, i0 - FO, j0 - FO, bar, tid);
+        const bool tma = prestaged ? false : stage_window<V>(sU, u, nx, (long)n, i0 - FO, j0 - FO, bar, tid);
         constexpr int NC = Strip<CX>::NMAIN;
         const int baseC = (j0 - CX) * nx + (i0 - CX);
         V vv[NC], vside = mk2<R>((R)0, (R)0);
@@ -491,7 +493,7 @@ struct ComposeConvTile {
         for (int k = 0; k < NC; k++) { const int r = min(ty + TY * k, CW - 1); vv[k] = load_v(v, nx, n, baseC, r, CX + tx); }
         if (SC_.sr >= 0) vside = load_v(v, nx, n, baseC, SC_.sr, SC_.sc);
         if (tma) { mbar_wait(bar, uses & 1u); uses++; }
-        else __syncthreads();
+        else if (!prestaged) __syncthreads();
         const TapBox tb(i0 - FO, j0 - FO, nx, ny);
 #pragma unroll
         for (int k = 0; k < NC; k++) { const int r = ty + TY * k; if (r < CW) compose_elem(sS, sU, u, nx, ny, n, i0, j0, tb, r, CX + tx, vv[k], add_only); }

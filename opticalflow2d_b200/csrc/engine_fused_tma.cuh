@@ -181,8 +181,7 @@ k_rt_compose_conv(EngK<float> K, int v_buf, int add_only, const __grid_constant_
     auto stage_u = [&](int s) { return reinterpret_cast<V *>(smem_dynamic + (unsigned)s * RG::C_STAGE); };
     auto stage_v = [&](int s) { return reinterpret_cast<V *>(smem_dynamic + (unsigned)s * RG::C_STAGE + RG::C_SU); };
     auto issue = [&](int tile, int s) {   // thread 0, after a barrier that ended every read of stage s
-        const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
-        if (!rt_tile_fast(i0, j0, nx, ny)) return;
+        const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;   // (border tiles too: the general instance takes the window from here)
         proxy_fence_async();
         mbar_expect_tx(&bars[s], RG::C_TX);
         tma_load_3d(stage_u(s), mu, i0 - FO, j0 - FO, pair, &bars[s]);
@@ -196,13 +195,10 @@ k_rt_compose_conv(EngK<float> K, int v_buf, int add_only, const __grid_constant_
         const int next = tile + gridDim.x;
         if (tid == 0 && next < T.ntiles) issue(next, s ^ 1);
         const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
-        if (rt_tile_fast(i0, j0, nx, ny)) {
-            mbar_wait(&bars[s], (phase >> s) & 1u);
-            phase ^= 1u << s;
-            RtComposeTile<KW>::run(stage_u(s), stage_v(s), X, u, out, nx, ny, i0, j0, add_only, W, acc);
-        } else {
-            ComposeConvTile<float, KW, false>::run(stage_u(s), stage_v(s), &bars[2], uses, SC_, u, v, out, nx, ny, n, i0, j0, add_only, W, acc);
-        }
+        mbar_wait(&bars[s], (phase >> s) & 1u);
+        phase ^= 1u << s;
+        if (rt_tile_fast(i0, j0, nx, ny)) RtComposeTile<KW>::run(stage_u(s), stage_v(s), X, u, out, nx, ny, i0, j0, add_only, W, acc);
+        else ComposeConvTile<float, KW, false>::run(stage_u(s), stage_v(s), &bars[2], uses, SC_, u, v, out, nx, ny, n, i0, j0, add_only, W, acc, true);
         __syncthreads();   // every read of stage s is over: the tile after the next may land there
     }
     logger_epilogue<float>(K, c, pair, acc.dsd, acc.dsp);
@@ -323,7 +319,6 @@ k_rt_force_conv(EngK<float> K, const float *__restrict__ Iref_all, const float *
     V *sC = reinterpret_cast<V *>(smem_dynamic + 2 * RG::F_STAGE + RG::F_SW);
     auto issue = [&](int tile, int s) {
         const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
-        if (!rt_tile_fast(i0, j0, nx, ny)) return;
         proxy_fence_async();
         mbar_expect_tx(&bars[s], RG::F_TX);
         tma_load_3d(stage_i(s), mi, i0 - FO, j0 - FO, pair, &bars[s]);
@@ -338,14 +333,11 @@ k_rt_force_conv(EngK<float> K, const float *__restrict__ Iref_all, const float *
         const int next = tile + gridDim.x;
         if (tid == 0 && next < T.ntiles) issue(next, s ^ 1);
         const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
-        if (rt_tile_fast(i0, j0, nx, ny)) {
-            mbar_wait(&bars[s], (phase >> s) & 1u);
-            phase ^= 1u << s;
-            RtForceTile<KW>::template run<EPI>(stage_i(s), stage_u(s), stage_r(s), sW, sC, XW, XC, Imov, out, nx, ny, i0, j0, sratio, W, divzero, mx);
-        } else {
-            // the general instance of engine_fused.cuh: its own staging into stage s's window array
-            ForceConvTile<float, KW, false>::template run<EPI>(stage_i(s), sC, sW, &bars[2], uses, SW_, SC_, u, Iref, Imov, out, nx, ny, n, i0, j0, sratio, W, divzero, mx);
-        }
+        mbar_wait(&bars[s], (phase >> s) & 1u);
+        phase ^= 1u << s;
+        if (rt_tile_fast(i0, j0, nx, ny)) RtForceTile<KW>::template run<EPI>(stage_i(s), stage_u(s), stage_r(s), sW, sC, XW, XC, Imov, out, nx, ny, i0, j0, sratio, W, divzero, mx);
+        else   // the general instance of engine_fused.cuh on the staged window (its other inputs come through plain loads with the flat bounds test)
+            ForceConvTile<float, KW, false>::template run<EPI>(stage_i(s), sC, sW, &bars[2], uses, SW_, SC_, u, Iref, Imov, out, nx, ny, n, i0, j0, sratio, W, divzero, mx, true);
         __syncthreads();
     }
     if (divzero) atomicOr(&c->flags, OF2D_FLAG_DIVZERO);
