@@ -83,7 +83,9 @@ struct Engine {
     CUtensorMap tm_est_win[2], tm_est_tile[2], tm_c_tile[2], tm_imov_win, tm_iref_tile;
     const void *tm_iref_ptr;
     bool tma_fluid;              // engine_fluid_tma.cuh: maps of the two estimate buffers and the increment (transposed layout)
-    CUtensorMap tm_fl[5];
+    CUtensorMap tm_fl[5], tm_rw_lvl[2], tm_rw_imov, tm_rw_iref;   // k_rt_fl_rewarp: level-motion buffers; Imov window and Iref tile (per refine call)
+    const void *tm_rw_imov_ptr, *tm_rw_iref_ptr;
+    bool tma_rewarp;
 #endif
 };
 #define of2d_engine Engine
@@ -383,8 +385,29 @@ int enqueue_iteration(of2d_engine *E, const EngK<R> &K, const R *d_Iref, int cur
             // regrid (ImageRegistrationFluid.cpp:108-124): level <- est + level o (id + est); est <- 0; re-warp; derivatives
             { ProfScope _pc(E->ctx, "regrid_compose"); pdl_launch(k_e_compose<R, true>, grid_tiles(E, k_e_compose<R, true>), b, 0, s, K, G_REGRID, B_LVL_CUR, B_EST_CUR, B_LVL_NEXT, 0); }
             OF2D_LAUNCH_CHECK(E->ctx);
-            { ProfScope _pw(E->ctx, "regrid_rewarp"); pdl_launch(k_fl_rewarp<R>, grid_tiles(E, k_fl_rewarp<R>), b, 0, s, K, G_REGRID, d_Iref, (const R *)E->cur_Imov, B_LVL_NEXT, (vec2_t<R> *)E->gradI, (R *)E->It, B_EST_NEXT); }
-            OF2D_LAUNCH_CHECK(E->ctx);
+            bool rewarp_done = false;
+#if OF2D_RELAXED
+            if constexpr (sizeof(R) == 4) {
+                if (E->tma_rewarp && (fused_tma_enabled() & 2)) {
+                    if (E->tm_rw_imov_ptr != E->cur_Imov)
+                        E->tm_rw_imov_ptr = make_field_map(&E->tm_rw_imov, E->cur_Imov, 4, d.dimx, d.dimy, d.batch, FW, FW) ? E->cur_Imov : nullptr;
+                    if (E->tm_rw_iref_ptr != (const void *)d_Iref)
+                        E->tm_rw_iref_ptr = make_field_map(&E->tm_rw_iref, d_Iref, 4, d.dimx, d.dimy, d.batch, TILE, TILE) ? (const void *)d_Iref : nullptr;
+                    if (E->tm_rw_imov_ptr && E->tm_rw_iref_ptr) {
+                        TmaMaps4 MR;
+                        MR.m[0] = E->tm_rw_lvl[0]; MR.m[1] = E->tm_rw_lvl[1]; MR.m[2] = E->tm_rw_imov; MR.m[3] = E->tm_rw_iref;
+                        TRY(of2d_ensure_dynamic_smem((const void *)k_rt_fl_rewarp, RW_SMEM));
+                        { ProfScope _pw(E->ctx, "regrid_rewarp"); pdl_launch(k_rt_fl_rewarp, grid_tiles(E, k_rt_fl_rewarp, RW_SMEM), b, RW_SMEM, s, K, (int)G_REGRID, d_Iref, (const float *)E->cur_Imov, (float2 *)E->gradI, (float *)E->It, (int)B_EST_NEXT, MR); }
+                        OF2D_LAUNCH_CHECK(E->ctx);
+                        rewarp_done = true;
+                    }
+                }
+            }
+#endif
+            if (!rewarp_done) {
+                { ProfScope _pw(E->ctx, "regrid_rewarp"); pdl_launch(k_fl_rewarp<R>, grid_tiles(E, k_fl_rewarp<R>), b, 0, s, K, G_REGRID, d_Iref, (const R *)E->cur_Imov, B_LVL_NEXT, (vec2_t<R> *)E->gradI, (R *)E->It, B_EST_NEXT); }
+                OF2D_LAUNCH_CHECK(E->ctx);
+            }
             pdl_launch(k_regrid_commit, ceil_div(K.batch, 128), 128, 0, s, K.ctl, K.batch);
             OF2D_LAUNCH_CHECK(E->ctx);
             break;
@@ -627,13 +650,18 @@ int ENG(create)(of2d_ctx *ctx, const of2d_engine_desc *desc, of2d_engine_head **
         E->tma_ready = ok;
     }
     E->tma_fluid = false;
+    E->tma_rewarp = false;
     if (m == 5 && !E->dbl) {   // transposed layout: P elements per line, nx lines per pair, nT elements per pair
         const void *bufs3[3] = {E->est[0], E->est[1], E->incr};
         bool ok = (E->nT % 2) == 0 && (E->P % 2) == 0;
         for (int k = 0; k < 3 && ok; k++) ok = make_field_map_pitched(&E->tm_fl[k], bufs3[k], 8, E->P, nx, (size_t)E->nT, B, FI_W, FI_H);
         for (int k = 0; k < 2 && ok; k++) ok = make_field_map_pitched(&E->tm_fl[3 + k], E->est[k], 8, E->P, nx, (size_t)E->nT, B, TILE, TILE);
         E->tma_fluid = ok;
+        bool okr = true;
+        for (int k = 0; k < 2 && okr; k++) okr = make_field_map(&E->tm_rw_lvl[k], E->lvl[k], 8, nx, ny, B, RW_LP, RW_H);
+        E->tma_rewarp = okr && (nx % 4) == 0;   // (the Imov / Iref maps are made per refine call: caller-owned arrays)
     }
+    E->tm_rw_imov_ptr = E->tm_rw_iref_ptr = nullptr;
 #endif
     if (m == 1) {
         if ((st = of2d_curvature_plan_create(ctx, nx, ny, desc->alpha, desc->tau, E->dbl ? 1 : 0, &E->plan))) return fail(st);

@@ -118,6 +118,121 @@ k_rt_fl_integrate(EngK<float> K, const float2 *__restrict__ incr_all, const __gr
     fl_integrate_epilogue<float>(K, c, pair, acc, mj);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fluid regrid, second half (k_fl_rewarp; ImageRegistrationFluid.cpp:116-124): Iaux = Imov o (id + level motion), derivatives of
+// (Iref, Iaux) into the transposed layout, estimate <- 0 -- from staged tiles: the new level motion on the 34 x 34 halo tile, the
+// 48 x 48 window of Imov the bilinear taps read (displacements beyond ~6 px: Image::warp2d from global memory), Iref on the tile.
+// ---------------------------------------------------------------------------------------------
+constexpr int RW_H = TILE + 2, RW_LP = 36;                       // halo tile of the level motion: [RW_H][RW_LP] float2, origin (i0 - 2, j0 - 1)
+constexpr unsigned RW_SL = rt_round128(RW_LP * RW_H * 8), RW_SI = FW * FW * 4, RW_SR = TILE * TILE * 4;
+constexpr unsigned RW_STAGE = RW_SL + RW_SI + RW_SR, RW_TX = RW_LP * RW_H * 8 + FW * FW * 4 + TILE * TILE * 4;
+constexpr unsigned RW_SW = rt_round128(RW_H * (RW_H + 1) * 4), RW_SG = rt_round128(TILE * (TILE + 1) * 8), RW_ST = rt_round128(TILE * (TILE + 1) * 4);
+constexpr unsigned RW_SMEM = 2 * RW_STAGE + RW_SW + RW_SG + RW_ST;
+
+__device__ __noinline__ float rt_rewarp_slow(const float *__restrict__ Imov, int nx, int ny, int i, int j, float ux, float uy) {
+    return warp_pixel_lazy<float>(Imov, nx, ny, i, j, make_float2(ux, uy), i + j * nx);
+}
+
+__global__ void __launch_bounds__(TX *TY, 3)
+k_rt_fl_rewarp(EngK<float> K, int gate, const float *__restrict__ Iref_all, const float *__restrict__ Imov_all, float2 *__restrict__ gradI_all, float *__restrict__ It_all, int zero_buf,
+               const __grid_constant__ TmaMaps4 M) {   // M.m[0 / 1]: level-motion buffers, m[2]: Imov window, m[3]: Iref tile
+    pdl_enter();
+    using V = float2;
+    extern __shared__ __align__(128) unsigned char smem_dynamic[];
+    __shared__ uint64_t bars[2];
+    const int pair = blockIdx.y;
+    const CtlHot h = load_ctl(K.ctl + pair);
+    if (!gate_open(h, gate)) return;
+    const int nx = K.nx, ny = K.ny;
+    const float *__restrict__ Imov = Imov_all + (size_t)pair * K.n;
+    V *__restrict__ zero = pick(K, zero_buf, h, pair, true);
+    const CUtensorMap *ml = &M.m[(h.msel & 1) ^ 1], *mi = &M.m[2], *mr = &M.m[3];   // B_LVL_NEXT
+    const int tid = threadIdx.x + threadIdx.y * TX;
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init_fence(); }
+    unsigned phase = 0u;
+    const TileWalk T(nx, ny);
+    auto stage_l = [&](int s) { return reinterpret_cast<V *>(smem_dynamic + (unsigned)s * RW_STAGE); };
+    auto stage_i = [&](int s) { return reinterpret_cast<float *>(smem_dynamic + (unsigned)s * RW_STAGE + RW_SL); };
+    auto stage_r = [&](int s) { return reinterpret_cast<float *>(smem_dynamic + (unsigned)s * RW_STAGE + RW_SL + RW_SI); };
+    float (*sw)[RW_H + 1] = reinterpret_cast<float (*)[RW_H + 1]>(smem_dynamic + 2 * RW_STAGE);
+    V (*sg)[TILE + 1] = reinterpret_cast<V (*)[TILE + 1]>(smem_dynamic + 2 * RW_STAGE + RW_SW);
+    float (*st)[TILE + 1] = reinterpret_cast<float (*)[TILE + 1]>(smem_dynamic + 2 * RW_STAGE + RW_SW + RW_SG);
+    auto issue = [&](int tile, int s) {
+        const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
+        proxy_fence_async();
+        mbar_expect_tx(&bars[s], RW_TX);
+        tma_load_3d(stage_l(s), ml, i0 - 2, j0 - 1, pair, &bars[s]);
+        tma_load_3d(stage_i(s), mi, i0 - FO, j0 - FO, pair, &bars[s]);
+        tma_load_3d(stage_r(s), mr, i0, j0, pair, &bars[s]);
+    };
+    __syncthreads();
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < T.ntiles) issue(tile, 0);
+    for (int k = 0; tile < T.ntiles; tile += gridDim.x, k++) {
+        const int s = k & 1;
+        const int next = tile + gridDim.x;
+        if (tid == 0 && next < T.ntiles) issue(next, s ^ 1);
+        const int i0 = T.tx(tile) * TILE, j0 = T.ty(tile) * TILE;
+        mbar_wait(&bars[s], (phase >> s) & 1u);
+        phase ^= 1u << s;
+        const V *sl = stage_l(s);
+        const float *si = stage_i(s), *sr = stage_r(s);
+        // taps inside the window AND inside the image: window positions [lx0, lx0 + lxn) x [ly0, ly0 + lyn)
+        const TapBox tb(i0 - FO, j0 - FO, nx, ny);
+        for (int e = tid; e < RW_H * RW_H; e += TX * TY) {
+            const int r = e / RW_H, cc = e - r * RW_H;
+            const int i = i0 + cc - 1, j = j0 + r - 1;
+            float w = 0.0f;
+            if (i >= 0 && i < nx && j >= 0 && j < ny) {
+                const V u = sl[r * RW_LP + cc + 1];
+                const float px = (float)i + u.x, flx = floorf(px), py = (float)j + u.y, fly = floorf(py);
+                const int lx = (int)flx - (i0 - FO), ly = (int)fly - (j0 - FO);
+                const float fx = px - flx, fy = py - fly;
+                if ((unsigned)(lx - tb.lx0) < tb.lxn && (unsigned)(ly - tb.ly0) < tb.lyn) {
+                    const float *p = si + ly * FW + lx;
+                    const float s00 = p[0], s10 = p[1], s01 = p[FW], s11 = p[FW + 1];
+                    const float lo = s00 + fx * (s10 - s00), hi = s01 + fx * (s11 - s01);
+                    w = lo + fy * (hi - lo);
+                } else w = rt_rewarp_slow(Imov, nx, ny, i, j, u.x, u.y);
+            }
+            sw[r][cc] = w;
+        }
+        __syncthreads();
+        const int i = i0 + threadIdx.x;
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int jl = threadIdx.y + p * TY, j = j0 + jl;
+            if (i < nx && j < ny) {
+                const int r = jl + 1, cc = threadIdx.x + 1;
+                const float ce = sw[r][cc];
+                float gx, gy;   // gradients.h:9-32 on the warped image
+                if (i == 0) gx = sw[r][cc + 1] - ce;
+                else if (i == nx - 1) gx = ce - sw[r][cc - 1];
+                else gx = (sw[r][cc + 1] - sw[r][cc - 1]) * 0.5f;
+                if (j == 0) gy = sw[r + 1][cc] - ce;
+                else if (j == ny - 1) gy = ce - sw[r - 1][cc];
+                else gy = (sw[r + 1][cc] - sw[r - 1][cc]) * 0.5f;
+                sg[jl][threadIdx.x] = make_float2(gx, gy);
+                st[jl][threadIdx.x] = ce - sr[jl * TILE + threadIdx.x];
+            }
+        }
+        __syncthreads();
+        const int jt = j0 + threadIdx.x;   // fast thread index runs along j now
+#pragma unroll
+        for (int p = 0; p < PY; p++) {
+            const int il = threadIdx.y + p * TY, it = i0 + il;
+            if (it < nx && jt < ny) {
+                const size_t o = (size_t)it * K.P + jt;
+                gradI_all[(size_t)pair * K.nT + o] = sg[threadIdx.x][il];
+                It_all[(size_t)pair * K.nT + o] = st[threadIdx.x][il];
+                zero[o] = make_float2(0.0f, 0.0f);
+            }
+        }
+        __syncthreads();   // every read of stage s and of the tile arrays is over
+    }
+}
+
 }  // namespace
 
 #endif  // OF2D_RELAXED
