@@ -44,6 +44,7 @@
 #include "engine_fused.cuh"
 #include "engine_fused_tma.cuh"
 #include "engine_fluid_tma.cuh"
+#include "engine_hs_tma.cuh"
 #include "sor_tile.cuh"
 
 // =================================================================================================
@@ -86,6 +87,8 @@ struct Engine {
     CUtensorMap tm_fl[5], tm_rw_lvl[2], tm_rw_imov, tm_rw_iref;   // k_rt_fl_rewarp: level-motion buffers; Imov window and Iref tile (per refine call)
     const void *tm_rw_imov_ptr, *tm_rw_iref_ptr;
     bool tma_rewarp;
+    bool tma_hs;                 // engine_hs_tma.cuh: estimate buffers (36 x 36 halo tile), gradI, It (34-row halo tiles)
+    CUtensorMap tm_hs[4];
 #endif
 };
 #define of2d_engine Engine
@@ -426,6 +429,18 @@ int enqueue_hs_pair(of2d_engine *E, const EngK<R> &K) {
     cudaStream_t s = E->ctx->stream;
     const dim3 b(TX, TY);
     const R alpha = (R)E->d.alpha;
+#if OF2D_RELAXED
+    if constexpr (sizeof(R) == 4) {
+        if (E->tma_hs && (fused_tma_enabled() & 1)) {
+            TmaMaps4 MH;
+            for (int q = 0; q < 4; q++) MH.m[q] = E->tm_hs[q];
+            TRY(of2d_ensure_dynamic_smem((const void *)k_rt_hs_pair, HP_SMEM));
+            { ProfScope _ps(E->ctx, "hs_pair"); pdl_launch(k_rt_hs_pair, grid_tiles(E, k_rt_hs_pair, HP_SMEM), b, HP_SMEM, s, K, alpha * alpha, MH); }
+            OF2D_LAUNCH_CHECK(E->ctx);
+            return OF2D_SUCCESS;
+        }
+    }
+#endif
     { ProfScope _ps(E->ctx, "hs_pair"); pdl_launch(k_hs_pair<R>, grid_tiles(E, k_hs_pair<R>), b, 0, s, K, (const vec2_t<R> *)E->gradI, (const R *)E->It, alpha * alpha); }
     OF2D_LAUNCH_CHECK(E->ctx);
     return OF2D_SUCCESS;
@@ -651,6 +666,10 @@ int ENG(create)(of2d_ctx *ctx, const of2d_engine_desc *desc, of2d_engine_head **
     }
     E->tma_fluid = false;
     E->tma_rewarp = false;
+    E->tma_hs = false;
+    if (m == 0 && !E->dbl)
+        E->tma_hs = make_field_map(&E->tm_hs[0], E->est[0], 8, nx, ny, B, HP_H0, HP_H0) && make_field_map(&E->tm_hs[1], E->est[1], 8, nx, ny, B, HP_H0, HP_H0) &&
+                    make_field_map(&E->tm_hs[2], E->gradI, 8, nx, ny, B, HP_GP, HP_H1) && make_field_map(&E->tm_hs[3], E->It, 4, nx, ny, B, HP_TP, HP_H1);
     if (m == 5 && !E->dbl) {   // transposed layout: P elements per line, nx lines per pair, nT elements per pair
         const void *bufs3[3] = {E->est[0], E->est[1], E->incr};
         bool ok = (E->nT % 2) == 0 && (E->P % 2) == 0;

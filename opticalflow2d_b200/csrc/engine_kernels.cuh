@@ -295,6 +295,39 @@ __device__ __forceinline__ vec2_t<R> hs_point(vec2_t<R> a, vec2_t<R> b, vec2_t<R
     return mk2<R>(q.x - f.x / den, q.y - f.y / den);
 }
 
+// end of a two-step Horn-Schunck launch: the Logger test of BOTH steps by the last CTA (the first step's break hands the step to the
+// next launch through `redo`)
+template <class R>
+__device__ __forceinline__ void hs_pair_epilogue(const EngK<R> &K, PairCtl *c, int pair, const NormAcc<R> &acc1, const NormAcc<R> &acc2, bool single, bool divzero) {
+    const int tid = threadIdx.x + threadIdx.y * TX;
+    if (divzero) atomicOr(&c->flags, OF2D_FLAG_DIVZERO);
+    if (single) { logger_epilogue<R>(K, c, pair, acc1.dsd, acc1.dsp, true); return; }
+    double sd1 = acc1.dsd, sp1 = acc1.dsp, sd2 = acc2.dsd, sp2 = acc2.dsp;
+    block_sum2(sd1, sp1);
+    block_sum2(sd2, sp2);
+    const double vals[4] = {sd1, sp1, sd2, sp2};
+    double *part = K.partials + (size_t)pair * K.pstride;
+    if (publish_partials<4>(vals, part, &c->ticket[0], gridDim.x, blockIdx.x)) {
+        double out[4];
+        reduce_partials<4>(part, gridDim.x, out, 0u, 0u);
+        if (tid == 0) {
+            const R n = (R)(unsigned)K.n;
+            const R dn = (R)out[0] / n, pn = (R)out[1] / n;                       // Motion.cpp:47
+            const R err1 = pn == 0 ? (R)0.0f : dn / pn;                           // Logger.cpp:39
+            const int itc = c->iter;
+            if ((err1 < (R)0.001f && itc > 1) || itc + 1 >= c->niter) {
+                c->redo = 1;   // the loop ends after the first step: state untouched, the single-step launch redoes it
+            } else {
+                c->err = (double)err1;
+                if (itc < K.tr.cap) K.tr.err[(size_t)pair * K.tr.cap + itc] = (double)err1;
+                c->iter = itc + 1;
+                c->sel ^= 1;
+                finalize_logger<R>(c, K.tr, pair, out[2], out[3], (unsigned)K.n, K.n_active);
+            }
+        }
+    }
+}
+
 template <class R>
 __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? OF2D_HS_MINB : 2) k_hs_pair(EngK<R> K, const vec2_t<R> *__restrict__ gradI_all, const R *__restrict__ It_all, R alphasq) {
     pdl_enter();
@@ -390,32 +423,7 @@ __global__ void __launch_bounds__(TX *TY, sizeof(R) == 4 ? OF2D_HS_MINB : 2) k_h
         }
         acc2.flush();
     }
-    if (divzero) atomicOr(&c->flags, OF2D_FLAG_DIVZERO);
-    if (single) { logger_epilogue<R>(K, c, pair, acc1.dsd, acc1.dsp, true); return; }
-    double sd1 = acc1.dsd, sp1 = acc1.dsp, sd2 = acc2.dsd, sp2 = acc2.dsp;
-    block_sum2(sd1, sp1);
-    block_sum2(sd2, sp2);
-    const double vals[4] = {sd1, sp1, sd2, sp2};
-    double *part = K.partials + (size_t)pair * K.pstride;
-    if (publish_partials<4>(vals, part, &c->ticket[0], gridDim.x, blockIdx.x)) {
-        double out[4];
-        reduce_partials<4>(part, gridDim.x, out, 0u, 0u);
-        if (tid == 0) {
-            const R n = (R)(unsigned)K.n;
-            const R dn = (R)out[0] / n, pn = (R)out[1] / n;                       // Motion.cpp:47
-            const R err1 = pn == 0 ? (R)0.0f : dn / pn;                           // Logger.cpp:39
-            const int itc = c->iter;
-            if ((err1 < (R)0.001f && itc > 1) || itc + 1 >= c->niter) {
-                c->redo = 1;   // the loop ends after the first step: state untouched, the single-step launch redoes it
-            } else {
-                c->err = (double)err1;
-                if (itc < K.tr.cap) K.tr.err[(size_t)pair * K.tr.cap + itc] = (double)err1;
-                c->iter = itc + 1;
-                c->sel ^= 1;
-                finalize_logger<R>(c, K.tr, pair, out[2], out[3], (unsigned)K.n, K.n_active);
-            }
-        }
-    }
+    hs_pair_epilogue<R>(K, c, pair, acc1, acc2, single, divzero);
 }
 
 // ---------------------------------------------------------------------------------------------
