@@ -60,7 +60,7 @@ BIG_STEPS = 5e-4
 
 @pytest.mark.parametrize("bits", [32, 64])
 @pytest.mark.parametrize("reg,params,niter", CASES, ids=[f"{of.METHOD_NAMES[c[0]]}-{k}" for k, c in enumerate(CASES)])
-@pytest.mark.parametrize("dimx,dimy", [(160, 96), (97, 131), (320, 260)])
+@pytest.mark.parametrize("dimx,dimy", [(160, 96), (97, 131), (320, 260), (100, 76)])   # (100, 76): rows of 16-byte multiples (tensor-map path) with partial tiles in x and y
 def test_relaxed_engine_within_north_star_of_strict(bits, reg, params, niter, dimx, dimy):
     R, T = S.make_pair(dimx, dimy, "lattice", shift=(1.5, -0.75), smooth=True, sigma_b=6.0 if reg == of.FLUID else 8.0)
     mr, tr, wr = run(bits, "relaxed", (dimx, dimy), R, T, reg, params, niter)
