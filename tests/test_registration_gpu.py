@@ -152,3 +152,18 @@ def test_sessions_register_equals_the_three_separate_calls(bits):
     finally:
         for s in sessions:
             s.close()
+
+
+def test_sessions_register_rejects_bad_lists():
+    """The same session twice in one list (its images would be overwritten while it is being solved) and null buffers are refused
+    before anything is enqueued."""
+    R, T = S.make_pair(64, 48, "lattice", shift=(1.0, 0.5), smooth=True)
+    Rd, Td = np.ascontiguousarray(R, dtype=np.float64), np.ascontiguousarray(T, dtype=np.float64)
+    out = np.zeros((2,) + R.shape)
+    with of.Session((64, 48), [4], 0, of.DIFFUSION, [0.5]) as s:
+        with pytest.raises(of.OF2DError):
+            of.Session.register_many_raw([s, s], [Rd.ctypes.data] * 2, [Td.ctypes.data] * 2, [out.ctypes.data] * 2)
+        with pytest.raises(of.OF2DError):
+            of.Session.register_many_raw([s], [0], [Td.ctypes.data], [out.ctypes.data])
+        of.Session.register_many_raw([s], [Rd.ctypes.data], [Td.ctypes.data], [out.ctypes.data])   # the session is still usable
+        assert s.trace()["total_iterations"] == 4
