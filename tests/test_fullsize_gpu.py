@@ -34,9 +34,10 @@ def test_full_size_matches_compiled_reference(path):
     assert tr["iterations"] == len(g["err"])
     assert np.array_equal(np.asarray(tr["regrid_iter"], dtype=int), g["regrid_iter"].astype(int))
     # the reference sums 4 M norm terms into one float accumulator (src/Motion.cpp:42-49): its own error series
-    # carries ~1e-3 relative rounding noise at this size
+    # carries ~1e-3 relative rounding noise at this size.  Measured against it (scratch/fullsize_errseries.py): 1.3e-3 (Curvature) ...
+    # 6.8e-3 (Diffeomorphic, where the norms of a 4e-3 error are sums of 1e-6-sized terms)
     rel = np.abs(np.asarray(tr["err"]) - g["err"]) / np.maximum(np.abs(g["err"]), 1e-12)
-    assert rel.max() <= 2e-2, (rel.max(), int(rel.argmax()))
+    assert rel.max() <= 1e-2, (rel.max(), int(rel.argmax()))
     st, off = int(g["stride"]), int(g["offset"])
     # north-star fp32 bar (px) on the samples at least 8 px from the image border.  Closer to it the out-of-bounds test of
     # Motion::accumulate (src/Motion.cpp:141-144: a pixel whose composed position leaves the image keeps its old value) is a
