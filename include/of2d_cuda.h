@@ -97,6 +97,10 @@ int of2d_image_to_double_f64(of2d_ctx *ctx, size_t n, const double *d_in, double
 /* Motion::copy_motion_to_input, src/Motion.cpp:23-39: AoS real -> planar double (x plane, y plane) */
 int of2d_motion_to_planar_double_f32(of2d_ctx *ctx, size_t n, const float *d_u, double *d_out);
 int of2d_motion_to_planar_double_f64(of2d_ctx *ctx, size_t n, const double *d_u, double *d_out);
+/* `batch` fields in one launch: d_u = [batch][n]{x,y}, d_out = [batch][2][n] (the batch protocols convert a whole wave at once: one launch
+   finds its way between the kernels of a running solve, a launch per pair waits for a gap each time) */
+int of2d_motion_to_planar_double_batch_f32(of2d_ctx *ctx, size_t n, int batch, const float *d_u, double *d_out);
+int of2d_motion_to_planar_double_batch_f64(of2d_ctx *ctx, size_t n, int batch, const double *d_u, double *d_out);
 
 /* ---- field primitives ---- */
 /* Image::warp2d, src/Image.cpp:119-182 (out of place: d_dst must not alias d_src) */

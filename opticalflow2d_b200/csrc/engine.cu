@@ -74,7 +74,7 @@ struct Engine {
     // host
     int *h_snap;                 // pinned [2]
     cudaEvent_t ev[2];
-    std::vector<PairCtl> h_ctl;
+    PairCtl *h_ctl;              // pinned [batch]: the control blocks after the last refine pass
     uint64_t iterations_enqueued;
     const void *cur_Imov;
     int last_niter;
@@ -497,7 +497,8 @@ int refine_impl(of2d_engine *E, const R *d_Iref, const R *d_Imov, R *d_motion, i
         }
         enq += m;
         E->iterations_enqueued += (uint64_t)m;
-        OF2D_CUDA_TRY(cudaMemcpyAsync(&E->h_snap[slot], E->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, s));
+        pdl_launch(k_snapshot_active, dim3(1), dim3(32), 0, s, (const int *)E->d_nactive, &E->h_snap[slot]);   // (not a memcpy: see the kernel)
+        OF2D_CUDA_TRY(cudaGetLastError());
         OF2D_CUDA_TRY(cudaEventRecord(E->ev[slot], s));
         pending[slot] = true;
         const int other = slot ^ 1;
@@ -525,7 +526,8 @@ int refine_impl(of2d_engine *E, const R *d_Iref, const R *d_Imov, R *d_motion, i
         { ProfScope _pc(E->ctx, "final_compose"); pdl_launch(k_e_compose<R, false>, grid_tiles(E, k_e_compose<R, false>), b, 0, s, K, G_NONE, B_LVL_CUR, B_EST_CUR, B_EXT, 0); }
     }
     OF2D_LAUNCH_CHECK(ctx);
-    OF2D_CUDA_TRY(cudaMemcpyAsync(E->h_ctl.data(), E->d_ctl, sizeof(PairCtl) * K.batch, cudaMemcpyDeviceToHost, s));
+    pdl_launch(k_copy_ctl_to_host, dim3(ceil_div((long)K.batch * (long)(sizeof(PairCtl) / sizeof(int4)), 256)), dim3(256), 0, s, (const PairCtl *)E->d_ctl, E->h_ctl, K.batch);
+    OF2D_CUDA_TRY(cudaGetLastError());
     OF2D_CUDA_TRY(cudaStreamSynchronize(s));
     unsigned flags = 0;
     int overflow = 0;
@@ -692,7 +694,8 @@ int ENG(create)(of2d_ctx *ctx, const of2d_engine_desc *desc, of2d_engine_head **
     if (cudaHostAlloc((void **)&E->h_snap, sizeof(int) * 2, cudaHostAllocDefault) != cudaSuccess) { of2d_set_error("engine: pinned allocation failed"); return fail(OF2D_ERR_CUDA); }
     for (int k = 0; k < 2; k++)
         if (cudaEventCreateWithFlags(&E->ev[k], cudaEventDisableTiming) != cudaSuccess) { of2d_set_error("engine: event creation failed"); return fail(OF2D_ERR_CUDA); }
-    E->h_ctl.resize((size_t)B);
+    if (cudaHostAlloc((void **)&E->h_ctl, sizeof(PairCtl) * (size_t)B, cudaHostAllocDefault) != cudaSuccess) { of2d_set_error("engine: pinned allocation failed"); return fail(OF2D_ERR_CUDA); }
+    memset(E->h_ctl, 0, sizeof(PairCtl) * (size_t)B);
     *out = E;
     return OF2D_SUCCESS;
 }
@@ -707,6 +710,7 @@ void ENG(destroy)(of2d_engine_head *H) {
     for (void *p : bufs) if (p) cudaFree(p);
     if (E->plan) of2d_curvature_plan_destroy(E->plan);
     if (E->h_snap) cudaFreeHost(E->h_snap);
+    if (E->h_ctl) cudaFreeHost(E->h_ctl);
     for (int k = 0; k < 2; k++) if (E->ev[k]) cudaEventDestroy(E->ev[k]);
     delete E;
 }

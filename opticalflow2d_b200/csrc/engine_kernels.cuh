@@ -168,6 +168,23 @@ __global__ void k_ctl_begin(PairCtl *ctl, int batch, int niter, int *n_active) {
     c->err = 0.0;
 }
 
+// Read-backs of the control state into PINNED host memory by a kernel (the host pointer is the device pointer under unified addressing)
+// instead of cudaMemcpyAsync: a device -> host memcpy queues on the copy engine behind whatever another stream is downloading (a
+// wave's motions, 512 MB), and the iteration loop -- which polls the counter of running pairs every 8 iterations -- stood still
+// for the length of that download (11 % of the streamed batch rate, ~1 ms per method of the pipelined sessions call).
+__global__ void k_snapshot_active(const int *__restrict__ n_active, int *host_slot) {
+    pdl_enter();
+    if (threadIdx.x == 0 && blockIdx.x == 0) { *host_slot = *n_active; __threadfence_system(); }
+}
+__global__ void k_copy_ctl_to_host(const PairCtl *__restrict__ ctl, PairCtl *host_ctl, int batch) {
+    pdl_enter();
+    const int n4 = batch * (int)(sizeof(PairCtl) / sizeof(int4));
+    const int4 *src = reinterpret_cast<const int4 *>(ctl);
+    int4 *dst = reinterpret_cast<int4 *>(host_ctl);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += gridDim.x * blockDim.x) dst[k] = __ldcg(src + k);
+    __threadfence_system();
+}
+
 __global__ void k_regrid_commit(PairCtl *ctl, int batch) {
     pdl_enter();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;

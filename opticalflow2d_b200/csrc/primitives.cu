@@ -33,6 +33,18 @@ __global__ void k_motion_to_planar(size_t n, const vec2_t<R> *__restrict__ u, do
     }
 }
 
+// the same for `batch` fields of n pixels in ONE launch (grid.y = field): out = [field][2][n]
+template <class R>
+__global__ void k_motion_to_planar_batch(size_t n, const vec2_t<R> *__restrict__ u, double *__restrict__ out) {
+    u += (size_t)blockIdx.y * n;
+    out += (size_t)blockIdx.y * 2 * n;
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        const vec2_t<R> v = u[k];
+        out[k] = (double)v.x;
+        out[k + n] = (double)v.y;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // warp / compose
 // ---------------------------------------------------------------------------------------------
@@ -542,6 +554,15 @@ int resample_impl(of2d_ctx *ctx, int ncomp, int ix, int iy, const R *in, int ox,
 // ---- C ABI ---------------------------------------------------------------------------------------
 #define G1(n) grid1d((n), ctx->sm_count), 256, 0, ctx->stream
 
+template <class R>
+static int planar_batch_impl(of2d_ctx *ctx, size_t n, int batch, const R *u, double *out) {
+    OF2D_REQUIRE(batch > 0 && batch <= 65535, "batch out of range");
+    const unsigned gx = (unsigned)((n + 1023) / 1024 < 64 ? (n + 1023) / 1024 : 64);   // few, long CTAs per field: the launch shares the device with a running solve
+    k_motion_to_planar_batch<R><<<dim3(gx ? gx : 1, (unsigned)batch), 256, 0, ctx->stream>>>(n, (const vec2_t<R> *)u, out);
+    OF2D_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 extern "C" {
 
 int of2d_image_from_double_f32(of2d_ctx *ctx, size_t n, const double *in, float *out) { k_cast<double, float><<<G1(n)>>>(n, in, out); OF2D_LAUNCH_CHECK(ctx); return 0; }
@@ -550,6 +571,8 @@ int of2d_image_to_double_f32(of2d_ctx *ctx, size_t n, const float *in, double *o
 int of2d_image_to_double_f64(of2d_ctx *ctx, size_t n, const double *in, double *out) { k_cast<double, double><<<G1(n)>>>(n, in, out); OF2D_LAUNCH_CHECK(ctx); return 0; }
 int of2d_motion_to_planar_double_f32(of2d_ctx *ctx, size_t n, const float *u, double *out) { k_motion_to_planar<float><<<G1(n)>>>(n, (const float2 *)u, out); OF2D_LAUNCH_CHECK(ctx); return 0; }
 int of2d_motion_to_planar_double_f64(of2d_ctx *ctx, size_t n, const double *u, double *out) { k_motion_to_planar<double><<<G1(n)>>>(n, (const double2 *)u, out); OF2D_LAUNCH_CHECK(ctx); return 0; }
+int of2d_motion_to_planar_double_batch_f32(of2d_ctx *ctx, size_t n, int batch, const float *u, double *out) { return planar_batch_impl<float>(ctx, n, batch, u, out); }
+int of2d_motion_to_planar_double_batch_f64(of2d_ctx *ctx, size_t n, int batch, const double *u, double *out) { return planar_batch_impl<double>(ctx, n, batch, u, out); }
 
 int of2d_warp2d_f32(of2d_ctx *ctx, int nx, int ny, int batch, const float *s, const float *u, float *d) { return warp2d_impl<float>(ctx, nx, ny, batch, s, u, d); }
 int of2d_warp2d_f64(of2d_ctx *ctx, int nx, int ny, int batch, const double *s, const double *u, double *d) { return warp2d_impl<double>(ctx, nx, ny, batch, s, u, d); }

@@ -155,8 +155,8 @@ void BatchRegistration::copy_estimated_motion(double* out) const {
     double* st = (double*)staging->device_discard();
     for (int w = 0; w < nwaves; w++) {
         const int p0 = w * wave, m = batch - p0 < wave ? batch - p0 : wave;
-        for (int k = 0; k < m; k++)
-            of2d::check(of2d::motion_to_planar(npix, mo + 2 * npix * (size_t)(p0 + k), st + 2 * npix * (size_t)k));
+        of2d::check(sizeof(of2d_real) == 8 ? of2d_motion_to_planar_double_batch_f64(ctx, npix, m, (const double*)(mo + 2 * npix * (size_t)p0), st)
+                                           : of2d_motion_to_planar_double_batch_f32(ctx, npix, m, (const float*)(mo + 2 * npix * (size_t)p0), st));
         of2d::check(of2d_d2h(ctx, out + 2 * npix * (size_t)p0, st, sizeof(double) * 2 * npix * (size_t)m));
     }
 }
@@ -198,11 +198,12 @@ void BatchRegistration::register_pairs(const double* ref, const double* mov, dou
         const int b = w & 1, m = count(w);
         const of2d_real* mo = (const of2d_real*)s_mot[b]->device_ro();
         double* st = (double*)s_out[b]->device_discard();
-        for (int k = 0; k < m; k++)
-            of2d::check(sizeof(of2d_real) == 8 ? of2d_motion_to_planar_double_f64(ctx_out, npix, (const double*)(mo + 2 * npix * (size_t)k), st + 2 * npix * (size_t)k)
-                                               : of2d_motion_to_planar_double_f32(ctx_out, npix, (const float*)(mo + 2 * npix * (size_t)k), st + 2 * npix * (size_t)k));
+        // one launch for the wave (a launch per pair waited for a gap between the solve's kernels each time: 11 % of the streamed rate)
+        of2d::check(sizeof(of2d_real) == 8 ? of2d_motion_to_planar_double_batch_f64(ctx_out, npix, m, (const double*)mo, st)
+                                           : of2d_motion_to_planar_double_batch_f32(ctx_out, npix, m, (const float*)mo, st));
         of2d::check(of2d_d2h_async(ctx_out, out + 2 * npix * (size_t)(w * wave), st, sizeof(double) * 2 * npix * (size_t)m));
     };
+    static const int diag = std::getenv("OF2D_BATCH_DIAG") ? std::atoi(std::getenv("OF2D_BATCH_DIAG")) : 0;   // experiments: 1 = no uploads after the first wave, 2 = no downloads
     issue_in(0);
     for (int w = 0; w < nwaves; w++) {
         const int b = w & 1;
@@ -213,11 +214,11 @@ void BatchRegistration::register_pairs(const double* ref, const double* mov, dou
         if (frames > 1 && w > 0) of2d::check(of2d_d2d(ctx, mo, s_mot[b ^ 1]->device_ro(), 2 * rb * wn));   // cine chain
         else of2d::check(of2d_memset(ctx, mo, 0, 2 * rb * wn));
         // neighbours' copies go under this wave's solve: set b ^ 1 is free (wave w - 1 is solved, wave w + 1 not started)
-        if (w + 1 < nwaves) issue_in(w + 1);
-        if (w >= 1) issue_out(w - 1);
+        if (w + 1 < nwaves && !(diag & 1)) issue_in(w + 1);
+        if (w >= 1 && !(diag & 2)) issue_out(w - 1);
         solve_wave(w, (const of2d_real*)s_ref[b]->device_ro(), (const of2d_real*)s_mov[b]->device_ro(), mo, count(w));
     }
-    issue_out(nwaves - 1);
+    if (!(diag & 2)) issue_out(nwaves - 1);
     of2d::check(of2d_ctx_sync(ctx_out));
     of2d::check(of2d_ctx_sync(ctx_in));
 }
