@@ -203,7 +203,6 @@ void BatchRegistration::register_pairs(const double* ref, const double* mov, dou
                                            : of2d_motion_to_planar_double_batch_f32(ctx_out, npix, m, (const float*)mo, st));
         of2d::check(of2d_d2h_async(ctx_out, out + 2 * npix * (size_t)(w * wave), st, sizeof(double) * 2 * npix * (size_t)m));
     };
-    static const int diag = std::getenv("OF2D_BATCH_DIAG") ? std::atoi(std::getenv("OF2D_BATCH_DIAG")) : 0;   // experiments: 1 = no uploads after the first wave, 2 = no downloads
     issue_in(0);
     for (int w = 0; w < nwaves; w++) {
         const int b = w & 1;
@@ -214,11 +213,11 @@ void BatchRegistration::register_pairs(const double* ref, const double* mov, dou
         if (frames > 1 && w > 0) of2d::check(of2d_d2d(ctx, mo, s_mot[b ^ 1]->device_ro(), 2 * rb * wn));   // cine chain
         else of2d::check(of2d_memset(ctx, mo, 0, 2 * rb * wn));
         // neighbours' copies go under this wave's solve: set b ^ 1 is free (wave w - 1 is solved, wave w + 1 not started)
-        if (w + 1 < nwaves && !(diag & 1)) issue_in(w + 1);
-        if (w >= 1 && !(diag & 2)) issue_out(w - 1);
+        if (w + 1 < nwaves) issue_in(w + 1);
+        if (w >= 1) issue_out(w - 1);
         solve_wave(w, (const of2d_real*)s_ref[b]->device_ro(), (const of2d_real*)s_mov[b]->device_ro(), mo, count(w));
     }
-    if (!(diag & 2)) issue_out(nwaves - 1);
+    issue_out(nwaves - 1);
     of2d::check(of2d_ctx_sync(ctx_out));
     of2d::check(of2d_ctx_sync(ctx_in));
 }
