@@ -8,8 +8,9 @@
 //                                (overwritten in place by the composed field) }
 //
 // The arithmetic of an interior tile is the FAST instance of engine_fused.cuh (no validity / wrap / border tests); border
-// tiles (about 6 % at 2048^2) run that file's general instance unchanged on the same shared arrays, so the flat-index
-// semantics of the reference's convolution (Field.tpp:245-248) and Image::warp2d's border rules stay where they were.
+// tiles (about 6 % at 2048^2, 23 % at 512^2) run that file's general instance on the same shared arrays -- with the source window
+// taken from the same prefetch (zeros outside the field, which no tap box reaches) -- so the flat-index semantics of the
+// reference's convolution (Field.tpp:245-248) and Image::warp2d's border rules stay where they were.
 // Reference computation: DemonsThirions.cpp:18-42, DemonsDiffeomorphic.cpp:15-30, Demons.cpp:34-63, Motion.cpp:113-178.
 #pragma once
 
