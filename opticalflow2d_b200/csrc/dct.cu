@@ -449,6 +449,7 @@ __device__ __forceinline__ int swz8(int i) {
 #define RG_C2 float2
 #define RG_S float
 #define RG_MK2 make_float2
+#define RG_PACKED 1
 #ifndef OF2D_RGF_MINB
 #define OF2D_RGF_MINB 3
 #endif

@@ -35,8 +35,22 @@ namespace RG_NS {
 
 __device__ __forceinline__ RG_C2 cmulf(RG_C2 a, RG_C2 b) { return RG_MK2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x)); }
 __device__ __forceinline__ RG_C2 cmulcf(RG_C2 a, RG_C2 b) { return RG_MK2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -(a.x * b.y))); }   // a conj(b)
+#ifdef RG_PACKED
+// fp32: both components of a complex addition in one packed sm_100a instruction (SASS FADD2)
+__device__ __forceinline__ unsigned long long pk2(float2 a) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
+__device__ __forceinline__ float2 upk2(unsigned long long v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ RG_C2 add2(RG_C2 a, RG_C2 b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b))); return upk2(r); }
+__device__ __forceinline__ RG_C2 sub2(RG_C2 a, RG_C2 b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b))); return upk2(r); }
+// Logger addend of fp32 fields in the relaxed engine: MUFU.SQRT without the subnormal fix-up (as engine_kernels.cuh's sqrt_approx)
+__device__ __forceinline__ float lg_sqrtf(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// eigenvalue 1 / (1 + tau alpha lap^2) of the relaxed engine: the argument is >= 1, MUFU.RCP (1 ulp) without the IEEE fix-up
+__device__ __forceinline__ float rg_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else
+__device__ __forceinline__ RG_S rg_rcp(RG_S x) { return (RG_S)1 / x; }
 __device__ __forceinline__ RG_C2 add2(RG_C2 a, RG_C2 b) { return RG_MK2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ RG_C2 sub2(RG_C2 a, RG_C2 b) { return RG_MK2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float lg_sqrtf(float x) { return sqrtf(x); }
+#endif
 template <int SIGN> __device__ __forceinline__ RG_C2 mul_i(RG_C2 a) { return SIGN > 0 ? RG_MK2(-a.y, a.x) : RG_MK2(a.y, -a.x); }   // a (SIGN i)
 
 // a e^{SIGN 2 pi i n / 16}
@@ -305,7 +319,7 @@ __global__ void __launch_bounds__(2 * Geo<L>::TPL, 2 * Geo<L>::TPL <= 256 ? RG_M
         // OpticalFlowCurvature.cpp:24, :135-136: 1 / (1 + tau alpha lap^2) for k and N-k, with one division for the two
         const RG_S lk = -4 + cxp + (RG_S)cosy[k], ln = -4 + cxp + (RG_S)cosy[nk];
         const RG_S dk = 1.0f + ta * (lk * lk), dn = 1.0f + ta * (ln * ln);
-        const RG_S r = (RG_S)1 / (dk * dn), ek = r * dn, en = r * dk;
+        const RG_S r = rg_rcp(dk * dn), ek = r * dn, en = r * dk;
         { const RG_S fk = (RG_S)ek, fn = (RG_S)en; ak.x *= fk; ak.y *= fk; an.x *= fn; an.y *= fn; }
         RG_C2 oj, on;
         pre_pair(ak, an, qk, oj, on);
@@ -323,7 +337,7 @@ __global__ void __launch_bounds__(2 * Geo<L>::TPL, 2 * Geo<L>::TPL <= 256 ? RG_M
         RG_C2 ak, an;
         post_pair(z, z, qk, ak, an);
         const RG_S lk = -4 + cxp + (RG_S)cosy[k];
-        const RG_S ek = 1.0f / (1.0f + ta * (lk * lk));
+        const RG_S ek = rg_rcp(1.0f + ta * (lk * lk));
         { const RG_S fk = (RG_S)ek; ak.x *= fk; ak.y *= fk; }
         RG_C2 oj, on;
         pre_pair(ak, ak, qk, oj, on);
@@ -409,14 +423,16 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
     if constexpr (PREFETCH) fft_inv<L>(a, x + l * N, u, k, T, fetch_prev);
     else { fft_inv<L>(a, x + l * N, u, k, T); fetch_prev(); }
     double sd = 0.0, sp = 0.0;
+    // 4 nx ny is a power of two on this path (both sizes are): multiplying by its reciprocal rounds exactly like the reference's division
+    const R inv4N = (R)1 / fourN;
     vec2_t<R> ue[FUSE ? 8 : 1], uo[FUSE ? 8 : 1];   // FUSE: the new estimate at the thread's 8 pixel pairs
     {
 #pragma unroll
         for (int qq = 0; qq < 8; qq++) {
             // t[m] (mine, m = k + S1 qq) is pixel 2m; pixel 2m+1 is t[N-1-m] = element 15-qq of lane ^ 16
             const RG_C2 ve = a[slot_q(16, qq)], vs = a[slot_q(16, 15 - qq)];
-            const vec2_t<R> o0 = mk2<R>((R)ve.x / fourN, (R)ve.y / fourN);                      // OpticalFlowCurvature.cpp:116-117
-            const vec2_t<R> os = mk2<R>((R)vs.x / fourN, (R)vs.y / fourN);
+            const vec2_t<R> o0 = mk2<R>((R)ve.x * inv4N, (R)ve.y * inv4N);                      // OpticalFlowCurvature.cpp:116-117
+            const vec2_t<R> os = mk2<R>((R)vs.x * inv4N, (R)vs.y * inv4N);
             const vec2_t<R> o1 = mk2<R>(__shfl_xor_sync(0xffffffffu, os.x, 16), __shfl_xor_sync(0xffffffffu, os.y, 16));
             store_px_pair<R>(unew + row + 2 * (k + G::S1 * qq), o0, o1);
             if (FUSE) { ue[qq] = o0; uo[qq] = o1; }
@@ -424,8 +440,8 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
                 const vec2_t<R> p0 = pv[2 * qq], p1 = pv[2 * qq + 1];
                 const vec2_t<R> d0 = mk2<R>(o0.x - p0.x, o0.y - p0.y), d1 = mk2<R>(o1.x - p1.x, o1.y - p1.y);
                 if (sizeof(R) == 4) {
-                    sd += (double)sqrtf((float)(d0.x * d0.x + d0.y * d0.y)) + (double)sqrtf((float)(d1.x * d1.x + d1.y * d1.y));
-                    sp += (double)sqrtf((float)(p0.x * p0.x + p0.y * p0.y)) + (double)sqrtf((float)(p1.x * p1.x + p1.y * p1.y));
+                    sd += (double)lg_sqrtf((float)(d0.x * d0.x + d0.y * d0.y)) + (double)lg_sqrtf((float)(d1.x * d1.x + d1.y * d1.y));
+                    sp += (double)lg_sqrtf((float)(p0.x * p0.x + p0.y * p0.y)) + (double)lg_sqrtf((float)(p1.x * p1.x + p1.y * p1.y));
                 } else {
                     sd += sqrt((double)(d0.x * d0.x + d0.y * d0.y)) + sqrt((double)(d1.x * d1.x + d1.y * d1.y));
                     sp += sqrt((double)(p0.x * p0.x + p0.y * p0.y)) + sqrt((double)(p1.x * p1.x + p1.y * p1.y));
@@ -492,3 +508,4 @@ struct Api {
 #undef RG_MK2
 #undef RG_MINB
 #undef RG_SWZ
+#undef RG_PACKED
