@@ -136,40 +136,50 @@ template <int L> struct Geo {
     }
 };
 
+// Shared-memory addressing of the super-passes.  RG_SWZ is linear over GF(2) (shifts, XORs, a mask), and in every access below the
+// index is A + B with the thread's part A and the unrolled loop's constant B on DISJOINT bits, so RG_SWZ(A + B) = RG_SWZ(A) ^ RG_SWZ(B):
+// the thread's byte offset is formed once per pass and every access costs one XOR with an immediate.
+constexpr unsigned ES = sizeof(RG_C2);
+#define RG_CS(i) ((unsigned)RG_SWZ(i) * ES)
+__device__ __forceinline__ RG_C2 &sm_at(RG_C2 *x, unsigned byte_off) { return *reinterpret_cast<RG_C2 *>(reinterpret_cast<unsigned char *>(x) + byte_off); }
+
 struct Tw16 { const RG_C2 *a, *b; };   // [4][S1] for super-pass 1 (w_N), [4][S2] for super-pass 2 (w_{N/16}); forward sign
 
 // ---- forward (DIF): registers -> ... -> shared memory, digit-reversed --------------------------------------------
 // in: a[j] = v[k + S1 j] (natural order); the threads of a line hold k1 = a permutation of 0 .. S1-1 and u = 0 .. S1-1.
-// out: X_k at xl[RG_SWZ(pos(k))], after the trailing barrier.
-template <int L> __device__ __forceinline__ void fft_fwd(RG_C2 (&a)[16], RG_C2 *xl, int u, int k1, Tw16 T) {
+// out: X_k at xl[RG_SWZ(pos(k))], xl = the line at byte offset lo of x, after the trailing barrier.
+template <int L> __device__ __forceinline__ void fft_fwd(RG_C2 (&a)[16], RG_C2 *x, unsigned lo, int u, int k1, Tw16 T) {
     using G = Geo<L>;
     {
         const int k = k1;
         dft<16, -1, 0>(a);
         twiddle16<true, false>(a, T.a[k], T.a[G::S1 + k], T.a[2 * G::S1 + k], T.a[3 * G::S1 + k]);
+        const unsigned t = lo + RG_CS(k);
 #pragma unroll
-        for (int s = 0; s < 16; s++) xl[RG_SWZ(k + G::S1 * slot_q(16, s))] = a[s];
+        for (int s = 0; s < 16; s++) sm_at(x, t ^ RG_CS(G::S1 * slot_q(16, s))) = a[s];
     }
     __syncthreads();
     {
         const int b = u / G::S2, k = u % G::S2, base = b * G::S1 + k;
+        const unsigned t = lo + RG_CS(base);
 #pragma unroll
-        for (int j = 0; j < 16; j++) a[j] = xl[RG_SWZ(base + G::S2 * j)];
+        for (int j = 0; j < 16; j++) a[j] = sm_at(x, t ^ RG_CS(G::S2 * j));
         dft<16, -1, 0>(a);
         twiddle16<true, false>(a, T.b[k], T.b[G::S2 + k], T.b[2 * G::S2 + k], T.b[3 * G::S2 + k]);
 #pragma unroll
-        for (int s = 0; s < 16; s++) xl[RG_SWZ(base + G::S2 * slot_q(16, s))] = a[s];
+        for (int s = 0; s < 16; s++) sm_at(x, t ^ RG_CS(G::S2 * slot_q(16, s))) = a[s];
     }
     __syncthreads();
     {
+        const unsigned t = lo + RG_CS(16 * u);
 #pragma unroll
-        for (int j = 0; j < 16; j++) a[j] = xl[RG_SWZ(16 * u + j)];
+        for (int j = 0; j < 16; j++) a[j] = sm_at(x, t ^ RG_CS(j));
         if constexpr (G::M3 == 16) dft<16, -1, 0>(a);
         if constexpr (G::M3 == 8) { dft<8, -1, 0>(a); dft<8, -1, 8>(a); }
         if constexpr (G::M3 == 4) { dft<4, -1, 0>(a); dft<4, -1, 4>(a); dft<4, -1, 8>(a); dft<4, -1, 12>(a); }
         if constexpr (G::M3 == 2) { dft<2, -1, 0>(a); dft<2, -1, 2>(a); dft<2, -1, 4>(a); dft<2, -1, 6>(a); dft<2, -1, 8>(a); dft<2, -1, 10>(a); dft<2, -1, 12>(a); dft<2, -1, 14>(a); }
 #pragma unroll
-        for (int s = 0; s < 16; s++) xl[RG_SWZ(16 * u + (s & ~(G::M3 - 1)) + slot_q(G::M3, s & (G::M3 - 1)))] = a[s];
+        for (int s = 0; s < 16; s++) sm_at(x, t ^ RG_CS((s & ~(G::M3 - 1)) + slot_q(G::M3, s & (G::M3 - 1)))) = a[s];
     }
     __syncthreads();
 }
@@ -178,34 +188,37 @@ template <int L> __device__ __forceinline__ void fft_fwd(RG_C2 (&a)[16], RG_C2 *
 // in: h_k at xl[RG_SWZ(pos(k))] (caller has synchronised).  out: a[s] = t[k1 + S1 q], q = slot_q(16, s).
 // `before_last_barrier` runs while a[] is dead (prefetches of the epilogue go there).
 struct NoHook { __device__ __forceinline__ void operator()() const {} };
-template <int L, class Hook = NoHook> __device__ __forceinline__ void fft_inv(RG_C2 (&a)[16], RG_C2 *xl, int u, int k1, Tw16 T, Hook before_last_barrier = Hook()) {
+template <int L, class Hook = NoHook> __device__ __forceinline__ void fft_inv(RG_C2 (&a)[16], RG_C2 *x, unsigned lo, int u, int k1, Tw16 T, Hook before_last_barrier = Hook()) {
     using G = Geo<L>;
     {
+        const unsigned t = lo + RG_CS(16 * u);
 #pragma unroll
-        for (int j = 0; j < 16; j++) a[j] = xl[RG_SWZ(16 * u + j)];
+        for (int j = 0; j < 16; j++) a[j] = sm_at(x, t ^ RG_CS(j));
         if constexpr (G::M3 == 16) dft<16, +1, 0>(a);
         if constexpr (G::M3 == 8) { dft<8, +1, 0>(a); dft<8, +1, 8>(a); }
         if constexpr (G::M3 == 4) { dft<4, +1, 0>(a); dft<4, +1, 4>(a); dft<4, +1, 8>(a); dft<4, +1, 12>(a); }
         if constexpr (G::M3 == 2) { dft<2, +1, 0>(a); dft<2, +1, 2>(a); dft<2, +1, 4>(a); dft<2, +1, 6>(a); dft<2, +1, 8>(a); dft<2, +1, 10>(a); dft<2, +1, 12>(a); dft<2, +1, 14>(a); }
 #pragma unroll
-        for (int s = 0; s < 16; s++) xl[RG_SWZ(16 * u + (s & ~(G::M3 - 1)) + slot_q(G::M3, s & (G::M3 - 1)))] = a[s];
+        for (int s = 0; s < 16; s++) sm_at(x, t ^ RG_CS((s & ~(G::M3 - 1)) + slot_q(G::M3, s & (G::M3 - 1)))) = a[s];
     }
     __syncthreads();
     {
         const int b = u / G::S2, k = u % G::S2, base = b * G::S1 + k;
+        const unsigned t = lo + RG_CS(base);
 #pragma unroll
-        for (int j = 0; j < 16; j++) a[j] = xl[RG_SWZ(base + G::S2 * j)];
+        for (int j = 0; j < 16; j++) a[j] = sm_at(x, t ^ RG_CS(G::S2 * j));
         twiddle16<false, true>(a, T.b[k], T.b[G::S2 + k], T.b[2 * G::S2 + k], T.b[3 * G::S2 + k]);
         dft<16, +1, 0>(a);
 #pragma unroll
-        for (int s = 0; s < 16; s++) xl[RG_SWZ(base + G::S2 * slot_q(16, s))] = a[s];
+        for (int s = 0; s < 16; s++) sm_at(x, t ^ RG_CS(G::S2 * slot_q(16, s))) = a[s];
     }
     before_last_barrier();
     __syncthreads();
     {
         const int k = k1;
+        const unsigned t = lo + RG_CS(k);
 #pragma unroll
-        for (int j = 0; j < 16; j++) a[j] = xl[RG_SWZ(k + G::S1 * j)];
+        for (int j = 0; j < 16; j++) a[j] = sm_at(x, t ^ RG_CS(G::S1 * j));
         twiddle16<false, true>(a, T.a[k], T.a[G::S1 + k], T.a[2 * G::S1 + k], T.a[3 * G::S1 + k]);
         dft<16, +1, 0>(a);
     }
@@ -255,7 +268,6 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
     }
     uin += pair_off; gradI += pair_off; It += pair_off; specT += pair_off;
     const int tid = threadIdx.x, l = tid / G::TPL, u = tid % G::TPL, j0 = blockIdx.x * LPC;
-    RG_C2 *xl = x + l * N;
     RG_C2 a[16];
     {   // pixel pairs (2m, 2m+1), m = k + S1 j (j < 8): the even pixel is v[m] (mine), the odd one v[N-1-m] (lane ^ 16, element 15-j)
         const int k = G::k1(u);
@@ -271,7 +283,7 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
             a[15 - j] = RG_MK2((RG_S)__shfl_xor_sync(0xffffffffu, ox, 16), (RG_S)__shfl_xor_sync(0xffffffffu, oy, 16));
         }
     }
-    fft_fwd<L>(a, xl, u, G::k1(u), T);
+    fft_fwd<L>(a, x, (unsigned)(l * N) * ES, u, G::k1(u), T);
     constexpr int hp = (N >> 1) + 1;
     for (int e = tid; e < LPC * hp; e += LPC * G::TPL) {
         const int ll = e % LPC, k = e / LPC, nk = (N - k) & (N - 1);
@@ -307,7 +319,7 @@ __global__ void __launch_bounds__(2 * Geo<L>::TPL, 2 * Geo<L>::TPL <= 256 ? RG_M
         const int m = u + G::S1 * j;
         a[j] = line[j < 8 ? 2 * m : 2 * (N - 1 - m) + 1];
     }
-    fft_fwd<L>(a, xl, u, u, T);
+    fft_fwd<L>(a, x, (unsigned)(l * N) * ES, u, u, T);
     const RG_S cxp = (RG_S)cosx[p], ta = (RG_S)tau_alpha;   // (rgf: the eigenvalue in single precision as well)
 #pragma unroll 4
     for (int c = 0; c < 8; c++) {   // pairs (k, N-k), k = 1 .. N/2-1 (and the self pair k = 0: thread 0, c = 0)
@@ -344,7 +356,7 @@ __global__ void __launch_bounds__(2 * Geo<L>::TPL, 2 * Geo<L>::TPL <= 256 ? RG_M
         xl[sk] = oj;
     }
     __syncthreads();
-    fft_inv<L>(a, xl, u, u, T);
+    fft_inv<L>(a, x, (unsigned)(l * N) * ES, u, u, T);
 #pragma unroll
     for (int s = 0; s < 16; s++) {
         const int qq = slot_q(16, s), m = u + G::S1 * qq, y = qq < 8 ? 2 * m : 2 * (N - 1 - m) + 1;
@@ -420,9 +432,10 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
             for (int qq = 0; qq < 8; qq++) load_px_pair<R>(uold + row + 2 * (k + G::S1 * qq), pv[2 * qq], pv[2 * qq + 1]);
         }
     };
-    if constexpr (PREFETCH) fft_inv<L>(a, x + l * N, u, k, T, fetch_prev);
-    else { fft_inv<L>(a, x + l * N, u, k, T); fetch_prev(); }
+    if constexpr (PREFETCH) fft_inv<L>(a, x, (unsigned)(l * N) * ES, u, k, T, fetch_prev);
+    else { fft_inv<L>(a, x, (unsigned)(l * N) * ES, u, k, T); fetch_prev(); }
     double sd = 0.0, sp = 0.0;
+    float fsd = 0.0f, fsp = 0.0f;
     // 4 nx ny is a power of two on this path (both sizes are): multiplying by its reciprocal rounds exactly like the reference's division
     const R inv4N = (R)1 / fourN;
     vec2_t<R> ue[FUSE ? 8 : 1], uo[FUSE ? 8 : 1];   // FUSE: the new estimate at the thread's 8 pixel pairs
@@ -440,8 +453,13 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
                 const vec2_t<R> p0 = pv[2 * qq], p1 = pv[2 * qq + 1];
                 const vec2_t<R> d0 = mk2<R>(o0.x - p0.x, o0.y - p0.y), d1 = mk2<R>(o1.x - p1.x, o1.y - p1.y);
                 if (sizeof(R) == 4) {
+#ifdef RG_PACKED   // relaxed engine: the thread's 16 addends summed in single precision, widened once (below)
+                    fsd += lg_sqrtf((float)(d0.x * d0.x + d0.y * d0.y)) + lg_sqrtf((float)(d1.x * d1.x + d1.y * d1.y));
+                    fsp += lg_sqrtf((float)(p0.x * p0.x + p0.y * p0.y)) + lg_sqrtf((float)(p1.x * p1.x + p1.y * p1.y));
+#else
                     sd += (double)lg_sqrtf((float)(d0.x * d0.x + d0.y * d0.y)) + (double)lg_sqrtf((float)(d1.x * d1.x + d1.y * d1.y));
                     sp += (double)lg_sqrtf((float)(p0.x * p0.x + p0.y * p0.y)) + (double)lg_sqrtf((float)(p1.x * p1.x + p1.y * p1.y));
+#endif
                 } else {
                     sd += sqrt((double)(d0.x * d0.x + d0.y * d0.y)) + sqrt((double)(d1.x * d1.x + d1.y * d1.y));
                     sp += sqrt((double)(p0.x * p0.x + p0.y * p0.y)) + sqrt((double)(p1.x * p1.x + p1.y * p1.y));
@@ -449,6 +467,7 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
             }
         }
     }
+    sd += (double)fsd; sp += (double)fsp;
     if constexpr (FUSE) {
         // P1 of the next iteration (k_rg_rows_fwd) on the new estimate held in registers
         gradI += pair_off; It += pair_off; specT += pair_off;
@@ -464,7 +483,7 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
             a[15 - j] = RG_MK2((RG_S)__shfl_xor_sync(0xffffffffu, ox, 16), (RG_S)__shfl_xor_sync(0xffffffffu, oy, 16));
         }
         __syncthreads();   // every thread has left the last shared-memory phase of the inverse transform
-        fft_fwd<L>(a, x + l * N, u, k, T);
+        fft_fwd<L>(a, x, (unsigned)(l * N) * ES, u, k, T);
         constexpr int hp = (N >> 1) + 1;
         for (int e = tid; e < LPC * hp; e += LPC * G::TPL) {
             const int ll = e % LPC, kk = e / LPC, nk = (N - kk) & (N - 1);
@@ -509,3 +528,4 @@ struct Api {
 #undef RG_MINB
 #undef RG_SWZ
 #undef RG_PACKED
+#undef RG_CS
