@@ -1,7 +1,9 @@
-// engine_fluid_tma.cuh -- relaxed build, fp32 fields: k_fl_integrate as a two-stage tensor-map TMA pipeline (the structure of
-// engine_fused_tma.cuh).  The halo tiles of the estimate and of the increment of a CTA's NEXT interior tile land in shared
+// engine_fluid_tma.cuh -- relaxed build, fp32 fields: k_fl_integrate as a tensor-map TMA pipeline of OF2D_FI_NST stages (the structure of
+// engine_fused_tma.cuh).  The halo tiles of the estimate and of the increment of a CTA's NEXT TWO interior tiles land in shared
 // memory (one cp.async.bulk.tensor.3d each, SASS UTMALDG) while the current tile is integrated, so no warp waits on global
 // memory -- the plain kernel spent 10.8 stall cycles per issued instruction on its loads (profiles/r2_fluid__k_fl_integrate_float.txt).
+// After a regrid Logger's prev (the pre-reset estimate = the buffer this kernel overwrites) is read by the thread that owns the
+// points, before it waits for the stage.
 // Reference computation: OpticalFlowFluid.cpp:97-121 (explicit Euler step), Image::jacobian / min Image.cpp:189-218, 96-104,
 // Logger.cpp:32-51, regrid decision ImageRegistrationFluid.cpp:99-124.  Border tiles, partial tiles and skipped steps
 // (dt >= 65, OpticalFlowFluid.cpp:135-137) go through the same staged tiles (zero fill outside the field, one-sided differences at its edge).
@@ -13,56 +15,74 @@ namespace {
 
 constexpr int FI_W = 36, FI_H = TILE + 2;                       // halo tile in shared memory: [FI_H rows i][FI_W columns j], origin (j0 - 2, i0 - 1)
 constexpr unsigned FI_TILE = rt_round128(FI_W * FI_H * 8);      // one array (float2)
-constexpr unsigned FI_PREV = TILE * TILE * 8;                    // after a regrid: Logger's prev (the pre-reset estimate, the OTHER buffer) on the tile
-constexpr unsigned FI_STAGE = 2 * FI_TILE + FI_PREV, FI_SMEM = 2 * FI_STAGE, FI_TX = 2 * FI_W * FI_H * 8;
-struct TmaMaps5 { CUtensorMap m[5]; };                           // estimate buffers 0 / 1 (halo tile), increment, estimate buffers 0 / 1 (tile only)
+#ifndef OF2D_FI_NST
+#define OF2D_FI_NST 3    // stages of the pipeline (tiles in flight per CTA = OF2D_FI_NST - 1)
+#endif
+#ifndef OF2D_FI_MINB
+#define OF2D_FI_MINB 3   // resident CTAs per SM the register allocation aims at (3 stages of 19.7 KB each: 3 CTAs; measured at 2048^2, 40 iterations:
+                         // 2 stages / 4 CTAs 5.53 ms, 3 / 3 5.30 ms, 4 / 2 5.32 ms; 2 stages with Logger's prev staged as well: 5.44 ms)
+#endif
+constexpr int FI_NST = OF2D_FI_NST;
+constexpr unsigned FI_STAGE = 2 * FI_TILE, FI_SMEM = FI_NST * FI_STAGE, FI_TX = 2 * FI_W * FI_H * 8;
+struct TmaMaps5 { CUtensorMap m[5]; };                           // estimate buffers 0 / 1 (halo tile), increment (m[3], m[4]: tile-only maps of the estimate, unused)
 
-__global__ void __launch_bounds__(TX *TY, 4)
+__global__ void __launch_bounds__(TX *TY, OF2D_FI_MINB)
 k_rt_fl_integrate(EngK<float> K, const float2 *__restrict__ incr_all, const __grid_constant__ TmaMaps5 M) {
     pdl_enter();
     using V = float2;
     extern __shared__ __align__(128) unsigned char smem_dynamic[];
-    __shared__ uint64_t bars[2];
+    __shared__ uint64_t bars[FI_NST];
     const int pair = blockIdx.y;
     PairCtl *c = K.ctl + pair;
     const CtlHot h = load_ctl(c);
     if (!h.active) return;
     const int nx = K.nx, ny = K.ny, P = K.P;
-    const V *__restrict__ u = pick(K, B_EST_CUR, h, pair, true);
     V *un = pick(K, B_EST_NEXT, h, pair, true);
     const V *__restrict__ incr = incr_all + (size_t)pair * K.nT;
     const bool skip = h.skip != 0;
     const bool prev_other = h.prev_other != 0;
     const float dt = (float)__ldcg(&c->dt);
-    const CUtensorMap *mu = &M.m[h.sel & 1], *mr = &M.m[2], *mp = &M.m[3 + ((h.sel & 1) ^ 1)];
+    const CUtensorMap *mu = &M.m[h.sel & 1], *mr = &M.m[2];
     const int tid = threadIdx.x + threadIdx.y * TX;
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init_fence(); }
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < FI_NST; s++) mbar_init(&bars[s], 1);
+        mbar_init_fence();
+    }
     unsigned phase = 0u;
     const TileWalk T(ny, nx);
     NormAcc<float> acc;
     float mj = INFINITY;
     auto stage_u = [&](int s) { return reinterpret_cast<V *>(smem_dynamic + (unsigned)s * FI_STAGE); };
     auto stage_r = [&](int s) { return reinterpret_cast<V *>(smem_dynamic + (unsigned)s * FI_STAGE + FI_TILE); };
-    auto stage_p = [&](int s) { return reinterpret_cast<V *>(smem_dynamic + (unsigned)s * FI_STAGE + 2 * FI_TILE); };
     // every tile goes through the staged halo tiles: outside the field TMA delivers zeros, which the one-sided differences of
     // the field's edge (gradients.h:9-32) never read; a skipped step (dt >= 65) integrates with dt = 0
     const float dte = skip ? 0.0f : dt;
     auto issue = [&](int tile, int s) {
         const int j0 = T.tx(tile) * TILE, i0 = T.ty(tile) * TILE;
         proxy_fence_async();
-        mbar_expect_tx(&bars[s], FI_TX + (prev_other ? FI_PREV : 0u));
+        mbar_expect_tx(&bars[s], FI_TX);
         tma_load_3d(stage_u(s), mu, j0 - 2, i0 - 1, pair, &bars[s]);
         tma_load_3d(stage_r(s), mr, j0 - 2, i0 - 1, pair, &bars[s]);
-        if (prev_other) tma_load_3d(stage_p(s), mp, j0, i0, pair, &bars[s]);
     };
     __syncthreads();
     int tile = blockIdx.x;
-    if (tid == 0 && tile < T.ntiles) issue(tile, 0);
-    for (int k = 0; tile < T.ntiles; tile += gridDim.x, k++) {
-        const int s = k & 1;
-        const int next = tile + gridDim.x;
-        if (tid == 0 && next < T.ntiles) issue(next, s ^ 1);
+    if (tid == 0) {
+#pragma unroll
+        for (int a = 0; a < FI_NST - 1; a++) if (tile + a * (int)gridDim.x < T.ntiles) issue(tile + a * (int)gridDim.x, a);
+    }
+    for (int s = 0; tile < T.ntiles; tile += gridDim.x, s = s + 1 == FI_NST ? 0 : s + 1) {
+        // the stage the tile FI_NST - 1 ahead lands in was read by the previous iteration, which ended with a block barrier
+        const int next = tile + (FI_NST - 1) * (int)gridDim.x;
+        if (tid == 0 && next < T.ntiles) issue(next, s == 0 ? FI_NST - 1 : s - 1);
         const int j0 = T.tx(tile) * TILE, i0 = T.ty(tile) * TILE;
+        const int ib = i0 + 4 * threadIdx.y, j = j0 + threadIdx.x;
+        const size_t o0 = (size_t)ib * P + (size_t)j;
+        V pvo[4];
+        if (prev_other) {   // after a regrid Logger's prev is the pre-reset estimate: the OTHER buffer, at the points this thread is about to overwrite
+#pragma unroll
+            for (int q = 0; q < 4; q++) pvo[q] = (ib + q < nx && j < ny) ? __ldcg(un + o0 + (size_t)q * P) : make_float2(0.0f, 0.0f);
+        }
         mbar_wait(&bars[s], (phase >> s) & 1u);
         phase ^= 1u << s;
         // a thread owns 4 consecutive i of one j: the new field u + dt R on its line i-1 .. i+4 and on the j-1 / j+1 neighbours of
@@ -75,13 +95,10 @@ k_rt_fl_integrate(EngK<float> K, const float2 *__restrict__ incr_all, const __gr
         for (int r = 0; r < 6; r++) ce[r] = nw(r * FI_W);
 #pragma unroll
         for (int q = 0; q < 4; q++) { le[q] = nw((q + 1) * FI_W - 1); ri[q] = nw((q + 1) * FI_W + 1); pv[q] = su[(q + 1) * FI_W]; }
-        if (prev_other) {   // after a regrid Logger's prev is the pre-reset estimate
-            const V *sp = stage_p(s) + (4 * threadIdx.y) * TILE + threadIdx.x;
+        if (prev_other) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) pv[q] = sp[q * TILE];
+            for (int q = 0; q < 4; q++) pv[q] = pvo[q];
         }
-        const int ib = i0 + 4 * threadIdx.y, j = j0 + threadIdx.x;
-        const size_t o0 = (size_t)ib * P + (size_t)j;
         if (j0 >= 1 && j0 + TILE < ny && i0 >= 1 && i0 + TILE < nx) {   // interior tile: central differences everywhere
 #pragma unroll
             for (int q = 0; q < 4; q++) {
