@@ -559,6 +559,7 @@ struct of2d_curvature_plan {
     void *blob_xf, *blob_yf;
     int spec_f32;
     double *d_cosx, *d_cosy;
+    float *d_cosxf, *d_cosyf;   // the same rounded to single precision (column kernel of the relaxed register path)
     void *d_spec;    // spectrum between the row and the column pass (transposed on the fast paths)
     void *d_spec2;   // register path: column pass output in the natural layout
     int cols_per_cta;
@@ -615,8 +616,9 @@ int launch_reg_cols(of2d_curvature_plan *P, const CurvHook &H, int batch) {
     constexpr auto kern = A::template cols<LY>();
     { int st = of2d_ensure_dynamic_smem((const void *)kern, smem); if (st) return st; }
     ProfScope _ps(ctx, "curv_cols");
-    pdl_launch(kern, dim3(P->nx / 2, batch), NT, smem, ctx->stream, P->nx, (const C2 *)P->d_spec, (C2 *)P->d_spec2, P->d_cosx, P->d_cosy, P->tau_alpha,
-               (const C2 *)TY.q, T, H);
+    pdl_launch(kern, dim3(P->nx / 2, batch), NT, smem, ctx->stream, P->nx, (const C2 *)P->d_spec, (C2 *)P->d_spec2,
+               (const typename A::S *)(sizeof(typename A::S) == 4 ? (const void *)P->d_cosxf : (const void *)P->d_cosx),
+               (const typename A::S *)(sizeof(typename A::S) == 4 ? (const void *)P->d_cosyf : (const void *)P->d_cosy), P->tau_alpha, (const C2 *)TY.q, T, H);
     OF2D_LAUNCH_CHECK(ctx);
     return OF2D_SUCCESS;
 }
@@ -753,7 +755,7 @@ int of2d_curvature_plan_create(of2d_ctx *ctx, int nx, int ny, double alpha, doub
 void of2d_curvature_plan_destroy(of2d_curvature_plan *P) {
     if (!P) return;
     cudaStreamSynchronize(P->ctx->stream);
-    cudaFree(P->blob_x); cudaFree(P->blob_y); cudaFree(P->blob_xf); cudaFree(P->blob_yf); cudaFree(P->d_cosx); cudaFree(P->d_cosy); cudaFree(P->d_spec); cudaFree(P->d_spec2);
+    cudaFree(P->blob_x); cudaFree(P->blob_y); cudaFree(P->blob_xf); cudaFree(P->blob_yf); cudaFree(P->d_cosx); cudaFree(P->d_cosy); cudaFree(P->d_cosxf); cudaFree(P->d_cosyf); cudaFree(P->d_spec); cudaFree(P->d_spec2);
     delete P;
 }
 
@@ -781,6 +783,19 @@ int of2d_curvature_plan_set_relaxed(of2d_curvature_plan *P, int on) {
         int st = build_tables<float>(P->nx, &P->Txf, &P->blob_xf);
         if (st == OF2D_SUCCESS) st = build_tables<float>(P->ny, &P->Tyf, &P->blob_yf);
         if (st != OF2D_SUCCESS) return st;
+    }
+    if (!P->d_cosxf) {   // 2 cos(p PI / n) as the column kernel used to round it on the fly: (float) of the double table's entries
+        const double REF_PI = 3.14159265;
+        const int nx = P->nx, ny = P->ny;
+        float *h = (float *)malloc(sizeof(float) * (size_t)(nx + ny));
+        for (int p = 0; p < nx; p++) h[p] = (float)(2 * cos((unsigned)p * REF_PI / (unsigned)nx));
+        for (int q = 0; q < ny; q++) h[nx + q] = (float)(2 * cos((unsigned)q * REF_PI / (unsigned)ny));
+        cudaError_t e = cudaMalloc(&P->d_cosxf, sizeof(float) * nx);
+        if (e == cudaSuccess) e = cudaMalloc(&P->d_cosyf, sizeof(float) * ny);
+        if (e == cudaSuccess) e = cudaMemcpy(P->d_cosxf, h, sizeof(float) * nx, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(P->d_cosyf, h + nx, sizeof(float) * ny, cudaMemcpyHostToDevice);
+        free(h);
+        if (e != cudaSuccess) { of2d_set_error("curvature plan: %s", cudaGetErrorString(e)); return OF2D_ERR_CUDA; }
     }
     P->spec_f32 = 1;
     return OF2D_SUCCESS;

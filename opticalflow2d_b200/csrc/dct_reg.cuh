@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
 // (l, l+16) fill whole 32-byte sectors, so P3 reads contiguous rows and all scattered traffic of the iteration is writes.
 template <int L>
 __global__ void __launch_bounds__(2 * Geo<L>::TPL, 2 * Geo<L>::TPL <= 256 ? RG_MINB : 1) k_rg_cols(int nx, const RG_C2 *__restrict__ specT, RG_C2 *__restrict__ specN,
-                                                                                        const double *__restrict__ cosx, const double *__restrict__ cosy, double tau_alpha,
+                                                                                        const RG_S *__restrict__ cosx, const RG_S *__restrict__ cosy, double tau_alpha,
                                                                                         const RG_C2 *__restrict__ q, Tw16 T, CurvHook H) {
     pdl_enter();
     using G = Geo<L>;
@@ -511,6 +511,7 @@ __global__ void __launch_bounds__(LPC * Geo<L>::TPL, LPC * Geo<L>::TPL <= 256 ? 
 // handle for the host launch code (dct.cu), which is written once for both instantiations of this file
 struct Api {
     using C2 = RG_C2;
+    using S = RG_S;
     using Tw = Tw16;
     template <int L> using G = Geo<L>;
     template <class R, int L, int LPC> static constexpr auto rows_fwd() { return &k_rg_rows_fwd<R, L, LPC>; }
