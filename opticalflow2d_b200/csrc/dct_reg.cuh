@@ -16,7 +16,8 @@
 //   * FMA is allowed inside the FFT (the reference's fftw has no defined operation order to reproduce); the
 //     reference's own expressions (force, rhs, 1/(4N), eigenvalue) keep their order and stay unfused.
 // Shared-memory indices go through an XOR swizzle (RG_SWZ: dct_fast.cuh's swz for 16-byte elements, swz8 below for 8-byte ones),
-// conflict-free for every power-of-two stride.
+// conflict-free for every power-of-two stride; inside the super-passes the swizzled byte offset is (thread part) ^ (immediate), see RG_CS.
+// Single-precision instance (RG_PACKED): a complex addition is one packed add.rn.f32x2 / sub.rn.f32x2 (SASS FADD2).
 //
 // The file is included TWICE by dct.cu: namespace rg (RG_S = double: the reference's precision, used by the strict path, the exact
 // engine and fp64 fields) and namespace rgf (RG_S = float: the relaxed engine on fp32 fields -- transform, twiddles and the
